@@ -1,0 +1,179 @@
+/*
+ * ltx2_b200 -- C ABI of the Blackwell-native LTX-2 denoising hot path.
+ *
+ * The reference (Acelogic/LTX-2-MLX) has no FFI: its boundary is Python duck typing
+ * (SURVEY.md section 8(b)).  This header is what a binding for that boundary links against:
+ * every entry point names the reference interface it replaces (paths relative to the
+ * reference repository root).  INTEGRATION.md shows the ctypes stub the reference would add.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     stream-ordered and returns without synchronising;
+ *   - return value: 0 on success, negative errno-style code otherwise (LTX2_ERR_* below);
+ *     ltx2_last_error() returns a thread-local message for the last failure;
+ *   - no exceptions, no torch types, no hidden global state besides opaque handles;
+ *   - handles are not thread-safe (one stream, one caller), like the reference's modules.
+ *   - dtype codes: 0 = float32, 1 = bfloat16, 2 = float16.
+ */
+#ifndef LTX2_B200_H_
+#define LTX2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTX2_OK 0
+#define LTX2_ERR_INVALID (-22)
+#define LTX2_ERR_NOMEM (-12)
+#define LTX2_ERR_CUDA (-5)
+#define LTX2_ERR_NOKEY (-2)
+#define LTX2_ERR_STATE (-1)
+
+#define LTX2_DTYPE_F32 0
+#define LTX2_DTYPE_BF16 1
+#define LTX2_DTYPE_F16 2
+
+int ltx2_version(void);
+const char* ltx2_last_error(void);
+
+/* =====================================================================================
+ * DiT engine  --  replaces LTX_2_MLX/model/transformer/model.py: LTXModel (:413-881) and
+ * X0Model (:884-936), i.e. the object every pipeline calls as `transformer(video_modality
+ * [, audio_modality], perturbations=...)` (pipelines/distilled.py:229-239, one_stage.py:274).
+ * ===================================================================================== */
+
+typedef struct LtxDit LtxDit;
+
+/* LTXModel.__init__ arguments (model.py:436-461) that shape the network. */
+typedef struct LtxDitConfig {
+  int32_t num_attention_heads;      /* 32 */
+  int32_t attention_head_dim;       /* 128 (64 or 128 supported) */
+  int32_t in_channels;              /* 128 */
+  int32_t out_channels;             /* 128 */
+  int32_t num_layers;               /* 48 */
+  int32_t cross_attention_dim;      /* 4096 */
+  int32_t caption_channels;         /* 3840; 0 = no caption projection (V2) */
+  int32_t cross_attention_adaln;    /* V2: 9-row adaLN + prompt KV modulation */
+  int32_t apply_gated_attention;    /* V2: per-head 2*sigmoid gate */
+  int32_t audio_enabled;            /* LTXModelType.AudioVideo */
+  int32_t audio_heads;              /* 32 (model.py:428) */
+  int32_t audio_head_dim;           /* 64 (model.py:429) */
+  int32_t audio_in_channels;        /* 128 */
+  int32_t audio_out_channels;       /* 128 */
+  float norm_eps;                   /* 1e-6 */
+  float positional_embedding_theta; /* 10000 */
+  float max_pos[3];                 /* {20, 2048, 2048} */
+  float audio_max_pos;              /* 20 (model.py:434) */
+  float timestep_scale_multiplier;  /* 1000 */
+  float av_ca_timestep_scale_multiplier; /* 1 (model.py:452); the CLI passes 1000 */
+} LtxDitConfig;
+
+/* One `Modality` (model.py:59-69), flattened.  latent/context dtype per *_dtype. */
+typedef struct LtxModalityView {
+  const void* latent;        /* [B, N, C_in] */
+  int32_t latent_dtype;
+  const void* context;       /* [B, S, C_ctx] */
+  int32_t context_dtype;
+  const float* timesteps;    /* [B * n_t] fp32: n_t == 1 (Modality.timesteps (B,)) or n_t == N ((B,N) / (B,N,1)) */
+  const float* sigma;        /* [B] fp32 or NULL (Modality.sigma) */
+  const float* positions;    /* [B, n_dims, N, 2] fp32 [start,end) bounds */
+  int32_t batch;
+  int32_t tokens;            /* N */
+  int32_t context_tokens;    /* S */
+  int32_t n_t;               /* 1 or N */
+  int32_t n_dims;            /* 3 video, 1 audio */
+} LtxModalityView;
+
+int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out);
+void ltx2_dit_destroy(LtxDit* dit);
+
+/* Replaces load_transformer_weights -> model.update (loader/weight_converter.py:318-446).
+ * `key` is the reference's MLX-side name, i.e. the checkpoint key minus "model.diffusion_model."
+ * after the renames of weight_converter.py:300-313 (e.g. "transformer_blocks.0.attn1.to_out.weight").
+ * The tensor is copied (and converted to the engine's storage type) before the call returns
+ * control of `data` to the caller on `stream`. */
+int ltx2_dit_set_weight(LtxDit* dit, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                        int32_t ndim, void* stream);
+/* number of weight tensors still missing; forward refuses to run until it is 0 */
+int ltx2_dit_missing_weights(LtxDit* dit, char* names_out, int64_t names_cap);
+
+/* LTXModel.__call__ (model.py:776-881): velocity [B,N,C_out] fp32 (and audio velocity).
+ * skip_* : per-block bit masks of the STG perturbations that apply to the WHOLE batch
+ * (BatchedPerturbationConfig.all_in_batch, transformer.py:486-501); bit i = block i; NULL = none.
+ * When x0 != 0 the outputs are denoised samples latent - t*velocity (X0Model, model.py:895-936). */
+typedef struct LtxDitSkip {
+  uint64_t video_self_attn;
+  uint64_t audio_self_attn;
+  uint64_t a2v_cross_attn;
+  uint64_t v2a_cross_attn;
+} LtxDitSkip;
+
+int ltx2_dit_forward(LtxDit* dit, const LtxModalityView* video, const LtxModalityView* audio /* nullable */,
+                     const LtxDitSkip* skip /* nullable */, int32_t x0, float* out_video, float* out_audio /* nullable */,
+                     void* stream);
+
+/* OneStagePipeline pokes block._cross_attn_scale (one_stage.py:207-222; transformer.py:526-528). */
+int ltx2_dit_set_cross_attn_scale(LtxDit* dit, int32_t block, float scale /* NaN = unset */);
+
+/* Context-parallel (ring attention) setup, SURVEY.md section 8(e).  rank/world describe this
+ * process' slice of the token axis; the K/V exchange itself is driven by the host layer
+ * (torch.distributed NCCL P2P) through ltx2_dit_forward_cp hooks -- see DESIGN.md. */
+
+/* =====================================================================================
+ * Per-op entry points (unit parity against the oracle)
+ * ===================================================================================== */
+
+/* nn.Linear + fused epilogue (attention.py:190-201, feed_forward.py:23-49).
+ * C[M,N] = A[M,K] W[N,K]^T; mode 0: bf16 out = acc+bias; 1: bf16 gelu_tanh(acc+bias);
+ * 2: f32 out = acc+bias; 3: f32 out += alpha * gate[row_cls[row], col] * (acc+bias). */
+int ltx2_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                   int32_t mode, const float* bias, void* out, int64_t ldo, const float* gate, int64_t gate_stride,
+                   const int32_t* row_cls, float alpha, void* stream);
+
+/* mx.fast.scaled_dot_product_attention + head merge + V2 gate (attention.py:12-34, 243-250).
+ * q [B,H,Tq,Dh], k [B,H,Tk,Dh], vt [B,H,Dh,Tkp] (V transposed), out [B,Tq,H*Dh]; all bf16. */
+int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
+                   int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
+                   void* stream);
+
+/* _compiled_adaln_forward / rms_norm / LayerNorm+modulate (transformer.py:16-31, model.py:744-758).
+ * norm_kind 0 none, 1 RMS, 2 LayerNorm(no affine). */
+int ltx2_norm_modulate(const void* x, int32_t x_dtype, int64_t ldx, void* out_bf16, int64_t ldo, int32_t M, int32_t D,
+                       int32_t norm_kind, float eps, const float* mod, int64_t mod_stride, int64_t shift_off,
+                       int64_t scale_off, const int32_t* row_cls, void* stream);
+
+/* q_norm/k_norm + apply_split_rotary_emb + head split (attention.py:231-237, rope.py:92-144). */
+int ltx2_headnorm_rope(const void* in_bf16, int64_t ld, const float* weight, const float* cos, const float* sin,
+                       void* out_bf16, int32_t B, int32_t T, int32_t H, int32_t Dh, float eps, void* stream);
+int ltx2_v_transpose(const void* v_bf16, int64_t ld, void* vt_bf16, int32_t B, int32_t T, int32_t Tp, int32_t H,
+                     int32_t Dh, void* stream);
+
+/* precompute_freqs_cis(rope_type=SPLIT, use_middle_indices_grid=True) (rope.py:365-418).
+ * cos/sin out: [B, T, dim/2] fp32 token-major (== reference (B,H,T,dim/2/H) transposed back). */
+int ltx2_rope_tables(const float* positions, int32_t B, int32_t n_dims, int32_t T, int32_t dim,
+                     const float* max_pos_host, float theta, float* cos, float* sin, void* stream);
+
+/* AdaLayerNormSingle pieces (timestep_embedding.py:10-60, 166-202). */
+int ltx2_timestep_sinusoid(const float* t, int32_t R, float multiplier, float* out256, void* stream);
+int ltx2_small_linear(const float* x, int32_t R, int32_t K, const void* W_bf16, const float* bias, float* y, int32_t N,
+                      int32_t act_in, void* stream);
+
+/* X0Model.denoise (model.py:912-918) */
+int ltx2_x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int32_t M,
+                          int32_t C, void* stream);
+
+/* The reference's own three kernels (kernels/fused_ops.py:50, 95, 183). */
+int ltx2_silu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream);
+int ltx2_gelu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream);
+int ltx2_interleaved_rope(const void* x, const void* cos, const void* sin, void* out, int64_t n, int32_t dtype,
+                          void* stream);
+
+int ltx2_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTX2_B200_H_ */

@@ -1,0 +1,345 @@
+// Flash-style attention on tcgen05 tensor cores:  O = softmax(Q K^T / sqrt(d)) V, non-causal, no mask.
+//
+// Reference op replaced: mx.fast.scaled_dot_product_attention as called from
+// _compiled_attention_core_no_mask (attention.py:12-34), plus the head merge
+// (B,H,T,D)->(B,T,H*D) (:34) and the V2 per-head gate 2*sigmoid(logits) (:243-250).
+//
+// One CTA per (128-query tile, batch*head).  6 warps:
+//   warp 0   TMA producer: Q once, then K_j / V^T_j tiles (128 keys) through 2-stage rings
+//   warp 1   MMA issuer:   S_j = Q K_j^T  (tcgen05, fp32 in TMEM, double-buffered) and
+//                          O_j = P_j V_j  (fresh accumulator per block, double-buffered)
+//   warps 2-5 softmax:     one thread per query row; two TMEM passes over S_j (row max, then
+//                          exp2/sum), P_j written as bf16 into a 128B-swizzled smem tile that is the
+//                          A operand of the second MMA; running output kept in registers and
+//                          rescaled by exp2(m_old - m_new) when O_{j-1} is folded in.
+// K is consumed [keys, d] (K-major for S), V is consumed TRANSPOSED [d, keys] (K-major for P V), so
+// both MMAs use the same K-major/128B-swizzle descriptor form as the GEMM.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ltx2 {
+
+namespace {
+
+constexpr int kAttnThreads = 192;
+constexpr int BQ = 128;    // queries per CTA
+constexpr int BKV = 128;   // keys per block
+
+template <int DH>
+struct AttnCfg {
+  static constexpr int kQBytes = BQ * DH * 2;
+  static constexpr int kKBytes = BKV * DH * 2;
+  static constexpr int kVBytes = DH * BKV * 2;
+  static constexpr int kPBytes = BQ * BKV * 2;
+  static constexpr int kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kOCol = 256;  // O accumulators start after the two S buffers
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
+                 float scale_log2, float scale, const float* __restrict__ gate_logits, float* __restrict__ lse_out) {
+  using Cfg = AttnCfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kQBytes;
+  uint8_t* sV = sK + 2 * Cfg::kKBytes;
+  uint8_t* sP = sV + 2 * Cfg::kVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2
+  uint64_t* s_empty = bars + 11;    // 2
+  uint64_t* o_full = bars + 13;     // 2
+  uint64_t* o_empty = bars + 15;    // 2
+  uint64_t* p_full = bars + 17;     // 1
+  uint64_t* p_empty = bars + 18;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int bh = blockIdx.y;
+  const int nkv = (Tk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 128);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+      for (int i = 0; i < DH / 64; ++i) tma_load_3d(sQ + i * (BQ * 128), &tmap_q, q_full, i * 64, q0, bh);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::kKBytes);
+#pragma unroll
+        for (int i = 0; i < DH / 64; ++i)
+          tma_load_3d(sK + st * Cfg::kKBytes + i * (BKV * 128), &tmap_k, &k_full[st], i * 64, j * BKV, bh);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], Cfg::kVBytes);
+#pragma unroll
+        for (int i = 0; i < BKV / 64; ++i)
+          tma_load_3d(sV + st * Cfg::kVBytes + i * (DH * 128), &tmap_v, &v_full[st], j * BKV + i * 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH);
+      auto issue_s = [&](int j) {
+        const int b = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[b], ph);
+        mbar_wait(&s_empty[b], ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(sQ + (ks / 4) * (BQ * 128))) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(sK + b * Cfg::kKBytes + (ks / 4) * (BKV * 128))) + 2 * (ks % 4);
+          umma_bf16_ss(tmem_base + b * BKV, ad, bd, idesc_s, ks != 0);
+        }
+        umma_commit(&s_full[b]);
+        umma_commit(&k_empty[b]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_s(j + 1);
+        const int b = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[b], ph);
+        mbar_wait(&o_empty[b], ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(sP + (ks / 4) * (BQ * 128))) + 2 * (ks % 4);
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(sV + b * Cfg::kVBytes + (ks / 4) * (DH * 128))) + 2 * (ks % 4);
+          umma_bf16_ss(tmem_base + Cfg::kOCol + b * DH, ad, bd, idesc_o, ks != 0);
+        }
+        umma_commit(&o_full[b]);
+        umma_commit(&v_empty[b]);
+        umma_commit(p_empty);
+      }
+    }
+  } else {
+    // ===================== softmax + output (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // query row inside the tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    float acc[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int kv_valid = Tk - j * BKV;                // >= 1
+      mbar_wait(&s_full[b], ph);
+      tc_fence_after();
+      // ---- pass 1: row max ----
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + b * BKV + c, v);
+        tmem_ld_wait();
+        if (kv_valid >= c + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float alpha = exp2f((m - mx) * scale_log2);   // m = -inf on the first block -> 0
+      const float mb = mx * scale_log2;
+      // ---- pass 2: p = exp2(s*c - m*c), row sum, P -> smem (bf16, 128B swizzle) ----
+      mbar_wait(p_empty, (j & 1) ^ 1);                   // P V_{j-1} has finished reading sP
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + b * BKV + c, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(fmaf(__uint_as_float(v[i]), scale_log2, -mb));
+          if (c + i >= kv_valid) e = 0.f;
+          p[i] = e;
+          rowsum += e;
+        }
+        uint8_t* prow = sP + (c / 64) * (BQ * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]);
+          w.y = pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]);
+          w.z = pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]);
+          w.w = pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]);
+          const int chunk = ((c % 64) / 8 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = w;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      l = l * alpha + rowsum;
+      m = mx;
+      // ---- fold in O_{j-1} (scaled to the previous max) and rescale to the new max ----
+      if (j > 0) {
+        const int pb = (j - 1) & 1;
+        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DH; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_lane + Cfg::kOCol + pb * DH + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c + i] = (acc[c + i] + __uint_as_float(v[i])) * alpha;
+        }
+        tc_fence_before();
+        mbar_arrive(&o_empty[pb]);
+      }
+    }
+    // ---- last block's O, normalise, gate, store ----
+    {
+      const int pb = (nkv - 1) & 1;
+      mbar_wait(&o_full[pb], ((nkv - 1) >> 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int row = q0 + r;
+      const int b_idx = bh / H, h_idx = bh % H;
+      float g = 1.f;
+      if (gate_logits != nullptr && row < Tq) {
+        const float z = gate_logits[(static_cast<int64_t>(b_idx) * Tq + row) * H + h_idx];
+        g = 2.0f / (1.0f + __expf(-z));
+      }
+      const float f = inv_l * g;
+      __nv_bfloat16* o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DH) + h_idx * DH;
+#pragma unroll
+      for (int c = 0; c < DH; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + Cfg::kOCol + pb * DH + c, v);
+        tmem_ld_wait();
+        if (row < Tq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2((acc[c + i + 0] + __uint_as_float(v[i + 0])) * f, (acc[c + i + 1] + __uint_as_float(v[i + 1])) * f);
+            w.y = pack_bf16x2((acc[c + i + 2] + __uint_as_float(v[i + 2])) * f, (acc[c + i + 3] + __uint_as_float(v[i + 3])) * f);
+            w.z = pack_bf16x2((acc[c + i + 4] + __uint_as_float(v[i + 4])) * f, (acc[c + i + 5] + __uint_as_float(v[i + 5])) * f);
+            w.w = pack_bf16x2((acc[c + i + 6] + __uint_as_float(v[i + 6])) * f, (acc[c + i + 7] + __uint_as_float(v[i + 7])) * f);
+            *reinterpret_cast<uint4*>(o + c + i) = w;
+          }
+        }
+      }
+      if (lse_out != nullptr && row < Tq)
+        lse_out[static_cast<int64_t>(bh) * Tq + row] = m * scale + logf(l);
+      tc_fence_before();
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int DH>
+int launch_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
+                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream) {
+  using Cfg = AttnCfg<DH>;
+  static bool configured = false;
+  if (!configured) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    configured = true;
+  }
+  const uint64_t BH = static_cast<uint64_t>(B) * H;
+  CUtensorMap mq, mk, mv;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(Tq), BH};
+    uint64_t str[2] = {static_cast<uint64_t>(DH) * 2, static_cast<uint64_t>(Tq) * DH * 2};
+    uint32_t box[3] = {64, BQ, 1};
+    LTX2_PROPAGATE(make_tensor_map_bf16(&mq, q, 3, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(Tk), BH};
+    uint64_t str[2] = {static_cast<uint64_t>(DH) * 2, static_cast<uint64_t>(Tk) * DH * 2};
+    uint32_t box[3] = {64, BKV, 1};
+    LTX2_PROPAGATE(make_tensor_map_bf16(&mk, k, 3, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(Tk), static_cast<uint64_t>(DH), BH};
+    uint64_t str[2] = {static_cast<uint64_t>(Tkp) * 2, static_cast<uint64_t>(Tkp) * DH * 2};
+    uint32_t box[3] = {64, static_cast<uint32_t>(DH), 1};
+    LTX2_PROPAGATE(make_tensor_map_bf16(&mv, vt, 3, dims, str, box));
+  }
+  dim3 grid((Tq + BQ - 1) / BQ, static_cast<unsigned>(BH));
+  const float kLog2e = 1.4426950408889634f;
+  attention_kernel<DH><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
+      mq, mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk, scale * kLog2e, scale, gate_logits, lse_out);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  return LTX2_OK;
+}
+
+}  // namespace
+
+int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
+                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream) {
+  LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
+  LTX2_REQUIRE(Tkp >= Tk && Tkp % 8 == 0, "attention: V^T pitch %d must be >= Tk=%d and a multiple of 8", Tkp, Tk);
+  LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
+  switch (Dh) {
+    case 128: return launch_attention<128>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, stream);
+    case 64: return launch_attention<64>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, stream);
+    default:
+      set_error("attention: head_dim %d unsupported (64 or 128)", Dh);
+      return LTX2_ERR_INVALID;
+  }
+}
+
+}  // namespace ltx2

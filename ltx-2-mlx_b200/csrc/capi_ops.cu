@@ -1,0 +1,122 @@
+// extern "C" shims of the per-op entry points declared in include/ltx2_b200.h.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/ltx2_b200.h"
+
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+using namespace ltx2;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int ltx2_version(void) { return 100; }
+const char* ltx2_last_error(void) { return last_error(); }
+
+int ltx2_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                   int32_t mode, const float* bias, void* out, int64_t ldo, const float* gate, int64_t gate_stride,
+                   const int32_t* row_cls, float alpha, void* stream) {
+  LTX2_REQUIRE(mode >= 0 && mode <= 3, "gemm: bad epilogue mode %d", mode);
+  GemmEpilogue ep;
+  ep.mode = mode;
+  ep.bias = bias;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.gate = gate;
+  ep.gate_stride = gate_stride;
+  ep.row_cls = row_cls;
+  ep.alpha = alpha;
+  return gemm_bf16(A, lda, W, ldw, M, N, K, ep, S(stream));
+}
+
+int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
+                   int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
+                   void* stream) {
+  return attention_bf16(q, k, vt, out, B, H, Tq, Tk, Tkp, Dh, scale, gate_logits, lse_out, S(stream));
+}
+
+int ltx2_norm_modulate(const void* x, int32_t x_dtype, int64_t ldx, void* out, int64_t ldo, int32_t M, int32_t D,
+                       int32_t norm_kind, float eps, const float* mod, int64_t mod_stride, int64_t shift_off,
+                       int64_t scale_off, const int32_t* row_cls, void* stream) {
+  LTX2_REQUIRE(x_dtype == LTX2_F32 || x_dtype == LTX2_BF16, "norm_modulate: x must be f32 or bf16");
+  return norm_modulate(x, x_dtype == LTX2_BF16, ldx, out, ldo, M, D, norm_kind, eps, mod, mod_stride, shift_off,
+                       scale_off, row_cls, S(stream));
+}
+
+int ltx2_headnorm_rope(const void* in, int64_t ld, const float* weight, const float* cos, const float* sin, void* out,
+                       int32_t B, int32_t T, int32_t H, int32_t Dh, float eps, void* stream) {
+  return headnorm_rope(in, ld, weight, cos, sin, out, B, T, H, Dh, eps, S(stream));
+}
+
+int ltx2_v_transpose(const void* v, int64_t ld, void* vt, int32_t B, int32_t T, int32_t Tp, int32_t H, int32_t Dh,
+                     void* stream) {
+  return v_transpose(v, ld, vt, B, T, Tp, H, Dh, S(stream));
+}
+
+int ltx2_rope_tables(const float* positions, int32_t B, int32_t n_dims, int32_t T, int32_t dim,
+                     const float* max_pos_host, float theta, float* cos, float* sin, void* stream) {
+  LTX2_REQUIRE(n_dims >= 1 && n_dims <= 3 && dim % (2 * n_dims) >= 0, "rope_tables: bad n_dims");
+  typedef std::tuple<float, int, int> Key;
+  static std::map<Key, float*> cache;
+  static std::mutex mu;
+  const int n = dim / (2 * n_dims);
+  float* dev = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    Key key(theta, n_dims, dim);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      std::vector<float> g(n);
+      for (int i = 0; i < n; ++i) {
+        const float lin = n > 1 ? static_cast<float>(static_cast<double>(i) / (n - 1)) : 0.f;
+        g[i] = static_cast<float>(pow(static_cast<double>(theta), static_cast<double>(lin)) * (M_PI / 2.0));
+      }
+      LTX2_CUDA_CHECK(cudaMalloc(&dev, n * 4 + 16));
+      LTX2_CUDA_CHECK(cudaMemcpy(dev, g.data(), n * 4, cudaMemcpyHostToDevice));
+      cache[key] = dev;
+    } else {
+      dev = it->second;
+    }
+  }
+  return rope_tables_dev(positions, B, n_dims, n_dims, T, dim, max_pos_host, dev, n, cos, sin, S(stream));
+}
+
+int ltx2_timestep_sinusoid(const float* t, int32_t R, float multiplier, float* out256, void* stream) {
+  return timestep_sinusoid(t, R, multiplier, out256, S(stream));
+}
+
+int ltx2_small_linear(const float* x, int32_t R, int32_t K, const void* W, const float* bias, float* y, int32_t N,
+                      int32_t act_in, void* stream) {
+  return small_linear(x, R, K, W, bias, y, N, act_in, S(stream));
+}
+
+int ltx2_x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int32_t M,
+                          int32_t C, void* stream) {
+  return x0_from_velocity(latent, velocity, t_row, x0, M, C, S(stream));
+}
+
+int ltx2_silu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream) {
+  return silu_mul(a, b, out, n, dtype, S(stream));
+}
+int ltx2_gelu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream) {
+  return gelu_mul(a, b, out, n, dtype, S(stream));
+}
+int ltx2_interleaved_rope(const void* x, const void* cos, const void* sin, void* out, int64_t n, int32_t dtype,
+                          void* stream) {
+  return interleaved_rope(x, cos, sin, out, n, dtype, S(stream));
+}
+
+int ltx2_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  if (dst_dtype == LTX2_BF16) return cast_to_bf16(src, src_dtype, dst, n, S(stream));
+  if (dst_dtype == LTX2_F32) return cast_to_f32(src, src_dtype, reinterpret_cast<float*>(dst), n, S(stream));
+  set_error("cast: destination dtype %d unsupported", dst_dtype);
+  return LTX2_ERR_INVALID;
+}
+
+}  // extern "C"

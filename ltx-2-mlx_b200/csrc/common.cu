@@ -1,0 +1,110 @@
+// Host-side helpers: last-error string, tensor-map creation through the driver entry
+// point (no libcuda link dependency, so the library loads on a GPU-less host), a small
+// tensor-map cache and device queries.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace ltx2 {
+
+static thread_local char g_err[512] = "";
+
+const char* last_error() { return g_err; }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return LTX2_ERR_CUDA;
+  }
+  cuuint64_t gdims[5], gstr[4];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=[%llu,%llu] stride=%llu box=[%u,%u]", (int)r,
+              base, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0);
+    return LTX2_ERR_INVALID;
+  }
+  return LTX2_OK;
+}
+
+int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
+  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t> Key;
+  static std::map<Key, CUtensorMap*> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key(base, rows, cols, ld, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return LTX2_OK;
+  }
+  if (cache.size() > 16384) {  // unbounded growth guard for callers that stream fresh buffers
+    for (auto& kv : cache) delete kv.second;
+    cache.clear();
+  }
+  CUtensorMap* m = new CUtensorMap;
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld * 2};
+  uint32_t box[2] = {64, box_rows};
+  int s = make_tensor_map_bf16(m, base, 2, dims, strides, box);
+  if (s != LTX2_OK) {
+    delete m;
+    return s;
+  }
+  cache[key] = m;
+  *out = m;
+  return LTX2_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace ltx2

@@ -1,0 +1,944 @@
+// DiT engine: owns the packed weights and the activation workspace, and issues the kernel
+// sequence of one LTXModel forward on a CUDA stream.
+//
+// Reference path replaced (LTX_2_MLX/model/transformer/):
+//   model.py:231-281,368-410   TransformerArgsPreprocessor / MultiModal...prepare
+//   transformer.py:457-648     BasicAVTransformerBlock.__call__ (the 48-iteration hot loop, model.py:720-728)
+//   model.py:744-774           output heads,   model.py:895-936  X0Model
+//
+// HBM layout
+//   weights   one arena; per Linear a bf16 [out,in] matrix (nn.Linear layout == K-major B operand) and an
+//             fp32 bias; q/k/v of a self-attention are adjacent so one GEMM (N = 3*inner) produces all three;
+//             k/v of a cross-attention are adjacent (N = 2*inner).  Norm weights and adaLN tables are fp32.
+//   residual  x: fp32 [B*N, D] (updated in place by the GEMM epilogues that end each sub-layer)
+//   GEMM inputs  bf16 row-major (written by the norm kernels / previous epilogues)
+//   attention operands  Q,K: bf16 [B,H,T,Dh];  V: bf16 [B,H,Dh,T] (transposed so P*V is K-major)
+//   modulation  fp32 [layer, class, row, D]: adaLN table row + timestep-embedding row, one "class" per
+//             distinct (batch, sigma); rows map to classes through an int32 array (per-token timesteps
+//             of image conditioning become 2 classes instead of a (B,N,6,D) tensor).
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/ltx2_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace ltx2 {
+
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+struct Slot {
+  void* dst = nullptr;
+  int storage = LTX2_F32;
+  int64_t rows = 0, cols = 0;     // cols == 0 -> 1-D of `rows`
+  bool loaded = false;
+};
+
+// Bump allocator.  A dry pass (base == 0) only measures; addresses are formed with integer arithmetic so the
+// dry and the real pass run exactly the same code.
+struct Arena {
+  uintptr_t base = 0;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    return reinterpret_cast<void*>(base + a);
+  }
+};
+template <typename T>
+inline T* offset_ptr(T* p, size_t elems) {
+  return reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + elems * sizeof(T));
+}
+
+struct LinearW {
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int out = 0, in = 0;
+};
+
+struct AttnW {
+  LinearW q, kv, o, gate;      // kv: [2*inner, ctx_dim]; for self-attention q.w is followed by kv.w (fused QKV)
+  float* qnorm = nullptr;
+  float* knorm = nullptr;
+  bool fused_qkv = false;
+  int heads = 0, dh = 0, inner = 0;
+};
+
+struct AdaLNW {                // AdaLayerNormSingle
+  LinearW l1, l2, lin;
+  int n_emb = 0;
+};
+
+struct StreamW {               // per-modality weights outside the blocks
+  LinearW patchify, cap1, cap2, proj_out;
+  AdaLNW adaln, prompt_adaln;
+  float* head_table = nullptr;   // [2, dim]
+  bool has_caption = false;
+};
+
+struct BlockStreamW {          // per-block, per-modality
+  AttnW attn1, attn2;
+  LinearW ff1, ff2;
+  float* table = nullptr;        // [n_ada, dim]
+  float* prompt_table = nullptr; // [2, dim]
+};
+
+struct BlockW {
+  BlockStreamW v, a;
+  AttnW a2v, v2a;
+  float* table_ca_audio = nullptr;  // [5, Da]
+  float* table_ca_video = nullptr;  // [5, D]
+};
+
+// activation workspace of one modality
+struct StreamBuf {
+  int B = 0, N = 0, S = 0, dim = 0, heads = 0, dh = 0, n_cls = 0;
+  float* x = nullptr;           // [M, dim] fp32 residual
+  bf16* xn = nullptr;           // [M, dim]
+  bf16* qkv = nullptr;          // [M, 3*dim]
+  bf16* attn = nullptr;         // [M, dim]
+  bf16* hidden = nullptr;       // [M, 4*dim]
+  bf16* qh = nullptr;           // [B,H,N,Dh]
+  bf16* kh = nullptr;           // [B,H,max(N,S,Nother),Dh]
+  bf16* vt = nullptr;           // [B,H,Dh,Tp]
+  bf16* lat = nullptr;          // [M, C_in] bf16
+  bf16* ctx_in = nullptr;       // [B*S, C_ctx]
+  bf16* ctx_mid = nullptr;      // [B*S, dim]
+  bf16* ctx = nullptr;          // [B*S, dim]
+  bf16* ctx_mod = nullptr;      // [B*S, dim] (V2)
+  bf16* kv = nullptr;           // [max(B*S, M_other), 2*dim_kv]
+  float* gate_logits = nullptr; // [M, H]
+  float* cos = nullptr;         // [B,N,dim/2]
+  float* sin = nullptr;
+  float* ccos = nullptr;        // cross-modal 1-D rope [B,N,Da/2]
+  float* csin = nullptr;
+  float* mod = nullptr;         // [L, n_cls, n_ada, dim]
+  float* prompt_mod = nullptr;  // [L, B, 2, dim]
+  float* ca_mod = nullptr;      // [L, B, 5, dim]
+  float* head_mod = nullptr;    // [n_cls, 2, dim]
+  float* emb_t = nullptr;       // [n_cls, dim] embedded timestep
+  int* row_cls = nullptr;       // [M]
+  int* row_batch = nullptr;     // [max(M, B*S)] = row / tokens
+  int* ctx_batch = nullptr;     // [B*S]
+  float* t_cls = nullptr;       // [n_cls] sigma per class
+  float* t_row = nullptr;       // [M] sigma per row
+  float* vel = nullptr;         // [M, C_out]
+};
+
+}  // namespace
+
+}  // namespace ltx2
+
+using namespace ltx2;
+
+struct LtxDit {
+  LtxDitConfig cfg;
+  int D = 0, Da = 0, n_ada = 6;
+  std::unordered_map<std::string, Slot> slots;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  StreamW vw, aw;
+  AdaLNW av_v_ss, av_v_gate, av_a_ss, av_a_gate;
+  std::vector<BlockW> blocks;
+  std::vector<float> cross_attn_scale;
+  float* table_arena_v = nullptr;   // [L, n_ada, D]   (contiguous per-layer tables -> one build_modulation)
+  float* table_arena_a = nullptr;
+  float* ptable_arena_v = nullptr;  // [L, 2, D]
+  float* ptable_arena_a = nullptr;
+  float* catable_arena_v = nullptr; // [L, 5, D]
+  float* catable_arena_a = nullptr; // [L, 5, Da]
+  // frequency grids (device)
+  float* fg_video = nullptr; int nf_video = 0;       // dim D, 3 axes
+  float* fg_audio = nullptr; int nf_audio = 0;       // dim Da, 1 axis
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  StreamBuf vb, ab;
+  float* scratch = nullptr;         // small fp32 scratch for timestep MLPs
+  std::vector<float> h_ts;          // host staging for per-token timestep dedupe
+};
+
+namespace ltx2 {
+namespace {
+
+// ------------------------------------------------------------------------------
+// weight layout
+// ------------------------------------------------------------------------------
+struct Layout {
+  LtxDit* e;
+  Arena* ar;
+  bool dry;
+
+  void slot(const std::string& key, void* dst, int storage, int64_t rows, int64_t cols) {
+    if (dry) return;
+    Slot s;
+    s.dst = dst; s.storage = storage; s.rows = rows; s.cols = cols;
+    e->slots[key] = s;
+  }
+  float* f32(const std::string& key, int64_t rows, int64_t cols) {
+    float* p = reinterpret_cast<float*>(ar->take(sizeof(float) * rows * (cols ? cols : 1)));
+    slot(key, p, LTX2_F32, rows, cols);
+    return p;
+  }
+  // registers an fp32 tensor inside a pre-taken region
+  float* f32_at(const std::string& key, float* p, int64_t rows, int64_t cols) {
+    slot(key, p, LTX2_F32, rows, cols);
+    return p;
+  }
+  LinearW linear_at(const std::string& prefix, int out, int in, bf16* w_at, float* b_at) {
+    LinearW L;
+    L.out = out; L.in = in;
+    L.w = w_at;
+    L.b = b_at;
+    slot(prefix + ".weight", L.w, LTX2_BF16, out, in);
+    slot(prefix + ".bias", L.b, LTX2_F32, out, 0);
+    return L;
+  }
+  LinearW linear(const std::string& prefix, int out, int in) {
+    bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(out) * in));
+    float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * out));
+    return linear_at(prefix, out, in, w, b);
+  }
+  AdaLNW adaln(const std::string& prefix, int dim, int n_emb) {
+    AdaLNW a;
+    a.n_emb = n_emb;
+    a.l1 = linear(prefix + ".emb.timestep_embedder.linear_1", dim, 256);
+    a.l2 = linear(prefix + ".emb.timestep_embedder.linear_2", dim, dim);
+    a.lin = linear(prefix + ".linear", n_emb * dim, dim);
+    return a;
+  }
+  AttnW attention(const std::string& prefix, int query_dim, int ctx_dim, int heads, int dh, bool self_attn,
+                  bool gated) {
+    AttnW a;
+    a.heads = heads; a.dh = dh; a.inner = heads * dh;
+    const int inner = a.inner;
+    a.fused_qkv = self_attn;
+    if (self_attn) {
+      bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(3) * inner * query_dim));
+      float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * 3 * inner));
+      a.q = linear_at(prefix + ".to_q", inner, query_dim, w, b);
+      a.kv = linear_at(prefix + ".to_k", inner, ctx_dim, offset_ptr(w, size_t(inner) * query_dim), offset_ptr(b, inner));
+      linear_at(prefix + ".to_v", inner, ctx_dim, offset_ptr(w, size_t(2) * inner * query_dim), offset_ptr(b, 2 * inner));
+    } else {
+      a.q = linear(prefix + ".to_q", inner, query_dim);
+      bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(2) * inner * ctx_dim));
+      float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * 2 * inner));
+      a.kv = linear_at(prefix + ".to_k", inner, ctx_dim, w, b);
+      linear_at(prefix + ".to_v", inner, ctx_dim, offset_ptr(w, size_t(inner) * ctx_dim), offset_ptr(b, inner));
+    }
+    a.kv.out = 2 * inner;
+    a.o = linear(prefix + ".to_out", query_dim, inner);
+    a.qnorm = f32(prefix + ".q_norm.weight", inner, 0);
+    a.knorm = f32(prefix + ".k_norm.weight", inner, 0);
+    if (gated) a.gate = linear(prefix + ".to_gate_logits", heads, query_dim);
+    return a;
+  }
+};
+
+void build_layout(LtxDit* e, Arena* ar, bool dry) {
+  Layout L{e, ar, dry};
+  const LtxDitConfig& c = e->cfg;
+  const int D = e->D, Da = e->Da, n = e->n_ada, nl = c.num_layers;
+  const bool v2 = c.cross_attention_adaln != 0, gated = c.apply_gated_attention != 0, audio = c.audio_enabled != 0;
+
+  auto stream_w = [&](StreamW& s, const std::string& p, int dim, int in_ch, int out_ch) {
+    s.patchify = L.linear(p + "patchify_proj", dim, in_ch);
+    s.adaln = L.adaln(p + "adaln_single", dim, n);
+    if (v2) s.prompt_adaln = L.adaln(p + "prompt_adaln_single", dim, 2);
+    s.has_caption = c.caption_channels > 0;
+    if (s.has_caption) {
+      s.cap1 = L.linear(p + "caption_projection.linear_1", dim, c.caption_channels);
+      s.cap2 = L.linear(p + "caption_projection.linear_2", dim, dim);
+    }
+    s.head_table = L.f32(p + "scale_shift_table", 2, dim);
+    s.proj_out = L.linear(p + "proj_out", out_ch, dim);
+  };
+  stream_w(e->vw, "", D, c.in_channels, c.out_channels);
+  if (audio) {
+    stream_w(e->aw, "audio_", Da, c.audio_in_channels, c.audio_out_channels);
+    e->av_v_ss = L.adaln("av_ca_video_scale_shift_adaln_single", D, 4);
+    e->av_v_gate = L.adaln("av_ca_a2v_gate_adaln_single", D, 1);
+    e->av_a_ss = L.adaln("av_ca_audio_scale_shift_adaln_single", Da, 4);
+    e->av_a_gate = L.adaln("av_ca_v2a_gate_adaln_single", Da, 1);
+  }
+  // contiguous per-layer table arenas
+  e->table_arena_v = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * n * D));
+  if (v2) e->ptable_arena_v = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * 2 * D));
+  if (audio) {
+    e->table_arena_a = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * n * Da));
+    if (v2) e->ptable_arena_a = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * 2 * Da));
+    e->catable_arena_v = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * 5 * D));
+    e->catable_arena_a = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(nl) * 5 * Da));
+  }
+  if (!dry) e->blocks.resize(nl);
+  for (int i = 0; i < nl; ++i) {
+    BlockW tmp;
+    BlockW& b = dry ? tmp : e->blocks[i];
+    const std::string P = "transformer_blocks." + std::to_string(i) + ".";
+    b.v.attn1 = L.attention(P + "attn1", D, D, c.num_attention_heads, c.attention_head_dim, true, gated);
+    b.v.attn2 = L.attention(P + "attn2", D, c.cross_attention_dim, c.num_attention_heads, c.attention_head_dim,
+                            false, gated);
+    b.v.ff1 = L.linear(P + "ff.project_in.proj", 4 * D, D);
+    b.v.ff2 = L.linear(P + "ff.project_out", D, 4 * D);
+    b.v.table = L.f32_at(P + "scale_shift_table", offset_ptr(e->table_arena_v, size_t(i) * n * D), n, D);
+    if (v2)
+      b.v.prompt_table = L.f32_at(P + "prompt_scale_shift_table", offset_ptr(e->ptable_arena_v, size_t(i) * 2 * D), 2, D);
+    if (audio) {
+      b.a.attn1 = L.attention(P + "audio_attn1", Da, Da, c.audio_heads, c.audio_head_dim, true, gated);
+      b.a.attn2 = L.attention(P + "audio_attn2", Da, Da, c.audio_heads, c.audio_head_dim, false, gated);
+      b.a.ff1 = L.linear(P + "audio_ff.project_in.proj", 4 * Da, Da);
+      b.a.ff2 = L.linear(P + "audio_ff.project_out", Da, 4 * Da);
+      b.a.table = L.f32_at(P + "audio_scale_shift_table", offset_ptr(e->table_arena_a, size_t(i) * n * Da), n, Da);
+      if (v2)
+        b.a.prompt_table = L.f32_at(P + "audio_prompt_scale_shift_table",
+                                    offset_ptr(e->ptable_arena_a, size_t(i) * 2 * Da), 2, Da);
+      b.a2v = L.attention(P + "audio_to_video_attn", D, Da, c.audio_heads, c.audio_head_dim, false, gated);
+      b.v2a = L.attention(P + "video_to_audio_attn", Da, D, c.audio_heads, c.audio_head_dim, false, gated);
+      b.table_ca_audio = L.f32_at(P + "scale_shift_table_a2v_ca_audio",
+                                  offset_ptr(e->catable_arena_a, size_t(i) * 5 * Da), 5, Da);
+      b.table_ca_video = L.f32_at(P + "scale_shift_table_a2v_ca_video",
+                                  offset_ptr(e->catable_arena_v, size_t(i) * 5 * D), 5, D);
+    }
+  }
+}
+
+std::vector<float> make_freq_grid(float theta, int n_dims, int dim) {
+  // generate_freq_grid (rope.py:181-211): theta ** linspace(0, 1, dim // (2*n_dims)) * pi/2, stored as fp32
+  const int n = dim / (2 * n_dims);
+  std::vector<float> g(n);
+  for (int i = 0; i < n; ++i) {
+    const float lin = n > 1 ? static_cast<float>(static_cast<double>(i) / (n - 1)) : 0.f;
+    g[i] = static_cast<float>(pow(static_cast<double>(theta), static_cast<double>(lin)) * (M_PI / 2.0));
+  }
+  return g;
+}
+
+__global__ void fill_row_index_kernel(int* row_batch, int M, int tokens) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) row_batch[i] = i / tokens;
+}
+__global__ void gather_f32_kernel(const float* src, const int* idx, float* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------
+struct Shapes {
+  int B, N, S, n_cls;        // video
+  int Na, Sa, n_cls_a;       // audio (0 when absent)
+};
+
+size_t layout_stream_buf(StreamBuf& sb, Arena& ar, const LtxDitConfig& c, int dim, int heads, int dh, int in_ch,
+                         int out_ch, int ctx_ch, int B, int N, int S, int n_cls, int n_ada, int other_tokens,
+                         int other_dim, int cross_dim, bool v2, bool gated, bool av) {
+  sb.B = B; sb.N = N; sb.S = S; sb.dim = dim; sb.heads = heads; sb.dh = dh; sb.n_cls = n_cls;
+  const size_t M = size_t(B) * N;
+  const int L = c.num_layers;
+  const size_t maxT = std::max(std::max(N, S), other_tokens);
+  const size_t Tp = (maxT + 63) / 64 * 64;
+  const int kv_dim = std::max(dim, cross_dim);   // inner dim of the widest K/V this stream's buffers must hold
+  auto T = [&](size_t bytes) { return ar.take(bytes); };
+  sb.x = (float*)T(M * dim * 4);
+  sb.xn = (bf16*)T(M * dim * 2);
+  sb.qkv = (bf16*)T(M * 3 * dim * 2);
+  sb.attn = (bf16*)T(M * dim * 2);
+  sb.hidden = (bf16*)T(M * 4 * dim * 2);
+  sb.qh = (bf16*)T(M * dim * 2);
+  sb.kh = (bf16*)T(size_t(B) * maxT * kv_dim * 2);
+  sb.vt = (bf16*)T(size_t(B) * Tp * kv_dim * 2);
+  sb.lat = (bf16*)T(M * in_ch * 2);
+  sb.ctx_in = (bf16*)T(size_t(B) * S * ctx_ch * 2);
+  sb.ctx_mid = (bf16*)T(size_t(B) * S * dim * 2);
+  sb.ctx = (bf16*)T(size_t(B) * S * dim * 2);
+  sb.ctx_mod = v2 ? (bf16*)T(size_t(B) * S * dim * 2) : nullptr;
+  sb.kv = (bf16*)T(size_t(B) * std::max<size_t>(S, other_tokens) * 2 * kv_dim * 2);
+  sb.gate_logits = gated ? (float*)T(M * std::max(heads, 32) * 4) : nullptr;
+  sb.cos = (float*)T(M * (dim / 2) * 4);
+  sb.sin = (float*)T(M * (dim / 2) * 4);
+  sb.ccos = av ? (float*)T(M * (cross_dim / 2) * 4) : nullptr;
+  sb.csin = av ? (float*)T(M * (cross_dim / 2) * 4) : nullptr;
+  sb.mod = (float*)T(size_t(L) * n_cls * n_ada * dim * 4);
+  sb.prompt_mod = v2 ? (float*)T(size_t(L) * B * 2 * dim * 4) : nullptr;
+  sb.ca_mod = av ? (float*)T(size_t(L) * B * 5 * dim * 4) : nullptr;
+  sb.head_mod = (float*)T(size_t(n_cls) * 2 * dim * 4);
+  sb.emb_t = (float*)T(size_t(n_cls) * dim * 4);
+  sb.row_cls = (int*)T(M * 4);
+  sb.row_batch = (int*)T(std::max(M, size_t(B) * S) * 4);
+  sb.ctx_batch = (int*)T(size_t(B) * S * 4);
+  sb.t_cls = (float*)T(size_t(n_cls) * 4);
+  sb.t_row = (float*)T(M * 4);
+  sb.vel = (float*)T(M * out_ch * 4);
+  return ar.off;
+}
+
+int ensure_workspace(LtxDit* e, const Shapes& s) {
+  const LtxDitConfig& c = e->cfg;
+  const bool v2 = c.cross_attention_adaln != 0, gated = c.apply_gated_attention != 0;
+  const bool av = s.Na > 0;
+  const int ctx_ch_v = c.caption_channels > 0 ? c.caption_channels : e->D;
+  const int ctx_ch_a = c.caption_channels > 0 ? c.caption_channels : e->Da;
+  for (int pass = 0; pass < 2; ++pass) {
+    Arena ar;
+    ar.base = pass == 0 ? 0 : reinterpret_cast<uintptr_t>(e->ws);
+    StreamBuf vb, ab;
+    layout_stream_buf(vb, ar, c, e->D, c.num_attention_heads, c.attention_head_dim, c.in_channels, c.out_channels,
+                      ctx_ch_v, s.B, s.N, s.S, s.n_cls, e->n_ada, s.Na, e->Da, e->Da, v2, gated, av);
+    if (av)
+      layout_stream_buf(ab, ar, c, e->Da, c.audio_heads, c.audio_head_dim, c.audio_in_channels, c.audio_out_channels,
+                        ctx_ch_a, s.B, s.Na, s.Sa, s.n_cls_a, e->n_ada, s.N, e->D, e->Da, v2, gated, av);
+    float* scratch = (float*)ar.take(size_t(64) * (256 + 12 * std::max(e->D, 1)) * 4);
+    if (pass == 0) {
+      const size_t need = ar.off + 1024;
+      if (need > e->ws_bytes) {
+        if (e->ws) cudaFree(e->ws);
+        e->ws = nullptr;
+        e->ws_bytes = 0;
+        if (cudaMalloc(&e->ws, need) != cudaSuccess) {
+          set_error("workspace allocation of %zu bytes failed", need);
+          return LTX2_ERR_NOMEM;
+        }
+        e->ws_bytes = need;
+      }
+    } else {
+      e->vb = vb;
+      e->ab = ab;
+      e->scratch = scratch;
+    }
+  }
+  return LTX2_OK;
+}
+
+// ------------------------------------------------------------------------------
+// forward helpers
+// ------------------------------------------------------------------------------
+inline int linear_bf16(const bf16* A, int64_t lda, const LinearW& L, int M, bf16* out, int64_t ldo, bool gelu,
+                       cudaStream_t st, int n_rows = -1, int row_off = 0) {
+  GemmEpilogue ep;
+  ep.mode = gelu ? GEMM_EPI_BF16_GELU : GEMM_EPI_BF16;
+  ep.bias = L.b + row_off;
+  ep.out = out;
+  ep.ldo = ldo;
+  return gemm_bf16(A, lda, L.w + size_t(row_off) * L.in, L.in, M, n_rows < 0 ? L.out : n_rows, L.in, ep, st);
+}
+
+inline int linear_residual(const bf16* A, int64_t lda, const LinearW& L, int M, float* x, int64_t ldx,
+                           const float* gate, int64_t gate_stride, const int* row_cls, float alpha, cudaStream_t st) {
+  GemmEpilogue ep;
+  ep.mode = GEMM_EPI_F32_RESIDUAL;
+  ep.bias = L.b;
+  ep.out = x;
+  ep.ldo = ldx;
+  ep.gate = gate;
+  ep.gate_stride = gate_stride;
+  ep.row_cls = row_cls;
+  ep.alpha = alpha;
+  return gemm_bf16(A, lda, L.w, L.in, M, L.out, L.in, ep, st);
+}
+
+inline int linear_f32(const bf16* A, int64_t lda, const LinearW& L, int M, float* out, int64_t ldo, cudaStream_t st) {
+  GemmEpilogue ep;
+  ep.mode = GEMM_EPI_F32;
+  ep.bias = L.b;
+  ep.out = out;
+  ep.ldo = ldo;
+  return gemm_bf16(A, lda, L.w, L.in, M, L.out, L.in, ep, st);
+}
+
+// AdaLayerNormSingle on R (<= 64) scalar timesteps already on the device: emb [R, n_emb*dim], e [R, dim]
+int run_adaln(LtxDit* e, const AdaLNW& a, const float* t_dev, int R, float mult, int dim, float* emb_out,
+              float* e_out, cudaStream_t st) {
+  float* sinus = e->scratch;                 // [R,256]
+  float* h1 = sinus + size_t(64) * 256;      // [R,dim]
+  float* e_tmp = h1 + size_t(64) * dim;      // [R,dim]
+  float* eo = e_out ? e_out : e_tmp;
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    const int r = std::min(8, R - r0);
+    LTX2_PROPAGATE(timestep_sinusoid(t_dev + r0, r, mult, sinus, st));
+    LTX2_PROPAGATE(small_linear(sinus, r, 256, a.l1.w, a.l1.b, h1, dim, 0, st));
+    LTX2_PROPAGATE(small_linear(h1, r, dim, a.l2.w, a.l2.b, eo + size_t(r0) * dim, dim, 1, st));
+    LTX2_PROPAGATE(small_linear(eo + size_t(r0) * dim, r, dim, a.lin.w, a.lin.b,
+                                emb_out + size_t(r0) * a.n_emb * dim, a.n_emb * dim, 1, st));
+  }
+  return LTX2_OK;
+}
+
+struct AttnCall {
+  const AttnW* w;
+  const bf16* xq; int64_t ldq; int Mq; int Tq;          // query-side input [B*Tq, query_dim]
+  const bf16* xkv; int64_t ldkv; int Tk;               // key/value-side input [B*Tk, ctx_dim] (== xq for self)
+  const float *qcos, *qsin, *kcos, *ksin;              // rope tables or null
+};
+
+// Attention.__call__ up to (not including) to_out: writes sb.attn [B*Tq, inner]
+int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaStream_t st) {
+  const AttnW& w = *c.w;
+  const int inner = w.inner, H = w.heads, Dh = w.dh;
+  const float eps = e->cfg.norm_eps;
+  const int Tkp = (c.Tk + 63) / 64 * 64;
+  const bf16 *qp, *kp, *vp;
+  int64_t ldq, ldk;
+  if (w.fused_qkv) {
+    LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    qp = sb.qkv; kp = sb.qkv + inner; vp = sb.qkv + 2 * inner;
+    ldq = ldk = 3 * inner;
+  } else {
+    LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, inner, false, st));
+    LTX2_PROPAGATE(linear_bf16(c.xkv, c.ldkv, w.kv, B * c.Tk, sb.kv, 2 * inner, false, st));
+    qp = sb.qkv; kp = sb.kv; vp = sb.kv + inner;
+    ldq = inner; ldk = 2 * inner;
+  }
+  LTX2_PROPAGATE(headnorm_rope(qp, ldq, w.qnorm, c.qcos, c.qsin, sb.qh, B, c.Tq, H, Dh, eps, st));
+  LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
+  LTX2_PROPAGATE(v_transpose(vp, ldk, sb.vt, B, c.Tk, Tkp, H, Dh, st));
+  const float* gl = nullptr;
+  if (w.gate.w != nullptr) {
+    // to_gate_logits(x): [Mq, H]; H < 32 is padded by the GEMM's N%32 rule, so heads must be a multiple of 32
+    // for the tensor-core path; small head counts (tests) use the row-wise linear instead.
+    if (H % 32 == 0) {
+      LTX2_PROPAGATE(linear_f32(c.xq, c.ldq, w.gate, c.Mq, sb.gate_logits, H, st));
+    } else {
+      LTX2_PROPAGATE(rowdot_bf16(c.xq, c.ldq, w.gate.w, w.gate.b, sb.gate_logits, c.Mq, H, w.gate.in, st));
+    }
+    gl = sb.gate_logits;
+  }
+  return attention_bf16(sb.qh, sb.kh, sb.vt, sb.attn, B, H, c.Tq, c.Tk, Tkp, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr,
+                        st);
+}
+
+}  // namespace
+}  // namespace ltx2
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out) {
+  LTX2_REQUIRE(cfg != nullptr && out != nullptr, "dit_create: null argument");
+  LTX2_REQUIRE(cfg->attention_head_dim == 64 || cfg->attention_head_dim == 128,
+               "dit_create: attention_head_dim must be 64 or 128 (got %d)", cfg->attention_head_dim);
+  LTX2_REQUIRE(!cfg->audio_enabled || cfg->audio_head_dim == 64 || cfg->audio_head_dim == 128,
+               "dit_create: audio_head_dim must be 64 or 128");
+  LTX2_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 64, "dit_create: num_layers must be in 1..64");
+  LTX2_REQUIRE(cfg->in_channels % 8 == 0 && cfg->out_channels % 32 == 0, "dit_create: in_channels %% 8, out_channels %% 32");
+  LtxDit* e = new LtxDit();
+  e->cfg = *cfg;
+  e->D = cfg->num_attention_heads * cfg->attention_head_dim;
+  e->Da = cfg->audio_enabled ? cfg->audio_heads * cfg->audio_head_dim : 0;
+  e->n_ada = cfg->cross_attention_adaln ? 9 : 6;
+  e->cross_attn_scale.assign(cfg->num_layers, NAN);
+  Arena dry;
+  build_layout(e, &dry, true);
+  e->arena_bytes = dry.off + 1024;
+  if (cudaMalloc(&e->arena, e->arena_bytes) != cudaSuccess) {
+    set_error("weight arena allocation of %zu bytes failed", e->arena_bytes);
+    delete e;
+    return LTX2_ERR_NOMEM;
+  }
+  Arena real;
+  real.base = reinterpret_cast<uintptr_t>(e->arena);
+  build_layout(e, &real, false);
+  auto upload = [&](const std::vector<float>& v, float** dst) -> int {
+    LTX2_CUDA_CHECK(cudaMalloc(dst, v.size() * 4 + 16));
+    LTX2_CUDA_CHECK(cudaMemcpy(*dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    return LTX2_OK;
+  };
+  std::vector<float> gv = make_freq_grid(cfg->positional_embedding_theta, 3, e->D);
+  e->nf_video = (int)gv.size();
+  int s = upload(gv, &e->fg_video);
+  if (s == LTX2_OK && cfg->audio_enabled) {
+    std::vector<float> ga = make_freq_grid(cfg->positional_embedding_theta, 1, e->Da);
+    e->nf_audio = (int)ga.size();
+    s = upload(ga, &e->fg_audio);
+  }
+  if (s != LTX2_OK) {
+    ltx2_dit_destroy(e);
+    return s;
+  }
+  *out = e;
+  return LTX2_OK;
+}
+
+void ltx2_dit_destroy(LtxDit* e) {
+  if (!e) return;
+  if (e->arena) cudaFree(e->arena);
+  if (e->ws) cudaFree(e->ws);
+  if (e->fg_video) cudaFree(e->fg_video);
+  if (e->fg_audio) cudaFree(e->fg_audio);
+  delete e;
+}
+
+int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                        int32_t ndim, void* stream) {
+  LTX2_REQUIRE(e && key && data, "dit_set_weight: null argument");
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) {
+    set_error("dit_set_weight: unknown key '%s'", key);
+    return LTX2_ERR_NOKEY;
+  }
+  Slot& s = it->second;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  const int64_t expect = s.rows * (s.cols ? s.cols : 1);
+  const bool shape_ok = (s.cols == 0) ? (n == s.rows)
+                                      : (ndim == 2 && shape[0] == s.rows && shape[1] == s.cols);
+  if (!shape_ok) {
+    set_error("dit_set_weight: '%s' expects [%lld,%lld], got %lld elements (ndim %d)", key, (long long)s.rows,
+              (long long)s.cols, (long long)n, ndim);
+    return LTX2_ERR_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = s.storage == LTX2_BF16 ? cast_to_bf16(data, dtype, s.dst, expect, st)
+                                 : cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), expect, st);
+  if (r == LTX2_OK) s.loaded = true;
+  return r;
+}
+
+int ltx2_dit_missing_weights(LtxDit* e, char* names_out, int64_t names_cap) {
+  int missing = 0;
+  std::string acc;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      ++missing;
+      if (acc.size() < 4000) acc += kv.first + "\n";
+    }
+  if (names_out && names_cap > 0) {
+    strncpy(names_out, acc.c_str(), names_cap - 1);
+    names_out[names_cap - 1] = 0;
+  }
+  return missing;
+}
+
+int ltx2_dit_set_cross_attn_scale(LtxDit* e, int32_t block, float scale) {
+  LTX2_REQUIRE(e && block >= 0 && block < e->cfg.num_layers, "set_cross_attn_scale: bad block %d", block);
+  e->cross_attn_scale[block] = scale;
+  return LTX2_OK;
+}
+
+}  // extern "C"
+
+namespace ltx2 {
+namespace {
+
+// Modulation classes = distinct (batch, sigma) pairs.  Scalar timesteps (n_t == 1): one class per batch element,
+// no host round trip.  Per-token timesteps (image conditioning, common.py:193-203): the B*N values are read back
+// once and de-duplicated on the host (typically 2 classes per batch element).
+int prepare_classes(LtxDit* e, const LtxModalityView& m, int* n_cls, std::vector<float>& cls_vals,
+                    std::vector<int>& row_cls_host, cudaStream_t st) {
+  const int B = m.batch, N = m.tokens;
+  cls_vals.clear();
+  row_cls_host.clear();
+  if (m.n_t == 1) {
+    *n_cls = B;
+    return LTX2_OK;
+  }
+  e->h_ts.resize(size_t(B) * N);
+  LTX2_CUDA_CHECK(cudaMemcpyAsync(e->h_ts.data(), m.timesteps, e->h_ts.size() * 4, cudaMemcpyDeviceToHost, st));
+  LTX2_CUDA_CHECK(cudaStreamSynchronize(st));
+  row_cls_host.resize(size_t(B) * N);
+  for (int b = 0; b < B; ++b) {
+    std::map<uint32_t, int> seen;
+    for (int t = 0; t < N; ++t) {
+      const float v = e->h_ts[size_t(b) * N + t];
+      uint32_t bits;
+      memcpy(&bits, &v, 4);
+      auto it = seen.find(bits);
+      if (it == seen.end()) {
+        it = seen.emplace(bits, (int)cls_vals.size()).first;
+        cls_vals.push_back(v);
+      }
+      row_cls_host[size_t(b) * N + t] = it->second;
+    }
+  }
+  *n_cls = (int)cls_vals.size();
+  return LTX2_OK;
+}
+
+struct Prepared {
+  int n_cls;
+};
+
+int upload_classes(StreamBuf& sb, const LtxModalityView& m, const std::vector<float>& cls_vals,
+                   const std::vector<int>& row_cls_host, cudaStream_t st) {
+  const int M = m.batch * m.tokens;
+  if (m.n_t == 1) {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.t_cls, m.timesteps, size_t(m.batch) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.t_cls, cls_vals.data(), cls_vals.size() * 4, cudaMemcpyHostToDevice, st));
+  }
+  fill_row_index_kernel<<<(std::max(M, m.batch * m.context_tokens) + 255) / 256, 256, 0, st>>>(
+      sb.row_batch, std::max(M, m.batch * m.context_tokens), m.tokens);
+  fill_row_index_kernel<<<(m.batch * m.context_tokens + 255) / 256, 256, 0, st>>>(sb.ctx_batch,
+                                                                                 m.batch * m.context_tokens,
+                                                                                 m.context_tokens);
+  if (m.n_t == 1) {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.row_cls, sb.row_batch, size_t(M) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.row_cls, row_cls_host.data(), size_t(M) * 4, cudaMemcpyHostToDevice, st));
+  }
+  gather_f32_kernel<<<(M + 255) / 256, 256, 0, st>>>(sb.t_cls, sb.row_cls, sb.t_row, M);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  return LTX2_OK;
+}
+
+// TransformerArgsPreprocessor.prepare for one modality
+int prepare_stream(LtxDit* e, StreamBuf& sb, const StreamW& w, const LtxModalityView& m, bool audio_side,
+                   float* table_arena, float* ptable_arena, cudaStream_t st) {
+  const LtxDitConfig& c = e->cfg;
+  const int dim = sb.dim, B = m.batch, N = m.tokens, S = m.context_tokens, M = B * N, L = c.num_layers;
+  const int n = e->n_ada;
+  // patchify projection -> fp32 residual stream
+  LTX2_PROPAGATE(cast_to_bf16(m.latent, m.latent_dtype, sb.lat, int64_t(M) * w.patchify.in, st));
+  LTX2_PROPAGATE(linear_f32(sb.lat, w.patchify.in, w.patchify, M, sb.x, dim, st));
+  // timestep adaLN -> per-layer modulation tables
+  float* emb = e->scratch + size_t(64) * (256 + 2 * dim);      // [n_cls, n*dim] (after run_adaln's own scratch)
+  LTX2_PROPAGATE(run_adaln(e, w.adaln, sb.t_cls, sb.n_cls, c.timestep_scale_multiplier, dim, emb, sb.emb_t, st));
+  LTX2_PROPAGATE(build_modulation_ex(table_arena, int64_t(n) * dim, emb, int64_t(n) * dim, dim, sb.mod,
+                                     int64_t(sb.n_cls) * n * dim, int64_t(n) * dim, L, sb.n_cls, n, dim, st));
+  LTX2_PROPAGATE(build_modulation_ex(w.head_table, 0, sb.emb_t, dim, 0, sb.head_mod, 0, int64_t(2) * dim, 1,
+                                     sb.n_cls, 2, dim, st));
+  if (c.cross_attention_adaln) {
+    // prompt adaLN uses the scalar sigma per batch element (model.py:250-260)
+    float* sig = e->scratch + size_t(64) * (256 + 11 * dim);
+    if (m.sigma != nullptr) {
+      LTX2_CUDA_CHECK(cudaMemcpyAsync(sig, m.sigma, size_t(B) * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      // first token's timestep of every batch element
+      LTX2_CUDA_CHECK(cudaMemcpy2DAsync(sig, 4, m.timesteps, size_t(m.n_t) * 4, 4, B, cudaMemcpyDeviceToDevice, st));
+    }
+    float* pemb = emb;   // reuse: [B, 2*dim]
+    LTX2_PROPAGATE(run_adaln(e, w.prompt_adaln, sig, B, c.timestep_scale_multiplier, dim, pemb, nullptr, st));
+    LTX2_PROPAGATE(build_modulation_ex(ptable_arena, int64_t(2) * dim, pemb, int64_t(2) * dim, dim, sb.prompt_mod,
+                                       int64_t(B) * 2 * dim, int64_t(2) * dim, L, B, 2, dim, st));
+  }
+  // context (caption projection for V1)
+  const int ctx_ch = w.has_caption ? w.cap1.in : dim;
+  LTX2_PROPAGATE(cast_to_bf16(m.context, m.context_dtype, w.has_caption ? sb.ctx_in : sb.ctx,
+                              int64_t(B) * S * ctx_ch, st));
+  if (w.has_caption) {
+    LTX2_PROPAGATE(linear_bf16(sb.ctx_in, ctx_ch, w.cap1, B * S, sb.ctx_mid, dim, true, st));
+    LTX2_PROPAGATE(linear_bf16(sb.ctx_mid, dim, w.cap2, B * S, sb.ctx, dim, false, st));
+  }
+  // RoPE tables
+  if (!audio_side) {
+    LTX2_PROPAGATE(rope_tables_dev(m.positions, B, 3, 3, N, dim, c.max_pos, e->fg_video, e->nf_video, sb.cos, sb.sin, st));
+  } else {
+    const float mp[1] = {c.audio_max_pos};
+    LTX2_PROPAGATE(rope_tables_dev(m.positions, B, 1, 1, N, dim, mp, e->fg_audio, e->nf_audio, sb.cos, sb.sin, st));
+  }
+  return LTX2_OK;
+}
+
+}  // namespace
+}  // namespace ltx2
+
+namespace ltx2 {
+namespace {
+
+// scalar sigma per batch element of a modality (Modality.sigma, else timesteps[:,0]) -> dst[B] (device)
+int scalar_sigma(const LtxModalityView& m, float* dst, cudaStream_t st) {
+  if (m.sigma != nullptr) {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(dst, m.sigma, size_t(m.batch) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    LTX2_CUDA_CHECK(cudaMemcpy2DAsync(dst, 4, m.timesteps, size_t(m.n_t) * 4, 4, m.batch, cudaMemcpyDeviceToDevice, st));
+  }
+  return LTX2_OK;
+}
+
+// cross-modal adaLN (model.py:345-366): ca_mod[l, b, 0..3] = table[l][0..3] + ss_emb[b], [4] = table[l][4] + gate_emb[b]
+int prepare_cross_mod(LtxDit* e, StreamBuf& sb, const AdaLNW& ss, const AdaLNW& gate, const float* table_arena,
+                      const LtxModalityView& other, cudaStream_t st) {
+  const LtxDitConfig& c = e->cfg;
+  const int dim = sb.dim, B = sb.B, L = c.num_layers;
+  float* sig = e->scratch + size_t(64) * (256 + 11 * std::max(e->D, 1));
+  float* emb = e->scratch + size_t(64) * (256 + 2 * std::max(e->D, 1));
+  LTX2_PROPAGATE(scalar_sigma(other, sig, st));
+  LTX2_PROPAGATE(run_adaln(e, ss, sig, B, c.timestep_scale_multiplier, dim, emb, nullptr, st));
+  LTX2_PROPAGATE(build_modulation_ex(table_arena, int64_t(5) * dim, emb, int64_t(4) * dim, dim, sb.ca_mod,
+                                     int64_t(B) * 5 * dim, int64_t(5) * dim, L, B, 4, dim, st));
+  // gate timestep: sigma * ts_mult * (av_ca_mult / ts_mult)
+  LTX2_PROPAGATE(run_adaln(e, gate, sig, B, c.av_ca_timestep_scale_multiplier, dim, emb, nullptr, st));
+  LTX2_PROPAGATE(build_modulation_ex(table_arena + 4 * dim, int64_t(5) * dim, emb, dim, dim, sb.ca_mod + 4 * dim,
+                                     int64_t(B) * 5 * dim, int64_t(5) * dim, L, B, 1, dim, st));
+  return LTX2_OK;
+}
+
+int rms_mod(const LtxDit* e, const StreamBuf& sb, bf16* out, const float* mod, int64_t mod_stride, int shift_row,
+            int scale_row, const int* cls, cudaStream_t st) {
+  const int M = sb.B * sb.N;
+  return norm_modulate(sb.x, 0, sb.dim, out, sb.dim, M, sb.dim, NORM_RMS, e->cfg.norm_eps, mod, mod_stride,
+                       int64_t(shift_row) * sb.dim, int64_t(scale_row) * sb.dim, cls, st);
+}
+
+// self-attention + text cross-attention of one modality (transformer.py:503-553)
+int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer, bool skip_self, float ca_scale,
+                      cudaStream_t st) {
+  const LtxDitConfig& c = e->cfg;
+  const int dim = sb.dim, B = sb.B, N = sb.N, S = sb.S, M = B * N, n = e->n_ada;
+  const bool v2 = c.cross_attention_adaln != 0;
+  const float* mod = sb.mod + size_t(layer) * sb.n_cls * n * dim;
+  const int64_t ms = int64_t(n) * dim;
+  if (!skip_self) {
+    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
+    AttnCall a{&w.attn1, sb.xn, dim, M, N, sb.xn, dim, N, sb.cos, sb.sin, sb.cos, sb.sin};
+    LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
+    LTX2_PROPAGATE(linear_residual(sb.attn, w.attn1.inner, w.attn1.o, M, sb.x, dim, mod + 2 * dim, ms, sb.row_cls,
+                                   1.0f, st));
+  }
+  const bf16* ctx = sb.ctx;
+  if (v2) {
+    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 6, 7, sb.row_cls, st));
+    const float* pm = sb.prompt_mod + size_t(layer) * B * 2 * dim;
+    LTX2_PROPAGATE(norm_modulate(sb.ctx, 1, dim, sb.ctx_mod, dim, B * S, dim, NORM_NONE, c.norm_eps, pm,
+                                 int64_t(2) * dim, 0, dim, sb.ctx_batch, st));
+    ctx = sb.ctx_mod;
+  } else {
+    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, nullptr, 0, 0, 0, nullptr, st));
+  }
+  AttnCall a{&w.attn2, sb.xn, dim, M, N, ctx, dim, S, nullptr, nullptr, nullptr, nullptr};
+  LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
+  return linear_residual(sb.attn, w.attn2.inner, w.attn2.o, M, sb.x, dim, v2 ? mod + 8 * dim : nullptr, ms,
+                         sb.row_cls, ca_scale, st);
+}
+
+int run_ffn(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer, cudaStream_t st) {
+  const int dim = sb.dim, M = sb.B * sb.N, n = e->n_ada;
+  const float* mod = sb.mod + size_t(layer) * sb.n_cls * n * dim;
+  const int64_t ms = int64_t(n) * dim;
+  LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 3, 4, sb.row_cls, st));
+  LTX2_PROPAGATE(linear_bf16(sb.xn, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
+  return linear_residual(sb.hidden, 4 * dim, w.ff2, M, sb.x, dim, mod + 5 * dim, ms, sb.row_cls, 1.0f, st);
+}
+
+int run_head(LtxDit* e, StreamBuf& sb, const StreamW& w, const LtxModalityView& m, int x0, float* out,
+             cudaStream_t st) {
+  const int dim = sb.dim, M = sb.B * sb.N, C = w.proj_out.out;
+  LTX2_PROPAGATE(norm_modulate(sb.x, 0, dim, sb.xn, dim, M, dim, NORM_LAYER, e->cfg.norm_eps, sb.head_mod,
+                               int64_t(2) * dim, 0, dim, sb.row_cls, st));
+  if (!x0) return linear_f32(sb.xn, dim, w.proj_out, M, out, C, st);
+  LTX2_REQUIRE(C == w.patchify.in, "x0 output needs in_channels == out_channels");
+  LTX2_PROPAGATE(linear_f32(sb.xn, dim, w.proj_out, M, sb.vel, C, st));
+  float* lat32 = sb.x;   // the residual stream is dead after the head norm
+  LTX2_PROPAGATE(cast_to_f32(m.latent, m.latent_dtype, lat32, int64_t(M) * C, st));
+  return x0_from_velocity(lat32, sb.vel, sb.t_row, out, M, C, st);
+}
+
+int check_view(const LtxModalityView* m, const char* name, int n_dims) {
+  LTX2_REQUIRE(m->latent && m->context && m->timesteps && m->positions, "%s modality: null pointer", name);
+  LTX2_REQUIRE(m->batch >= 1 && m->tokens >= 1 && m->context_tokens >= 1, "%s modality: empty", name);
+  LTX2_REQUIRE(m->n_t == 1 || m->n_t == m->tokens, "%s modality: timesteps must be (B,) or (B,N)", name);
+  LTX2_REQUIRE(m->n_dims == n_dims, "%s modality: positions must have %d axes (got %d)", name, n_dims, m->n_dims);
+  return LTX2_OK;
+}
+
+}  // namespace
+}  // namespace ltx2
+
+extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const LtxModalityView* audio,
+                                const LtxDitSkip* skip, int32_t x0, float* out_video, float* out_audio,
+                                void* stream) {
+  LTX2_REQUIRE(e != nullptr, "dit_forward: null handle");
+  if (video == nullptr) {
+    set_error("Video modality required for video-enabled model");   // model.py:824
+    return LTX2_ERR_INVALID;
+  }
+  LTX2_REQUIRE(out_video != nullptr, "dit_forward: null output");
+  {
+    int missing = 0;
+    for (auto& kv : e->slots) missing += kv.second.loaded ? 0 : 1;
+    if (missing) {
+      set_error("dit_forward: %d weight tensors have not been set", missing);
+      return LTX2_ERR_STATE;
+    }
+  }
+  const LtxDitConfig& c = e->cfg;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LTX2_PROPAGATE(check_view(video, "video", 3));
+  const bool has_audio = c.audio_enabled && audio != nullptr && audio->tokens > 0;
+  if (has_audio) {
+    LTX2_PROPAGATE(check_view(audio, "audio", 1));
+    LTX2_REQUIRE(audio->batch == video->batch, "audio/video batch mismatch");
+    LTX2_REQUIRE(out_audio != nullptr, "dit_forward: audio modality given but out_audio is null");
+  }
+  LtxDitSkip sk = {0, 0, 0, 0};
+  if (skip) sk = *skip;
+
+  std::vector<float> cls_v, cls_a;
+  std::vector<int> rc_v, rc_a;
+  int ncv = 0, nca = 0;
+  LTX2_PROPAGATE(prepare_classes(e, *video, &ncv, cls_v, rc_v, st));
+  if (has_audio) LTX2_PROPAGATE(prepare_classes(e, *audio, &nca, cls_a, rc_a, st));
+  LTX2_REQUIRE(ncv <= 64 && nca <= 64, "more than 64 distinct (batch, sigma) classes");
+  Shapes sh;
+  sh.B = video->batch; sh.N = video->tokens; sh.S = video->context_tokens; sh.n_cls = ncv;
+  sh.Na = has_audio ? audio->tokens : 0; sh.Sa = has_audio ? audio->context_tokens : 0;
+  sh.n_cls_a = has_audio ? nca : 0;
+  LTX2_PROPAGATE(ensure_workspace(e, sh));
+  StreamBuf& vb = e->vb;
+  StreamBuf& ab = e->ab;
+  LTX2_PROPAGATE(upload_classes(vb, *video, cls_v, rc_v, st));
+  if (has_audio) LTX2_PROPAGATE(upload_classes(ab, *audio, cls_a, rc_a, st));
+
+  LTX2_PROPAGATE(prepare_stream(e, vb, e->vw, *video, false, e->table_arena_v, e->ptable_arena_v, st));
+  if (has_audio) {
+    LTX2_PROPAGATE(prepare_stream(e, ab, e->aw, *audio, true, e->table_arena_a, e->ptable_arena_a, st));
+    // cross-modal RoPE: THIS modality's temporal axis at the audio width (model.py:320-343).  For the audio
+    // stream that is exactly its self-attention table (same dim, max_pos and positions).
+    const float mp[1] = {c.audio_max_pos};
+    LTX2_PROPAGATE(rope_tables_dev(video->positions, sh.B, 3, 1, sh.N, e->Da, mp, e->fg_audio, e->nf_audio, vb.ccos,
+                                   vb.csin, st));
+    // cross-attention timestep embeddings use the OTHER modality's sigma (model.py:394-399)
+    LTX2_PROPAGATE(prepare_cross_mod(e, vb, e->av_v_ss, e->av_v_gate, e->catable_arena_v, *audio, st));
+    LTX2_PROPAGATE(prepare_cross_mod(e, ab, e->av_a_ss, e->av_a_gate, e->catable_arena_a, *video, st));
+  }
+
+  const int D = e->D, Da = e->Da, B = sh.B, N = sh.N, Na = sh.Na;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const BlockW& w = e->blocks[l];
+    const uint64_t bit = uint64_t(1) << l;
+    const float cas = isnan(e->cross_attn_scale[l]) ? 1.0f : e->cross_attn_scale[l];
+    LTX2_PROPAGATE(run_self_and_text(e, vb, w.v, l, (sk.video_self_attn & bit) != 0, cas, st));
+    if (has_audio) {
+      LTX2_PROPAGATE(run_self_and_text(e, ab, w.a, l, (sk.audio_self_attn & bit) != 0, 1.0f, st));
+      const bool do_a2v = (sk.a2v_cross_attn & bit) == 0, do_v2a = (sk.v2a_cross_attn & bit) == 0;
+      const float* cmv = vb.ca_mod + size_t(l) * B * 5 * D;     // rows: scale_a2v, shift_a2v, scale_v2a, shift_v2a, gate
+      const float* cma = ab.ca_mod + size_t(l) * B * 5 * Da;
+      // all four modulated inputs are formed from the PRE-update residuals (transformer.py:561-562)
+      bf16* vq = vb.xn; bf16* ak = ab.xn; bf16* aq = ab.hidden; bf16* vk = vb.hidden;
+      if (do_a2v) {
+        LTX2_PROPAGATE(rms_mod(e, vb, vq, cmv, int64_t(5) * D, 1, 0, vb.row_batch, st));
+        LTX2_PROPAGATE(rms_mod(e, ab, ak, cma, int64_t(5) * Da, 1, 0, ab.row_batch, st));
+      }
+      if (do_v2a) {
+        LTX2_PROPAGATE(rms_mod(e, ab, aq, cma, int64_t(5) * Da, 3, 2, ab.row_batch, st));
+        LTX2_PROPAGATE(rms_mod(e, vb, vk, cmv, int64_t(5) * D, 3, 2, vb.row_batch, st));
+      }
+      if (do_a2v) {
+        AttnCall a{&w.a2v, vq, D, B * N, N, ak, Da, Na, vb.ccos, vb.csin, ab.cos, ab.sin};
+        LTX2_PROPAGATE(run_attention_core(e, vb, a, B, st));
+        LTX2_PROPAGATE(linear_residual(vb.attn, w.a2v.inner, w.a2v.o, B * N, vb.x, D, cmv + 4 * D, int64_t(5) * D,
+                                       vb.row_batch, 1.0f, st));
+      }
+      if (do_v2a) {
+        AttnCall a{&w.v2a, aq, Da, B * Na, Na, vk, D, N, ab.cos, ab.sin, vb.ccos, vb.csin};
+        LTX2_PROPAGATE(run_attention_core(e, ab, a, B, st));
+        LTX2_PROPAGATE(linear_residual(ab.attn, w.v2a.inner, w.v2a.o, B * Na, ab.x, Da, cma + 4 * Da, int64_t(5) * Da,
+                                       ab.row_batch, 1.0f, st));
+      }
+    }
+    LTX2_PROPAGATE(run_ffn(e, vb, w.v, l, st));
+    if (has_audio) LTX2_PROPAGATE(run_ffn(e, ab, w.a, l, st));
+  }
+  LTX2_PROPAGATE(run_head(e, vb, e->vw, *video, x0, out_video, st));
+  if (has_audio) LTX2_PROPAGATE(run_head(e, ab, e->aw, *audio, x0, out_audio, st));
+  return LTX2_OK;
+}

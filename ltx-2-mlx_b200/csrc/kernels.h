@@ -1,0 +1,109 @@
+// Internal (C++) launch interface of the sm_100a kernels.  The public C ABI in
+// include/ltx2_b200.h is a thin shim over these.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ltx2 {
+
+// ---------------------------------------------------------------------------------
+// GEMM  C[M,N] = A[M,K] W[N,K]^T with fused epilogue (gemm_sm100.cu)
+// ---------------------------------------------------------------------------------
+enum GemmEpilogueMode {
+  GEMM_EPI_BF16 = 0,          // out_bf16 = acc + bias
+  GEMM_EPI_BF16_GELU = 1,     // out_bf16 = gelu_tanh(acc + bias)
+  GEMM_EPI_F32 = 2,           // out_f32  = acc + bias
+  GEMM_EPI_F32_RESIDUAL = 3,  // out_f32 += alpha * gate[row_cls[row], col] * (acc + bias)
+};
+
+struct GemmEpilogue {
+  int mode = GEMM_EPI_BF16;
+  const float* bias = nullptr;     // [N] fp32 or null
+  void* out = nullptr;             // bf16 or fp32, row pitch ldo elements
+  int64_t ldo = 0;
+  const float* gate = nullptr;     // [n_cls, gate_stride] fp32 or null (= 1)
+  int64_t gate_stride = 0;
+  const int* row_cls = nullptr;    // [M] modulation class of each row, or null (= 0)
+  float alpha = 1.0f;
+};
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------
+// attention (attention_sm100.cu):  O = softmax(Q K^T * scale) V, no mask
+//   q  [B,H,Tq,Dh] bf16, k [B,H,Tk,Dh] bf16, vt [B,H,Dh,Tkp] bf16 (V transposed, pitch Tkp >= Tk, Tkp % 8 == 0)
+//   out [B,Tq,H*Dh] bf16 (token-major).  gate_logits [B*Tq, H] fp32 or null: out *= 2*sigmoid(logit)
+//   partial (optional, for ring attention): when lse_out != null the kernel also writes the
+//   log-sum-exp (natural log, scaled scores) per row to lse_out [B,H,Tq] fp32.
+// ---------------------------------------------------------------------------------
+int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
+                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------
+// row kernels (rowops.cu)
+// ---------------------------------------------------------------------------------
+enum NormKind { NORM_NONE = 0, NORM_RMS = 1, NORM_LAYER = 2 };
+
+// out_bf16[row,:] = norm(x[row,:]) * (1 + scale) + shift, with
+//   shift = mod[cls*mod_stride + shift_off + col], scale = mod[cls*mod_stride + scale_off + col], cls = row_cls[row]
+//   (mod == null -> plain norm).  x is fp32 (x_is_bf16 = 0) or bf16.
+int norm_modulate(const void* x, int x_is_bf16, int64_t ldx, void* out_bf16, int64_t ldo, int M, int D, int norm_kind,
+                  float eps, const float* mod, int64_t mod_stride, int64_t shift_off, int64_t scale_off,
+                  const int* row_cls, cudaStream_t stream);
+
+// RMSNorm over the full row with a learned weight, optional split-RoPE, then scatter to heads:
+//   in [B*T, inner] bf16 (pitch ld) -> out [B,H,T,Dh] bf16.   cos/sin [B,T,inner/2] fp32 or null.
+int headnorm_rope(const void* in, int64_t ld, const float* weight, const float* cos, const float* sin, void* out,
+                  int B, int T, int H, int Dh, float eps, cudaStream_t stream);
+
+// V [B*T, inner] bf16 (pitch ld) -> Vt [B,H,Dh,Tp] bf16 (zero-padded to pitch Tp)
+int v_transpose(const void* v, int64_t ld, void* vt, int B, int T, int Tp, int H, int Dh, cudaStream_t stream);
+
+// y[r, n] = act_out( sum_k act_in(x[r,k]) * W[n,k] + bias[n] ), x fp32 [R<=8 rows, K], W bf16 [N,K], y fp32
+//   act_in: 0 none, 1 SiLU.  Used for the timestep-embedding MLPs (timestep_embedding.py:166-202).
+int small_linear(const float* x, int R, int K, const void* W, const float* bias, float* y, int N, int act_in,
+                 cudaStream_t stream);
+
+// out[m,h] = x[m,:].W[h,:] + b[h], x/W bf16, out fp32 (small-H fallback for to_gate_logits, attention.py:244)
+int rowdot_bf16(const void* x, int64_t ldx, const void* W, const float* bias, float* out, int M, int H, int K,
+                cudaStream_t stream);
+
+// sinusoidal timestep features [cos | sin] of 1000*sigma, 256 wide (timestep_embedding.py:10-60 with
+// flip_sin_to_cos=True, shift 0;  simple_decoder.py:12-39 is the same formula)
+int timestep_sinusoid(const float* t, int R, float multiplier, float* out256, cudaStream_t stream);
+
+// out[l, c, k, :] = tables[l*table_layer_stride + k*D + :] + emb[c*emb_cls_stride + k*emb_row_stride + :]
+// written at out + l*out_layer_stride + c*out_cls_stride + k*D   (adaLN table row + timestep-embedding row;
+// get_ada_values transformer.py:369-392, output head model.py:750-754)
+int build_modulation_ex(const float* tables, int64_t table_layer_stride, const float* emb, int64_t emb_cls_stride,
+                        int64_t emb_row_stride, float* out, int64_t out_layer_stride, int64_t out_cls_stride, int L,
+                        int C, int R, int D, cudaStream_t stream);
+
+// split-RoPE tables from [start,end) position bounds (rope.py:365-418): positions [B,n_dims,T,2] fp32 ->
+// cos,sin [B,T,dim/2] fp32 in token-major order (head h owns columns [h*dim/2/H, (h+1)*dim/2/H) ).
+// freq_grid_dev: device array of n_freq = dim/(2*n_dims) floats, theta^linspace(0,1,n_freq) * pi/2.
+// positions carry pos_dims axes per batch element; only the first n_dims are used (the cross-modal table
+// uses the temporal axis of the 3-axis video positions, model.py:330-331).
+int rope_tables_dev(const float* positions, int B, int pos_dims, int n_dims, int T, int dim, const float* max_pos_host,
+                    const float* freq_grid_dev, int n_freq, float* cos, float* sin, cudaStream_t stream);
+
+// x0 = latent - t[row] * velocity  (model.py:912-918), fp32
+int x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int M, int C,
+                     cudaStream_t stream);
+
+int cast_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStream_t stream);
+int cast_to_f32(const void* src, int src_dtype, float* dst, int64_t n, cudaStream_t stream);
+
+// The reference's three Metal kernels (kernels/fused_ops.py), fp32/bf16/fp16 by dtype code
+int silu_mul(const void* a, const void* b, void* out, int64_t n, int dtype, cudaStream_t stream);
+int gelu_mul(const void* a, const void* b, void* out, int64_t n, int dtype, cudaStream_t stream);
+int interleaved_rope(const void* x, const void* cos, const void* sin, void* out, int64_t n, int dtype,
+                     cudaStream_t stream);
+
+// dtype codes shared with the C ABI
+enum { LTX2_F32 = 0, LTX2_BF16 = 1, LTX2_F16 = 2 };
+
+}  // namespace ltx2

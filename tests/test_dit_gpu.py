@@ -1,0 +1,150 @@
+"""GPU parity of the full DiT forward (through LTXModel -> C ABI) against the oracle on the same seeded
+synthetic checkpoint and inputs.  The oracle runs in fp32 on the bf16-rounded weights, so the remaining
+difference is bf16 activations at the GEMM/attention inputs (fp32 accumulation, fp32 residual stream).
+
+Tolerances: relative L2 error <= 2e-2 and the reference's own metric, Pearson r (tests/test_parity.py:53-59),
+>= 0.999 (the reference's gate is r >= 0.95, test_parity.py:38)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def pearson(a, b):
+    a, b = a.double().flatten().cpu().numpy(), b.double().flatten().cpu().numpy()
+    return float(np.corrcoef(a, b)[0, 1])
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm())
+
+
+def bf16_round(w):
+    return {k: (v.to(torch.bfloat16).float() if v.ndim == 2 and "scale_shift_table" not in k else v) for k, v in w.items()}
+
+
+def build(cfg, seed):
+    from ltx2_b200 import synthetic
+    from ltx2_b200.loader import load_transformer_state_dict
+    from ltx2_b200.transformer import LTXModel, LTXModelType
+    from oracle import dit_oracle as O
+
+    class Small(LTXModel):
+        AUDIO_ATTENTION_HEADS = cfg.audio_heads
+        AUDIO_HEAD_DIM = cfg.audio_head_dim
+
+    w = synthetic.dit_weights(cfg, seed=seed)
+    m = Small(model_type=LTXModelType.AudioVideo if cfg.audio else LTXModelType.VideoOnly,
+              num_attention_heads=cfg.num_attention_heads, attention_head_dim=cfg.attention_head_dim,
+              in_channels=cfg.in_channels, out_channels=cfg.out_channels, num_layers=cfg.num_layers,
+              cross_attention_dim=cfg.cross_attention_dim, caption_channels=cfg.caption_channels,
+              cross_attention_adaln=cfg.cross_attention_adaln, apply_gated_attention=cfg.apply_gated_attention,
+              av_ca_timestep_scale_multiplier=1000)
+    load_transformer_state_dict(m, w)
+    assert m.missing_weights() == []
+    return m, O.to_engine_keys(bf16_round(w))
+
+
+def video_inputs(cfg, B, F, H, W, S, seed, ctx_dim):
+    from ltx2_b200 import synthetic
+    N = F * H * W
+    lat = synthetic.latents((B, N, cfg.in_channels), seed=seed)
+    ctx = synthetic.latents((B, S, ctx_dim), seed=seed + 1, std=0.5)
+    pos = synthetic.video_positions(B, F, H, W, fps=24.0)
+    return lat, ctx, pos
+
+
+@pytest.mark.parametrize("mode", ["scalar", "pertoken"])
+def test_dit_v1_forward_matches_oracle(mode):
+    from ltx2_b200 import synthetic
+    from ltx2_b200.transformer import Modality, X0Model
+    from oracle import dit_oracle as O
+    cfg = synthetic.DitConfig(num_attention_heads=4, attention_head_dim=128, in_channels=32, out_channels=32,
+                              num_layers=2, cross_attention_dim=512, caption_channels=64)
+    m, w = build(cfg, seed=11)
+    B, F, H, W, S = 2, 3, 4, 6, 40
+    lat, ctx, pos = video_inputs(cfg, B, F, H, W, S, 100, 64)
+    N = F * H * W
+    if mode == "scalar":
+        ts = torch.tensor([0.9, 0.4])
+    else:
+        ts = torch.where(torch.arange(N)[None, :, None] < H * W, torch.zeros(1), torch.tensor([0.725, 0.25])[:, None, None])
+    ref = O.dit_forward(w, dict(latent=lat, context=ctx, timesteps=ts, positions=pos), num_layers=2, heads=4)
+    mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=ts, positions=pos)
+    out = m(mod)
+    assert out.shape == ref.shape and out.dtype == torch.float32 and out.is_cuda
+    assert rel(out, ref) < 2e-2, rel(out, ref)
+    assert pearson(out, ref) > 0.999
+    x0 = X0Model(m)(mod)
+    assert rel(x0, O.to_x0(lat, ts, ref)) < 2e-2
+    # numpy inputs and bf16 inputs are accepted like the reference's mx.array
+    out_np = m(Modality(latent=lat.numpy(), context=ctx.numpy(), context_mask=None, timesteps=ts.numpy(),
+                        positions=pos.numpy()))
+    assert torch.equal(out_np, out)
+
+
+def test_dit_v1_cross_attn_scale_and_errors():
+    from ltx2_b200 import synthetic
+    from ltx2_b200._lib import Ltx2Error
+    from ltx2_b200.transformer import LTXModel, Modality
+    from oracle import dit_oracle as O
+    cfg = synthetic.DitConfig(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32,
+                              num_layers=1, cross_attention_dim=128, caption_channels=64)
+    m, w = build(cfg, seed=12)
+    lat, ctx, pos = video_inputs(cfg, 1, 2, 3, 4, 24, 110, 64)
+    ts = torch.tensor([0.6])
+    mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=ts, positions=pos)
+    base = m(mod)
+    m.transformer_blocks[0]._cross_attn_scale = 0.0
+    off = m(mod)
+    del m.transformer_blocks[0]._cross_attn_scale
+    assert torch.equal(m(mod), base) and not torch.allclose(off, base)
+    with pytest.raises(ValueError, match="Video modality required"):
+        m(None)
+    fresh = LTXModel(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32, num_layers=1,
+                     cross_attention_dim=128, caption_channels=64)
+    with pytest.raises(Ltx2Error, match="have not been set"):
+        fresh(mod)
+
+
+def test_dit_v2_audio_video_and_stg_match_oracle():
+    from ltx2_b200 import synthetic
+    from ltx2_b200.transformer import (BatchedPerturbationConfig, Modality, Perturbation, PerturbationConfig,
+                                       PerturbationType, X0Model)
+    from oracle import dit_oracle as O
+    cfg = synthetic.DitConfig(num_attention_heads=4, attention_head_dim=128, in_channels=32, out_channels=32,
+                              num_layers=2, cross_attention_dim=512, caption_channels=None,
+                              cross_attention_adaln=True, apply_gated_attention=True, audio=True,
+                              audio_heads=4, audio_head_dim=64)
+    m, w = build(cfg, seed=13)
+    B, F, H, W, S, Na = 2, 3, 4, 6, 40, 9
+    lat, ctx, pos = video_inputs(cfg, B, F, H, W, S, 120, 512)
+    alat = synthetic.latents((B, Na, 128), seed=130)
+    actx = synthetic.latents((B, S, 256), seed=131, std=0.5)
+    apos = synthetic.audio_positions(B, Na)
+    sv, sa = torch.tensor([0.9, 0.4]), torch.tensor([0.8, 0.3])
+    kw = dict(num_layers=2, heads=4, audio_heads=4, v2=True, av_ca_timestep_scale_multiplier=1000)
+    vd = dict(latent=lat, context=ctx, timesteps=sv, positions=pos, sigma=sv)
+    ad = dict(latent=alat, context=actx, timesteps=sa, positions=apos, sigma=sa)
+    rv, ra = O.dit_forward(w, vd, ad, **kw)
+    vm = Modality(latent=lat, context=ctx, context_mask=None, timesteps=sv, positions=pos, sigma=sv)
+    am = Modality(latent=alat, context=actx, context_mask=None, timesteps=sa, positions=apos, sigma=sa)
+    ov, oa = m(vm, am)
+    assert rel(ov, rv) < 2e-2 and rel(oa, ra) < 2e-2, (rel(ov, rv), rel(oa, ra))
+    assert pearson(ov, rv) > 0.999 and pearson(oa, ra) > 0.999
+    # video-only inference on the AV model
+    v_only, a_empty = m(vm, None)
+    assert a_empty.shape == (B, 0, 128)
+    assert rel(v_only, O.dit_forward(w, vd, None, **kw)) < 2e-2
+    assert X0Model(m)(vm, None).shape == lat.shape
+    # STG: skip video self-attention in block 1 and a2v in block 0 for the whole batch
+    pc = PerturbationConfig([Perturbation(PerturbationType.SKIP_VIDEO_SELF_ATTN, [1]),
+                             Perturbation(PerturbationType.SKIP_A2V_CROSS_ATTN, [0])])
+    pv, pa = m(vm, am, perturbations=BatchedPerturbationConfig([pc, pc]))
+    sv_, sa_ = O.dit_forward(w, vd, ad, skip_blocks={"video_self": [1], "a2v": [0]}, **kw)
+    assert rel(pv, sv_) < 2e-2 and rel(pa, sa_) < 2e-2
+    # a perturbation that only applies to half the batch is NOT applied (all_in_batch, transformer.py:486-501)
+    half = BatchedPerturbationConfig([pc, PerturbationConfig.empty()])
+    hv, _ = m(vm, am, perturbations=half)
+    assert torch.equal(hv, ov)

@@ -1,0 +1,225 @@
+"""GPU parity of each sm_100a kernel, called through the C ABI, against a torch fp32 reference of the
+same op on the same (bf16-rounded) inputs and against the oracle's functions."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0, std=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * std).to(dtype).to(dev())
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# bf16 output rounding is 2^-9 relative per element; fp32-accumulated GEMMs differ only by summation order.
+TOL_BF16_OUT = 6e-3
+TOL_F32_OUT = 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (200, 384, 320), (1000, 128, 128),
+                                   (96, 32, 4096), (130, 64, 192), (3456, 4096, 4096), (864, 12288, 512)])
+def test_gemm_bf16_store(M, N, K):
+    from ltx2_b200 import ops
+    a, w = rnd(M, K, seed=1, dtype=torch.bfloat16), rnd(N, K, seed=2, std=K ** -0.5, dtype=torch.bfloat16)
+    bias = rnd(N, seed=3)
+    ref = a.float() @ w.float().T + bias
+    out = ops.gemm(a, w, bias, mode=ops.EPI_BF16)
+    assert rel_err(out.float(), ref) < TOL_BF16_OUT
+    out32 = ops.gemm(a, w, bias, mode=ops.EPI_F32)
+    assert rel_err(out32, ref) < TOL_F32_OUT
+    assert float((out32 - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_gemm_epilogues_gelu_and_gated_residual():
+    from ltx2_b200 import ops
+    M, N, K = 520, 512, 256
+    a, w = rnd(M, K, seed=4, dtype=torch.bfloat16), rnd(N, K, seed=5, std=K ** -0.5, dtype=torch.bfloat16)
+    bias = rnd(N, seed=6)
+    lin = a.float() @ w.float().T + bias
+    out = ops.gemm(a, w, bias, mode=ops.EPI_BF16_GELU)
+    assert rel_err(out.float(), torch.nn.functional.gelu(lin, approximate="tanh")) < TOL_BF16_OUT
+    x = rnd(M, N, seed=7)
+    gate = rnd(3, 2 * N, seed=8)                       # 3 classes, row pitch 2N, gate lives in the 2nd half
+    cls = (torch.arange(M, device=dev()) % 3).to(torch.int32)
+    ref = x + 0.5 * gate[:, N:][cls.long()] * lin
+    y = x.clone()
+    ops.gemm(a, w, bias, mode=ops.EPI_F32_RESIDUAL, out=y, gate=gate[:, N:], row_cls=cls, alpha=0.5)
+    assert rel_err(y, ref) < TOL_F32_OUT
+    y2 = x.clone()
+    ops.gemm(a, w, None, mode=ops.EPI_F32_RESIDUAL, out=y2)      # no bias, no gate
+    assert rel_err(y2, x + a.float() @ w.float().T) < TOL_F32_OUT
+
+
+def test_gemm_strided_operands_fused_qkv_layout():
+    from ltx2_b200 import ops
+    M, D = 300, 256
+    a = rnd(M, D, seed=9, dtype=torch.bfloat16)
+    wqkv = rnd(3 * D, D, seed=10, std=D ** -0.5, dtype=torch.bfloat16)
+    out = torch.zeros(M, 3 * D, device=dev(), dtype=torch.bfloat16)
+    ops.gemm(a, wqkv, None, mode=ops.EPI_BF16, out=out)
+    assert rel_err(out.float(), a.float() @ wqkv.float().T) < TOL_BF16_OUT
+    # second GEMM reads a column slice (row pitch 3D) as its A operand
+    wo = rnd(D, D, seed=11, std=D ** -0.5, dtype=torch.bfloat16)
+    k_slice = out[:, D:2 * D]
+    assert not k_slice.is_contiguous()
+    y = torch.empty(M, D, device=dev(), dtype=torch.bfloat16)
+    from ltx2_b200._lib import lib, ptr, stream_ptr, check
+    import ctypes as C
+    check(lib().ltx2_gemm_bf16(ptr(k_slice), C.c_int64(3 * D), ptr(wo), C.c_int64(D), M, D, D, 0, None, ptr(y),
+                               C.c_int64(D), None, C.c_int64(0), None, C.c_float(1.0), stream_ptr()))
+    assert rel_err(y.float(), k_slice.float() @ wo.float().T) < TOL_BF16_OUT
+
+
+def _attn_ref(q, k, v, gate=None):
+    B, H, Tq, Dh = q.shape
+    s = (q.float() @ k.float().transpose(-1, -2)) / math.sqrt(Dh)
+    o = torch.softmax(s, -1) @ v.float()                      # (B,H,Tq,Dh)
+    lse = torch.logsumexp(s, -1)
+    if gate is not None:
+        o = o * (2 * torch.sigmoid(gate)).reshape(B, Tq, H).permute(0, 2, 1)[..., None]
+    return o.permute(0, 2, 1, 3).reshape(B, Tq, H * Dh), lse
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,Dh", [(1, 2, 128, 128, 128), (1, 2, 256, 384, 128), (2, 3, 200, 333, 128),
+                                          (1, 4, 130, 65, 64), (1, 2, 65, 520, 64), (1, 2, 864, 864, 128),
+                                          (1, 32, 3456, 3456, 128), (1, 8, 384, 1024, 128)])
+def test_attention(B, H, Tq, Tk, Dh):
+    from ltx2_b200 import ops
+    q = rnd(B, H, Tq, Dh, seed=20, dtype=torch.bfloat16)
+    k = rnd(B, H, Tk, Dh, seed=21, dtype=torch.bfloat16)
+    v = rnd(B, H, Tk, Dh, seed=22, dtype=torch.bfloat16)
+    Tp = (Tk + 63) // 64 * 64
+    vt = torch.zeros(B, H, Dh, Tp, device=dev(), dtype=torch.bfloat16)
+    vt[..., :Tk] = v.transpose(-1, -2)
+    out, lse = ops.attention(q, k, vt.contiguous(), Tk, want_lse=True)
+    ref, ref_lse = _attn_ref(q, k, v)
+    # P is rounded to bf16 before P*V and the output is bf16: ~2^-8 relative
+    assert rel_err(out.float(), ref) < 1.2e-2
+    assert float((lse - ref_lse).abs().max()) < 2e-3
+
+
+def test_attention_sharp_softmax_and_gate():
+    from ltx2_b200 import ops
+    B, H, Tq, Tk, Dh = 1, 2, 256, 300, 128
+    q = rnd(B, H, Tq, Dh, seed=23, std=4.0, dtype=torch.bfloat16)     # large logits -> running max moves a lot
+    k = rnd(B, H, Tk, Dh, seed=24, std=2.0, dtype=torch.bfloat16)
+    v = rnd(B, H, Tk, Dh, seed=25, dtype=torch.bfloat16)
+    gate = rnd(B * Tq, H, seed=26)
+    Tp = (Tk + 63) // 64 * 64
+    vt = torch.zeros(B, H, Dh, Tp, device=dev(), dtype=torch.bfloat16)
+    vt[..., :Tk] = v.transpose(-1, -2)
+    out = ops.attention(q, k, vt, Tk, gate_logits=gate)
+    ref, _ = _attn_ref(q, k, v, gate)
+    assert rel_err(out.float(), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("D", [128, 512, 4096])
+def test_norm_modulate(D):
+    from ltx2_b200 import ops
+    from oracle import dit_oracle as O
+    M = 77
+    x = rnd(M, D, seed=30, std=3.0)
+    mod = rnd(4, 9, D, seed=31, std=0.3)
+    cls = (torch.arange(M, device=dev()) % 4).to(torch.int32)
+    shift, scale = mod[cls.long(), 3], mod[cls.long(), 4]
+    ref = O.rms_norm(x) * (1 + scale) + shift
+    out = ops.norm_modulate(x, kind=ops.NORM_RMS, mod=mod, shift_row=3, scale_row=4, row_cls=cls)
+    assert rel_err(out.float(), ref) < 4e-3
+    assert rel_err(ops.norm_modulate(x, kind=ops.NORM_RMS).float(), O.rms_norm(x)) < 4e-3
+    ln = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[cls.long(), 1]) + mod[cls.long(), 0]
+    out = ops.norm_modulate(x, kind=ops.NORM_LAYER, mod=mod, shift_row=0, scale_row=1, row_cls=cls)
+    assert rel_err(out.float(), ln) < 4e-3
+    xb = x.to(torch.bfloat16)
+    out = ops.norm_modulate(xb, kind=ops.NORM_NONE, mod=mod, shift_row=0, scale_row=1, row_cls=cls)
+    assert rel_err(out.float(), xb.float() * (1 + mod[cls.long(), 1]) + mod[cls.long(), 0]) < 4e-3
+
+
+def test_rope_tables_match_reference_golden():
+    from ltx2_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "rope.npz"))
+    pos = torch.from_numpy(g["positions"]).to(dev())
+    cos, sin = ops.rope_tables(pos, 4096, (20, 2048, 2048))
+    ref_c = torch.from_numpy(g["cos"]).permute(0, 2, 1, 3).reshape(cos.shape).to(dev())   # (B,H,T,64)->(B,T,2048)
+    ref_s = torch.from_numpy(g["sin"]).permute(0, 2, 1, 3).reshape(sin.shape).to(dev())
+    # fp32 arguments up to ~1.5e4 rad: an ulp of the frequency grid moves cos/sin by ~1e-3
+    assert float((cos - ref_c).abs().max()) < 1.5e-2 and float((sin - ref_s).abs().max()) < 1.5e-2
+    assert float((cos - ref_c).abs().mean()) < 2e-4
+    c1, s1 = ops.rope_tables(pos[:, 0:1].contiguous(), 2048, (20,))
+    r1 = torch.from_numpy(g["cos_1d"]).permute(0, 2, 1, 3).reshape(c1.shape).to(dev())
+    assert float((c1 - r1).abs().max()) < 1.5e-2
+
+
+@pytest.mark.parametrize("H,Dh", [(4, 128), (32, 128), (4, 64)])
+def test_headnorm_rope_and_v_transpose(H, Dh):
+    from ltx2_b200 import ops
+    from oracle import dit_oracle as O
+    B, T = 2, 70
+    inner = H * Dh
+    qkv = rnd(B * T, 3 * inner, seed=40, dtype=torch.bfloat16)
+    w = 1 + 0.1 * rnd(inner, seed=41)
+    cos = torch.cos(rnd(B, T, inner // 2, seed=42, std=3.0))
+    sin = torch.sin(rnd(B, T, inner // 2, seed=42, std=3.0))
+    q = qkv[:, :inner]
+    out = ops.headnorm_rope(q, w, B, T, H, Dh, cos, sin)
+    cos_h = cos.reshape(B, T, H, Dh // 2).permute(0, 2, 1, 3).cpu()
+    sin_h = sin.reshape(B, T, H, Dh // 2).permute(0, 2, 1, 3).cpu()
+    qn = O.rms_norm(q.float().cpu().reshape(B, T, inner), w.cpu())
+    ref = O.apply_split_rope(qn, cos_h, sin_h).reshape(B, T, H, Dh).permute(0, 2, 1, 3)
+    assert rel_err(out.float().cpu(), ref) < 4e-3
+    out = ops.headnorm_rope(q, w, B, T, H, Dh)                      # no RoPE (cross-attention)
+    assert rel_err(out.float().cpu(), qn.reshape(B, T, H, Dh).permute(0, 2, 1, 3)) < 4e-3
+    v = qkv[:, 2 * inner:]
+    vt = ops.v_transpose(v, B, T, H, Dh)
+    ref_v = v.reshape(B, T, H, Dh).permute(0, 2, 3, 1)
+    assert torch.equal(vt[..., :T], ref_v)
+
+
+def test_timestep_embedding_pieces():
+    from ltx2_b200 import ops
+    from oracle import dit_oracle as O
+    t = torch.tensor([1.0, 0.725, 0.05], device=dev())
+    s = ops.timestep_sinusoid(t, 1000.0)
+    ref = O.sinusoid_dit(t.cpu() * 1000.0)
+    assert float((s.cpu() - ref).abs().max()) < 2e-4      # fp32 sin/cos of arguments up to 1000 rad
+    x = rnd(3, 512, seed=50)
+    w = rnd(1536, 512, seed=51, std=512 ** -0.5, dtype=torch.bfloat16)
+    b = rnd(1536, seed=52)
+    y = ops.small_linear(x, w, b, act_in=1)
+    ref = torch.nn.functional.silu(x) @ w.float().T + b
+    assert rel_err(y, ref) < 1e-5
+
+
+def test_x0_and_reference_metal_kernels():
+    from ltx2_b200 import ops
+    from oracle import dit_oracle as O
+    lat, vel = rnd(50, 128, seed=60), rnd(50, 128, seed=61)
+    t = torch.rand(50, device=dev())
+    assert torch.allclose(ops.x0_from_velocity(lat, vel, t), lat - t[:, None] * vel, atol=1e-6)
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2), (torch.float16, 2e-3)):
+        a, b = rnd(3, 7, 64, seed=62, dtype=dt), rnd(3, 7, 64, seed=63, dtype=dt)
+        assert rel_err(ops.silu_mul(a, b).float(), O.silu_mul(a.float(), b.float())) < tol
+        assert rel_err(ops.gelu_mul(a, b).float(), O.gelu_mul(a.float(), b.float())) < tol
+        th = torch.rand(3, 7, 32, device=dev()) * 6.28
+        cos, sin = torch.cos(th).repeat_interleave(2, -1).to(dt), torch.sin(th).repeat_interleave(2, -1).to(dt)
+        assert rel_err(ops.interleaved_rope(a, cos, sin).float(),
+                       O.interleaved_rope(a.float(), cos.float(), sin.float())) < tol
+    # empty input (the reference asserts equal shapes and launches a zero-size grid)
+    e = torch.empty(0, 8, device=dev())
+    assert ops.silu_mul(e, e).shape == (0, 8)
+    with pytest.raises(AssertionError):
+        ops.silu_mul(rnd(2, 4), rnd(2, 5))
