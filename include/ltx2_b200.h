@@ -118,6 +118,12 @@ int ltx2_dit_forward(LtxDit* dit, const LtxModalityView* video, const LtxModalit
 /* OneStagePipeline pokes block._cross_attn_scale (one_stage.py:207-222; transformer.py:526-528). */
 int ltx2_dit_set_cross_attn_scale(LtxDit* dit, int32_t block, float scale /* NaN = unset */);
 
+/* Measurement hooks (bench.py): per-class CUDA-event timing of one forward (class 0 = GEMM launches,
+ * 1 = attention launches) and the number of kernels this library has launched since load. */
+int ltx2_dit_set_profile(LtxDit* dit, int32_t on);
+int ltx2_dit_profile_read(LtxDit* dit, double* ms_out, double* flops_out, int64_t* launches_out, int32_t n_classes);
+int64_t ltx2_launch_count(void);
+
 /* Context-parallel (ring attention) setup, SURVEY.md section 8(e).  rank/world describe this
  * process' slice of the token axis; the K/V exchange itself is driven by the host layer
  * (torch.distributed NCCL P2P) through ltx2_dit_forward_cp hooks -- see DESIGN.md. */

@@ -323,6 +323,7 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
   attention_kernel<DH><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
       mq, mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk, scale * kLog2e, scale, gate_logits, lse_out);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 

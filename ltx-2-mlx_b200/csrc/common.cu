@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -96,6 +97,10 @@ int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, 
   *out = m;
   return LTX2_OK;
 }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
   static int n = 0;

@@ -57,6 +57,10 @@ int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, 
 
 int num_sms();
 
+// number of kernels launched by this library since load (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+int64_t launch_count();
+
 // ---------------------------------------------------------------------------------
 // device-side PTX wrappers
 // ---------------------------------------------------------------------------------

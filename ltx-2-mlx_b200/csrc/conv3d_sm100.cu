@@ -1,0 +1,295 @@
+// 3x3x3 convolution of the video-VAE decoder as an implicit GEMM on tcgen05 tensor cores.
+//
+// Reference op replaced: Conv3dSimple.__call__ (model/video_vae/simple_decoder.py:90-180), i.e. 3 x mx.conv2d
+// per conv over a reflect(H,W)/replicate(T)-padded input, plus what follows it in the decoder:
+//   bias (:178), ResBlock residual add (:240), DepthToSpaceUpsample3d rearrange + first-frame drop + tiled
+//   residual (:274-313), conv_out + unpatchify (:545-552, ops.py:70-131).
+//
+// Data layout: activations are channels-last bf16 [B, T, H, W, C].  The producer of a conv input writes it
+// already PADDED ([B, T+2, H+2, W+2, C], vae_rowops.cu), so every filter tap is a plain shifted TMA box:
+//   A tile (128 output positions = 16 rows x 8 columns of one frame) for tap (kt,kh,kw), channels [c0,c0+64):
+//     4-D box {64, 8, 16, 1} at {c0, w0+kw, h0+kh, b*(T+2)+t+kt}  ->  128 x 128 B rows, 128B swizzle (K-major)
+//   B tile: weights re-laid at load time as [C_out, 27*C_in] (tap-major, channel-minor) -> 2-D box {64, BN}
+// so the main loop is the GEMM's (gemm_sm100.cu): TMA producer warp, single-thread tcgen05.mma issuer with fp32
+// accumulators in TMEM (double-buffered), 4 epilogue warps.  K = 27*C_in.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ltx2 {
+
+namespace {
+
+constexpr int CBM = 128, CBK = 64, CTW = 8, CTH = 16;
+constexpr int kConvThreads = 192;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kABytes = CBM * CBK * 2;
+  static constexpr int kBBytes = BN * CBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_w = (p.W + CTW - 1) / CTW;
+  const int tiles_h = (p.H + CTH - 1) / CTH;
+  const int num_m = p.B * p.T * tiles_h * tiles_w;
+  const int num_n = (p.Cout_pad + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int cchunks = p.Cin / CBK;
+  const int num_kb = 27 * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % num_m, nt = tile / num_m;
+        const int wx = mt % tiles_w;
+        const int hy = (mt / tiles_w) % tiles_h;
+        const int bt = mt / (tiles_w * tiles_h);          // b*T + t
+        const int b = bt / p.T, t = bt % p.T;
+        const int plane0 = b * (p.T + 2) + t;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cchunks, cc = kb % cchunks;
+          const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw,
+                      hy * CTH + kh, plane0 + kt);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * CBK, nt * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(CBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < CBK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int sp = p.ft * p.fh * p.fw;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile % num_m, nt = tile / num_m;
+      const int wx = mt % tiles_w;
+      const int hy = (mt / tiles_w) % tiles_h;
+      const int bt = mt / (tiles_w * tiles_h);
+      const int b = bt / p.T, t = bt % p.T;
+      const int r = quarter * 32 + lane;
+      const int h = hy * CTH + r / CTW, w = wx * CTW + r % CTW;
+      const bool pos_ok = h < p.H && w < p.W;
+      const int64_t pos = ((static_cast<int64_t>(bt) * p.H + h) * p.W + w);     // unpadded NDHWC position index
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(t_row + c, rr);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c;
+        if (!pos_ok || col0 >= p.Cout_pad) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          v[j] = __uint_as_float(rr[j]) + bb.x;
+          v[j + 1] = __uint_as_float(rr[j + 1]) + bb.y;
+          v[j + 2] = __uint_as_float(rr[j + 2]) + bb.z;
+          v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
+        }
+        if (p.mode == CONV_EPI_PLAIN || p.mode == CONV_EPI_RESIDUAL) {
+          if (p.mode == CONV_EPI_RESIDUAL) {
+            const __nv_bfloat16* rs = p.residual + pos * p.Cout + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(hh[q]);
+                v[j + 2 * q] += f.x;
+                v[j + 2 * q + 1] += f.y;
+              }
+            }
+          }
+          __nv_bfloat16* o = p.out + pos * p.Cout + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            q.x = pack_bf16x2(v[j], v[j + 1]);
+            q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = q;
+          }
+        } else if (p.mode == CONV_EPI_D2S) {
+          // weight rows were permuted at load time to (sub-position major, output channel minor):
+          // col = sub * Cf + c, sub = (a*fh + bb)*fw + d  ->  32 consecutive columns share one output pixel.
+          const int Cf = p.Cout / sp;
+          const int sub = col0 / Cf, c0 = col0 % Cf;
+          const int a = sub / (p.fh * p.fw), bb2 = (sub / p.fw) % p.fh, d = sub % p.fw;
+          const int drop = (p.ft > 1) ? 1 : 0;
+          const int to = t * p.ft + a - drop;
+          if (to < 0) continue;
+          const int To = p.T * p.ft - drop, Ho = p.H * p.fh, Wo = p.W * p.fw;
+          if (p.c_d2s > 0) {
+            // residual = depth_to_space(x) tiled along channels: source channel (c % c_d2s)*sp + sub of THIS position
+            const __nv_bfloat16* rs = p.residual + pos * p.Cin;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rs[((c0 + j) % p.c_d2s) * sp + sub]);
+          }
+          __nv_bfloat16* o = p.out + (((static_cast<int64_t>(b) * To + to) * Ho + (h * p.fh + bb2)) * Wo + (w * p.fw + d)) * Cf + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            q.x = pack_bf16x2(v[j], v[j + 1]);
+            q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = q;
+          }
+        } else {  // CONV_EPI_UNPATCHIFY: col = (ch*4 + rw)*4 + rh -> out_f32[b, ch, t, h*4+rh, w*4+rw]
+          const int Hp = p.H * 4, Wp = p.W * 4;
+#pragma unroll
+          for (int j = 0; j < 32; j += 16) {
+            const int ch = (col0 + j) / 16;
+            if (ch >= p.Cout / 16) break;
+            float* o = p.out_f32 + ((static_cast<int64_t>(b) * (p.Cout / 16) + ch) * p.T + t) * Hp * static_cast<int64_t>(Wp);
+#pragma unroll
+            for (int rh = 0; rh < 4; ++rh)
+              *reinterpret_cast<float4*>(o + static_cast<int64_t>(h * 4 + rh) * Wp + w * 4) =
+                  make_float4(v[j + rh], v[j + 4 + rh], v[j + 8 + rh], v[j + 12 + rh]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& tx, const CUtensorMap* tw, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(conv3d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.B * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW) * ((p.Cout_pad + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3d_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tx, *tw, p);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+}  // namespace
+
+int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p, cudaStream_t stream) {
+  LTX2_REQUIRE(p.Cin % 64 == 0, "conv3d: C_in=%d must be a multiple of 64", p.Cin);
+  LTX2_REQUIRE(p.Cout_pad % 32 == 0 && p.Cout_pad >= p.Cout, "conv3d: padded C_out=%d invalid", p.Cout_pad);
+  LTX2_REQUIRE(p.B > 0 && p.T > 0 && p.H > 0 && p.W > 0, "conv3d: empty input");
+  CUtensorMap tx;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(p.Cin), static_cast<uint64_t>(p.W + 2), static_cast<uint64_t>(p.H + 2),
+                        static_cast<uint64_t>(p.B) * (p.T + 2)};
+    uint64_t str[3] = {static_cast<uint64_t>(p.Cin) * 2, static_cast<uint64_t>(p.W + 2) * p.Cin * 2,
+                       static_cast<uint64_t>(p.H + 2) * (p.W + 2) * p.Cin * 2};
+    uint32_t box[4] = {CBK, CTW, CTH, 1};
+    LTX2_PROPAGATE(make_tensor_map_bf16(&tx, x_padded, 4, dims, str, box));
+  }
+  int bn = 256;
+  if (p.Cout_pad % 256 != 0) bn = 128;
+  if (p.Cout_pad % 128 != 0) bn = 64;
+  if (p.Cout_pad % 64 != 0) bn = 32;
+  if (p.mode == CONV_EPI_D2S) {
+    const int Cf = p.Cout / (p.ft * p.fh * p.fw);
+    LTX2_REQUIRE(Cf % 32 == 0, "conv3d: depth-to-space needs C_out/stride_product %% 32 == 0 (got %d)", Cf);
+  }
+  const CUtensorMap* tw;
+  LTX2_PROPAGATE(get_tensor_map_2d(&tw, w_packed, p.Cout_pad, static_cast<uint64_t>(27) * p.Cin,
+                                   static_cast<uint64_t>(27) * p.Cin, bn));
+  switch (bn) {
+    case 256: return launch_conv<256>(tx, tw, p, stream);
+    case 128: return launch_conv<128>(tx, tw, p, stream);
+    case 64: return launch_conv<64>(tx, tw, p, stream);
+    default: return launch_conv<32>(tx, tw, p, stream);
+  }
+}
+
+}  // namespace ltx2

@@ -138,7 +138,43 @@ struct StreamBuf {
 
 using namespace ltx2;
 
+// Optional per-kernel-class timing (bench.py's roofline leg): CUDA events around every GEMM and attention
+// launch of one forward, on the launching stream.  Off by default -- the timed bench steps run without it.
+struct DitProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> events;
+  size_t used = 0;
+  struct Rec { int cat; double work; size_t e0; };
+  std::vector<Rec> recs;
+  size_t begin(int cat, double work, cudaStream_t st) {
+    if (used + 2 > events.size()) {
+      const size_t old = events.size();
+      events.resize(old + 512);
+      for (size_t i = old; i < events.size(); ++i) cudaEventCreate(&events[i]);
+    }
+    recs.push_back({cat, work, used});
+    cudaEventRecord(events[used], st);
+    used += 2;
+    return used - 2;
+  }
+  void end(size_t e0, cudaStream_t st) { cudaEventRecord(events[e0 + 1], st); }
+};
+static thread_local DitProfiler* g_prof = nullptr;
+struct ProfScope {
+  size_t e0 = 0;
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cat, double work, cudaStream_t s) : st(s), on(g_prof && g_prof->on) {
+    if (on) e0 = g_prof->begin(cat, work, st);
+  }
+  ~ProfScope() {
+    if (on) g_prof->end(e0, st);
+  }
+};
+enum { PROF_GEMM = 0, PROF_ATTN = 1 };
+
 struct LtxDit {
+  DitProfiler prof;
   LtxDitConfig cfg;
   int D = 0, Da = 0, n_ada = 6;
   std::unordered_map<std::string, Slot> slots;
@@ -427,7 +463,9 @@ inline int linear_bf16(const bf16* A, int64_t lda, const LinearW& L, int M, bf16
   ep.bias = L.b + row_off;
   ep.out = out;
   ep.ldo = ldo;
-  return gemm_bf16(A, lda, L.w + size_t(row_off) * L.in, L.in, M, n_rows < 0 ? L.out : n_rows, L.in, ep, st);
+  const int N = n_rows < 0 ? L.out : n_rows;
+  ProfScope ps(PROF_GEMM, 2.0 * M * double(N) * L.in, st);
+  return gemm_bf16(A, lda, L.w + size_t(row_off) * L.in, L.in, M, N, L.in, ep, st);
 }
 
 inline int linear_residual(const bf16* A, int64_t lda, const LinearW& L, int M, float* x, int64_t ldx,
@@ -441,6 +479,7 @@ inline int linear_residual(const bf16* A, int64_t lda, const LinearW& L, int M, 
   ep.gate_stride = gate_stride;
   ep.row_cls = row_cls;
   ep.alpha = alpha;
+  ProfScope ps(PROF_GEMM, 2.0 * M * double(L.out) * L.in, st);
   return gemm_bf16(A, lda, L.w, L.in, M, L.out, L.in, ep, st);
 }
 
@@ -450,6 +489,7 @@ inline int linear_f32(const bf16* A, int64_t lda, const LinearW& L, int M, float
   ep.bias = L.b;
   ep.out = out;
   ep.ldo = ldo;
+  ProfScope ps(PROF_GEMM, 2.0 * M * double(L.out) * L.in, st);
   return gemm_bf16(A, lda, L.w, L.in, M, L.out, L.in, ep, st);
 }
 
@@ -510,6 +550,7 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     }
     gl = sb.gate_logits;
   }
+  ProfScope ps(PROF_ATTN, 4.0 * B * H * double(c.Tq) * c.Tk * Dh, st);
   return attention_bf16(sb.qh, sb.kh, sb.vt, sb.attn, B, H, c.Tq, c.Tk, Tkp, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr,
                         st);
 }
@@ -570,6 +611,7 @@ int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out) {
 
 void ltx2_dit_destroy(LtxDit* e) {
   if (!e) return;
+  for (auto ev : e->prof.events) cudaEventDestroy(ev);
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   if (e->fg_video) cudaFree(e->fg_video);
@@ -871,6 +913,9 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   }
   LtxDitSkip sk = {0, 0, 0, 0};
   if (skip) sk = *skip;
+  g_prof = &e->prof;
+  e->prof.used = 0;
+  e->prof.recs.clear();
 
   std::vector<float> cls_v, cls_a;
   std::vector<int> rc_v, rc_a;
@@ -942,3 +987,28 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   if (has_audio) LTX2_PROPAGATE(run_head(e, ab, e->aw, *audio, x0, out_audio, st));
   return LTX2_OK;
 }
+
+extern "C" int ltx2_dit_set_profile(LtxDit* e, int32_t on) {
+  LTX2_REQUIRE(e != nullptr, "dit_set_profile: null handle");
+  e->prof.on = on != 0;
+  return LTX2_OK;
+}
+
+// After a profiled forward: synchronises the device and returns, per class (0 = GEMM, 1 = attention), the summed
+// kernel time in ms, the summed algorithmic FLOPs and the launch count.
+extern "C" int ltx2_dit_profile_read(LtxDit* e, double* ms_out, double* flops_out, int64_t* launches_out,
+                                     int32_t n_classes) {
+  LTX2_REQUIRE(e && ms_out && flops_out && launches_out && n_classes >= 2, "dit_profile_read: bad argument");
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) { ms_out[i] = 0; flops_out[i] = 0; launches_out[i] = 0; }
+  for (auto& r : e->prof.recs) {
+    float ms = 0.f;
+    LTX2_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof.events[r.e0], e->prof.events[r.e0 + 1]));
+    ms_out[r.cat] += ms;
+    flops_out[r.cat] += r.work;
+    launches_out[r.cat] += 1;
+  }
+  return LTX2_OK;
+}
+
+extern "C" int64_t ltx2_launch_count(void) { return ltx2::launch_count(); }

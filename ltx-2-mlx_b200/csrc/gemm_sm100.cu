@@ -219,6 +219,7 @@ int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int 
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ta, *tb, M, N, K, ep);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 

@@ -103,6 +103,56 @@ int gelu_mul(const void* a, const void* b, void* out, int64_t n, int dtype, cuda
 int interleaved_rope(const void* x, const void* cos, const void* sin, void* out, int64_t n, int dtype,
                      cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------
+// video-VAE decoder kernels (conv3d_sm100.cu, vae_rowops.cu)
+// ---------------------------------------------------------------------------------
+enum ConvEpilogueMode {
+  CONV_EPI_PLAIN = 0,       // out[B,T,H,W,Cout] bf16 = acc + bias
+  CONV_EPI_RESIDUAL = 1,    // ... + residual[B,T,H,W,Cout] (may alias out)
+  CONV_EPI_D2S = 2,         // depth-to-space scatter (+ tiled d2s residual gathered from the conv input)
+  CONV_EPI_UNPATCHIFY = 3,  // conv_out: fp32 [B, Cout/16, T, 4H, 4W]
+};
+
+struct ConvParams {
+  int B = 0, T = 0, H = 0, W = 0;      // output (= unpadded input) grid
+  int Cin = 0, Cout = 0, Cout_pad = 0; // Cout_pad: rows of the packed weight / bias (multiple of 32)
+  int mode = CONV_EPI_PLAIN;
+  const float* bias = nullptr;          // [Cout_pad]
+  __nv_bfloat16* out = nullptr;
+  float* out_f32 = nullptr;
+  const __nv_bfloat16* residual = nullptr;   // RESIDUAL: [.,Cout];  D2S: the UNPADDED conv input [.,Cin]
+  int ft = 1, fh = 1, fw = 1;           // D2S strides
+  int c_d2s = 0;                        // D2S residual: Cin / (ft*fh*fw); 0 = no residual
+};
+
+// x_padded: bf16 [B, T+2, H+2, W+2, Cin]; w_packed: bf16 [Cout_pad, 27*Cin] (tap-major, channel-minor)
+int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p, cudaStream_t stream);
+
+// PyTorch conv weight [Cout, Cin, 3,3,3] (any float dtype) -> packed bf16 [Cout_pad, 27*Cin]; row permutation for
+// depth-to-space convs: packed row (sub*Cf + c) <- source row (c*sp + sub); rows >= Cout are zero.  Same for bias.
+int pack_conv_weight(const void* w, int dtype, void* packed, int Cout, int Cout_pad, int Cin, int sp,
+                     cudaStream_t stream);
+int pack_conv_bias(const void* b, int dtype, float* packed, int Cout, int Cout_pad, int sp, cudaStream_t stream);
+
+// latent NCDHW (fp32/bf16/fp16) -> padded channels-last bf16 [B,T+2,H+2,W+2,C] with de-normalisation
+// (x*std+mean, simple_decoder.py:492-493) and optional noise blend (:496-498): noise*s + (1-s)*x
+int latent_to_padded(const void* latent, int dtype, const float* std_, const float* mean, const float* noise,
+                     float noise_scale, void* out, int B, int C, int T, int H, int W, int causal,
+                     cudaStream_t stream);
+
+// x [B,T,H,W,C] bf16 -> padded [B,T+2,H+2,W+2,C] bf16 applying (when act != 0)
+//   silu(pixel_norm(x) * (1 + scale[b]) + shift[b])   (simple_decoder.py:229-231, 339-342, 528-542)
+// mod: fp32 [B, mod_stride] with rows shift at shift_off and scale at scale_off; reflect pad H/W, replicate pad T.
+int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, int act, const float* mod,
+                 int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream);
+
+// decode_latent post-processing (simple_decoder.py:749-798)
+//   blend: dst[:, :, t0+i] = dst*(1-r_i) + src[:, :, i]*r_i for i < overlap (r = linspace(0,1,overlap)), then copy tail
+int blend_chunk(float* dst, const float* src, int BC, int T_dst, int T_src, int HW, int t0, int overlap,
+                cudaStream_t stream);
+//   video [1,3,T,H,W] fp32 in [-1,1] -> uint8 [T,H,W,3]
+int video_to_uint8(const float* video, uint8_t* out, int T, int H, int W, cudaStream_t stream);
+
 // dtype codes shared with the C ABI
 enum { LTX2_F32 = 0, LTX2_BF16 = 1, LTX2_F16 = 2 };
 

@@ -404,6 +404,7 @@ int norm_modulate(const void* x, int x_is_bf16, int64_t ldx, void* out, int64_t 
                                                                norm_kind, eps, mod, mod_stride, shift_off, scale_off,
                                                                row_cls);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -416,6 +417,7 @@ int headnorm_rope(const void* in, int64_t ld, const float* weight, const float* 
   headnorm_rope_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, weight, cos,
                                                           sin, reinterpret_cast<__nv_bfloat16*>(out), T, H, Dh, eps);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -426,6 +428,7 @@ int v_transpose(const void* v, int64_t ld, void* vt, int B, int T, int Tp, int H
   v_transpose_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(v), ld,
                                                reinterpret_cast<__nv_bfloat16*>(vt), T, Tp, H, Dh);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -436,6 +439,7 @@ int small_linear(const float* x, int R, int K, const void* W, const float* bias,
   small_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(x, R, K, reinterpret_cast<const __nv_bfloat16*>(W), bias, y, N,
                                                        act_in);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -447,12 +451,14 @@ int rowdot_bf16(const void* x, int64_t ldx, const void* W, const float* bias, fl
   rowdot_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(W), bias, out, M, H, K);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
 int timestep_sinusoid(const float* t, int R, float multiplier, float* out256, cudaStream_t stream) {
   timestep_sinusoid_kernel<<<(R * 128 + 127) / 128, 128, 0, stream>>>(t, R, multiplier, out256);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -468,6 +474,7 @@ int build_modulation_ex(const float* tables, int64_t table_layer_stride, const f
                                                                emb_row_stride, out, out_layer_stride, out_cls_stride,
                                                                L, C, R, D);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -483,6 +490,7 @@ int rope_tables_dev(const float* positions, int B, int pos_dims, int n_dims, int
   rope_tables_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(positions, pos_dims, n_dims, T, half, n_freq,
                                                                                    freq_grid_dev, mp, cos, sin, total);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -492,6 +500,7 @@ int x0_from_velocity(const float* latent, const float* velocity, const float* t_
   if (n == 0) return LTX2_OK;
   x0_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(latent, velocity, t_row, x0, n, C);
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -506,6 +515,7 @@ int cast_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStrea
     default: set_error("cast_to_bf16: bad dtype %d", src_dtype); return LTX2_ERR_INVALID;
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -519,6 +529,7 @@ int cast_to_f32(const void* src, int src_dtype, float* dst, int64_t n, cudaStrea
     default: set_error("cast_to_f32: bad dtype %d", src_dtype); return LTX2_ERR_INVALID;
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -544,6 +555,7 @@ static int act_mul(const void* a, const void* b, void* out, int64_t n, int dtype
     default: set_error("act_mul: bad dtype %d", dtype); return LTX2_ERR_INVALID;
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 
@@ -577,6 +589,7 @@ int interleaved_rope(const void* x, const void* c, const void* s, void* out, int
     default: set_error("interleaved_rope: bad dtype %d", dtype); return LTX2_ERR_INVALID;
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return LTX2_OK;
 }
 

@@ -21,7 +21,8 @@ NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
 def _cuda(*ts):
     for t in ts:
         if t is not None:
-            assert t.is_cuda and t.is_contiguous(), "ltx2_b200 ops need contiguous CUDA tensors"
+            ok = t.is_contiguous() or (t.ndim == 2 and t.stride(1) == 1)     # row-pitched 2-D views are fine
+            assert t.is_cuda and ok, "ltx2_b200 ops need CUDA tensors with a contiguous innermost dimension"
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, mode: int = EPI_BF16,
