@@ -129,6 +129,55 @@ int64_t ltx2_launch_count(void);
  * (torch.distributed NCCL P2P) through ltx2_dit_forward_cp hooks -- see DESIGN.md. */
 
 /* =====================================================================================
+ * Video-VAE decoder engine -- replaces LTX_2_MLX/model/video_vae/simple_decoder.py:
+ * SimpleVideoDecoder (:364-563), load_vae_decoder_weights (:566-673) and the device work of
+ * decode_latent (:676-800).  Called by pipelines as `decode_latent(latent, decoder[, timestep])`
+ * (pipelines/distilled.py:496, scripts/generate.py:2085) and `decoder_fn(tile, timestep=...)`
+ * (model/video_vae/tiling.py:363).
+ * ===================================================================================== */
+
+typedef struct LtxVae LtxVae;
+
+/* one entry of the reversed decoder_blocks list (simple_decoder.py:403-427) */
+typedef struct LtxVaeStage {
+  int32_t kind;        /* 0 = "res_x" group, 1 = "compress_*" depth-to-space upsample */
+  int32_t num_layers;  /* res_x: number of ResBlock3d */
+  int32_t stride_t, stride_h, stride_w; /* upsample: (2,2,2) all, (2,1,1) time, (1,2,2) space */
+  int32_t multiplier;  /* upsample: out_channels_reduction_factor */
+  int32_t residual;    /* upsample: add depth-to-space residual */
+} LtxVaeStage;
+
+typedef struct LtxVaeConfig {
+  int32_t num_stages;
+  LtxVaeStage stages[16];          /* execution order (latent -> pixels) */
+  int32_t base_channels;           /* 128; feature channels start at 8x (multiple of 64 required) */
+  int32_t latent_channels;         /* 128 */
+  int32_t timestep_conditioning;   /* V2.0-style decoders */
+} LtxVaeConfig;
+
+int ltx2_vae_create(const LtxVaeConfig* cfg, LtxVae** out);
+void ltx2_vae_destroy(LtxVae* vae);
+/* `key` is the CHECKPOINT key the reference loader reads, e.g. "vae.decoder.up_blocks.0.res_blocks.1.conv1.conv.weight"
+ * (simple_decoder.py:592-671).  Conv weights arrive in PyTorch layout [C_out, C_in, 3, 3, 3]. */
+int ltx2_vae_set_weight(LtxVae* vae, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                        int32_t ndim, void* stream);
+int ltx2_vae_missing_weights(LtxVae* vae, char* names_out, int64_t names_cap);
+int ltx2_vae_output_shape(LtxVae* vae, const int64_t in_shape[5], int64_t out_shape[5]);
+
+/* SimpleVideoDecoder.__call__ (:446-563).  latent [B,128,T,H,W] (NCDHW, dtype code) -> out [B,3,T',32H,32W] fp32.
+ * timestep < 0 means None.  noise (fp32, latent-shaped, N(0,1)) is blended as noise*s + (1-s)*x when
+ * timestep conditioning is on (:496-498); pass NULL or s = 0 for the deterministic decode the parity test uses. */
+int ltx2_vae_decode(LtxVae* vae, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
+                    float noise_scale, const float* noise, int32_t causal, float* out, void* stream);
+
+/* decode_latent's chunk stitching (:749-790): dst [BC,T_dst,HW] <- cross-fade of src [BC,T_src,HW] placed at frame t0,
+ * linear ramp over the first `overlap` frames, plain copy after; and the uint8 conversion (:793-798):
+ * video [1,3,T,H,W] fp32 in [-1,1] -> uint8 [T,H,W,3]. */
+int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, int32_t T_src, int32_t HW, int32_t t0,
+                     int32_t overlap, void* stream);
+int ltx2_video_to_uint8(const float* video, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream);
+
+/* =====================================================================================
  * Per-op entry points (unit parity against the oracle)
  * ===================================================================================== */
 

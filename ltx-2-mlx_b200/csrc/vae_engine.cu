@@ -1,0 +1,464 @@
+// Video-VAE decoder engine: packed conv weights + activation workspace + the launch sequence of one
+// SimpleVideoDecoder forward.
+//
+// Reference path replaced (LTX_2_MLX/model/video_vae/simple_decoder.py):
+//   SimpleVideoDecoder.__init__/__call__ (:364-563), ResBlockGroup/ResBlock3d (:183-240, 316-336),
+//   DepthToSpaceUpsample3d (:243-313), TimestepEmbedder (:42-59), load_vae_decoder_weights key names (:566-673).
+//
+// HBM layout: activations channels-last bf16 [B,T,H,W,C]; every conv input is materialised PADDED
+// ([B,T+2,H+2,W+2,C]) by the kernel that also applies pixel-norm/scale-shift/SiLU, so the conv's TMA boxes need no
+// boundary logic.  Conv weights are packed once at load time as bf16 [C_out, 27*C_in] (tap-major).
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/ltx2_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace ltx2;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+enum SlotKind { SK_CONV_W, SK_CONV_B, SK_F32, SK_LIN_W, SK_SCALAR };
+
+struct VSlot {
+  int kind = SK_F32;
+  void* dst = nullptr;
+  int64_t n = 0;                 // element count expected (SK_F32 / SK_LIN_W / SK_CONV_B source length)
+  int Cout = 0, Cout_pad = 0, Cin = 0, sp = 1;
+  int64_t rows = 0, cols = 0;    // SK_LIN_W
+  bool loaded = false;
+};
+
+struct ConvW {
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int Cin = 0, Cout = 0, Cout_pad = 0, sp = 1;
+};
+
+struct MlpW {                    // TimestepEmbedder: Linear(256,h) -> SiLU -> Linear(h,out)
+  bf16 *w1 = nullptr, *w2 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr;
+  int hidden = 0, out = 0;
+  bool present = false;
+};
+
+struct StageW {
+  int kind = 0;                  // 0 res group, 1 upsample
+  int C = 0;                     // input channels
+  int num_layers = 0;
+  std::vector<ConvW> conv1, conv2;
+  float* tables = nullptr;       // [num_layers, 4, C]
+  MlpW temb;
+  ConvW up;
+  int ft = 1, fh = 1, fw = 1, multiplier = 1, residual = 0;
+};
+
+struct VArena {
+  uintptr_t base = 0;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    return reinterpret_cast<void*>(base + a);
+  }
+};
+
+}  // namespace
+
+struct LtxVae {
+  LtxVaeConfig cfg;
+  std::unordered_map<std::string, VSlot> slots;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  float *mean = nullptr, *stdv = nullptr;
+  ConvW conv_in, conv_out;
+  std::vector<StageW> stages;
+  float* last_table = nullptr;   // [2, Cf]
+  MlpW last_temb;
+  int Cf = 0;
+  float ts_multiplier = 1000.0f;
+  float* ts_mult_dev = nullptr;
+  // workspace
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+namespace {
+
+int pad32(int c) { return (c + 31) / 32 * 32; }
+
+struct VLayout {
+  LtxVae* e;
+  VArena* ar;
+  bool dry;
+  void put(const std::string& key, const VSlot& s) {
+    if (!dry) e->slots[key] = s;
+  }
+  ConvW conv(const std::string& prefix, int Cout, int Cin, int sp = 1, int Cout_pad = -1) {
+    ConvW c;
+    c.Cin = Cin; c.Cout = Cout; c.sp = sp;
+    c.Cout_pad = Cout_pad > 0 ? Cout_pad : pad32(Cout);
+    c.w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(c.Cout_pad) * 27 * Cin));
+    c.b = reinterpret_cast<float*>(ar->take(sizeof(float) * c.Cout_pad));
+    VSlot w;
+    w.kind = SK_CONV_W; w.dst = c.w; w.n = int64_t(Cout) * Cin * 27; w.Cout = Cout; w.Cout_pad = c.Cout_pad;
+    w.Cin = Cin; w.sp = sp;
+    put(prefix + ".weight", w);
+    VSlot b;
+    b.kind = SK_CONV_B; b.dst = c.b; b.n = Cout; b.Cout = Cout; b.Cout_pad = c.Cout_pad; b.sp = sp;
+    put(prefix + ".bias", b);
+    return c;
+  }
+  float* f32(const std::string& key, int64_t n) {
+    float* p = reinterpret_cast<float*>(ar->take(sizeof(float) * n));
+    VSlot s;
+    s.kind = SK_F32; s.dst = p; s.n = n;
+    put(key, s);
+    return p;
+  }
+  MlpW mlp(const std::string& prefix, int hidden, int out) {
+    MlpW m;
+    m.hidden = hidden; m.out = out; m.present = true;
+    m.w1 = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(hidden) * 256));
+    m.b1 = reinterpret_cast<float*>(ar->take(sizeof(float) * hidden));
+    m.w2 = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(out) * hidden));
+    m.b2 = reinterpret_cast<float*>(ar->take(sizeof(float) * out));
+    VSlot s;
+    s.kind = SK_LIN_W; s.dst = m.w1; s.rows = hidden; s.cols = 256; s.n = int64_t(hidden) * 256;
+    put(prefix + ".linear_1.weight", s);
+    s.dst = m.w2; s.rows = out; s.cols = hidden; s.n = int64_t(out) * hidden;
+    put(prefix + ".linear_2.weight", s);
+    VSlot b;
+    b.kind = SK_F32; b.dst = m.b1; b.n = hidden;
+    put(prefix + ".linear_1.bias", b);
+    b.dst = m.b2; b.n = out;
+    put(prefix + ".linear_2.bias", b);
+    return m;
+  }
+};
+
+int build_vae_layout(LtxVae* e, VArena* ar, bool dry) {
+  VLayout L{e, ar, dry};
+  const LtxVaeConfig& c = e->cfg;
+  const int Lc = c.latent_channels;
+  e->mean = L.f32("vae.per_channel_statistics.mean-of-means", Lc);
+  e->stdv = L.f32("vae.per_channel_statistics.std-of-means", Lc);
+  int C = c.base_channels * 8;
+  e->conv_in = L.conv("vae.decoder.conv_in.conv", C, Lc);
+  std::vector<StageW> stages;
+  for (int i = 0; i < c.num_stages; ++i) {
+    const LtxVaeStage& s = c.stages[i];
+    const std::string U = "vae.decoder.up_blocks." + std::to_string(i);
+    StageW st;
+    st.kind = s.kind; st.C = C;
+    if (s.kind == 0) {
+      st.num_layers = s.num_layers;
+      st.tables = reinterpret_cast<float*>(ar->take(sizeof(float) * size_t(s.num_layers) * 4 * C));
+      for (int j = 0; j < s.num_layers; ++j) {
+        const std::string R = U + ".res_blocks." + std::to_string(j);
+        st.conv1.push_back(L.conv(R + ".conv1.conv", C, C));
+        st.conv2.push_back(L.conv(R + ".conv2.conv", C, C));
+        VSlot t;
+        t.kind = SK_F32; t.n = int64_t(4) * C;
+        t.dst = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(st.tables) + sizeof(float) * size_t(j) * 4 * C);
+        L.put(R + ".scale_shift_table", t);
+      }
+      if (c.timestep_conditioning) st.temb = L.mlp(U + ".time_embedder.timestep_embedder", 4 * C, 4 * C);
+    } else {
+      st.ft = s.stride_t; st.fh = s.stride_h; st.fw = s.stride_w;
+      st.multiplier = s.multiplier > 0 ? s.multiplier : 1;
+      st.residual = s.residual;
+      const int sp = st.ft * st.fh * st.fw;
+      if ((sp * C) % st.multiplier != 0 || C % sp != 0) {
+        set_error("vae: stage %d: channels %d incompatible with stride product %d / multiplier %d", i, C, sp,
+                  st.multiplier);
+        return LTX2_ERR_INVALID;
+      }
+      st.up = L.conv(U + ".conv.conv", sp * C / st.multiplier, C, sp);
+      C = C / st.multiplier;
+    }
+    stages.push_back(st);
+  }
+  e->Cf = C;
+  e->conv_out = L.conv("vae.decoder.conv_out.conv", 48, C, 1, 64);
+  e->last_table = L.f32("vae.decoder.last_scale_shift_table", int64_t(2) * C);
+  if (c.timestep_conditioning) {
+    VSlot s;
+    s.kind = SK_SCALAR; s.n = 1;
+    e->ts_mult_dev = reinterpret_cast<float*>(ar->take(16));
+    s.dst = e->ts_mult_dev;
+    L.put("vae.decoder.timestep_scale_multiplier", s);
+    // the reference hard-codes hidden 256 here (simple_decoder.py:663-665)
+    e->last_temb = L.mlp("vae.decoder.last_time_embedder.timestep_embedder", 256, 2 * C);
+  }
+  if (!dry) e->stages = stages;
+  return LTX2_OK;
+}
+
+struct Dims { int T, H, W, C; };
+
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+}  // namespace
+
+extern "C" {
+
+int ltx2_vae_create(const LtxVaeConfig* cfg, LtxVae** out) {
+  LTX2_REQUIRE(cfg && out, "vae_create: null argument");
+  LTX2_REQUIRE(cfg->num_stages >= 1 && cfg->num_stages <= 16, "vae_create: 1..16 stages");
+  LTX2_REQUIRE(cfg->base_channels % 64 == 0, "vae_create: base_channels must be a multiple of 64 (got %d)",
+               cfg->base_channels);
+  LTX2_REQUIRE(cfg->latent_channels % 64 == 0, "vae_create: latent_channels must be a multiple of 64");
+  LtxVae* e = new LtxVae();
+  e->cfg = *cfg;
+  VArena dry;
+  int s = build_vae_layout(e, &dry, true);
+  if (s != LTX2_OK) { delete e; return s; }
+  e->arena_bytes = dry.off + 1024;
+  if (cudaMalloc(&e->arena, e->arena_bytes) != cudaSuccess) {
+    set_error("vae weight arena allocation of %zu bytes failed", e->arena_bytes);
+    delete e;
+    return LTX2_ERR_NOMEM;
+  }
+  cudaMemset(e->arena, 0, e->arena_bytes);
+  VArena real;
+  real.base = reinterpret_cast<uintptr_t>(e->arena);
+  build_vae_layout(e, &real, false);
+  for (auto& st : e->stages) {
+    const int sp = st.ft * st.fh * st.fw;
+    if (st.kind == 1 && (st.up.Cout / sp) % 32 != 0) {
+      set_error("vae: upsample output channels %d must be a multiple of 32", st.up.Cout / sp);
+      ltx2_vae_destroy(e);
+      return LTX2_ERR_INVALID;
+    }
+  }
+  // tensors the reference treats as optional start as "loaded" with neutral values only where it does so:
+  // none -- every slot must be set (the timestep MLPs are optional in the reference loader, see missing_weights).
+  *out = e;
+  return LTX2_OK;
+}
+
+void ltx2_vae_destroy(LtxVae* e) {
+  if (!e) return;
+  if (e->arena) cudaFree(e->arena);
+  if (e->ws) cudaFree(e->ws);
+  delete e;
+}
+
+int ltx2_vae_set_weight(LtxVae* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                        int32_t ndim, void* stream) {
+  LTX2_REQUIRE(e && key && data, "vae_set_weight: null argument");
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) {
+    set_error("vae_set_weight: unknown key '%s'", key);
+    return LTX2_ERR_NOKEY;
+  }
+  VSlot& s = it->second;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int r = LTX2_OK;
+  switch (s.kind) {
+    case SK_CONV_W:
+      LTX2_REQUIRE(ndim == 5 && shape[0] == s.Cout && shape[1] == s.Cin && shape[2] == 3 && shape[3] == 3 && shape[4] == 3,
+                   "vae_set_weight: '%s' expects [%d,%d,3,3,3]", key, s.Cout, s.Cin);
+      r = pack_conv_weight(data, dtype, s.dst, s.Cout, s.Cout_pad, s.Cin, s.sp, st);
+      break;
+    case SK_CONV_B:
+      LTX2_REQUIRE(n == s.Cout, "vae_set_weight: '%s' expects %d elements, got %lld", key, s.Cout, (long long)n);
+      r = pack_conv_bias(data, dtype, reinterpret_cast<float*>(s.dst), s.Cout, s.Cout_pad, s.sp, st);
+      break;
+    case SK_LIN_W:
+      LTX2_REQUIRE(ndim == 2 && shape[0] == s.rows && shape[1] == s.cols, "vae_set_weight: '%s' expects [%lld,%lld]",
+                   key, (long long)s.rows, (long long)s.cols);
+      r = cast_to_bf16(data, dtype, s.dst, n, st);
+      break;
+    case SK_SCALAR: {
+      LTX2_REQUIRE(n == 1, "vae_set_weight: '%s' is a scalar", key);
+      r = cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), 1, st);
+      if (r == LTX2_OK) {
+        LTX2_CUDA_CHECK(cudaMemcpyAsync(&e->ts_multiplier, s.dst, 4, cudaMemcpyDeviceToHost, st));
+        LTX2_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      break;
+    }
+    default:
+      LTX2_REQUIRE(n == s.n, "vae_set_weight: '%s' expects %lld elements, got %lld", key, (long long)s.n, (long long)n);
+      r = cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), n, st);
+  }
+  if (r == LTX2_OK) s.loaded = true;
+  return r;
+}
+
+int ltx2_vae_missing_weights(LtxVae* e, char* names_out, int64_t names_cap) {
+  int missing = 0;
+  std::string acc;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      ++missing;
+      if (acc.size() < 4000) acc += kv.first + "\n";
+    }
+  if (names_out && names_cap > 0) {
+    strncpy(names_out, acc.c_str(), names_cap - 1);
+    names_out[names_cap - 1] = 0;
+  }
+  return missing;
+}
+
+int ltx2_vae_output_shape(LtxVae* e, const int64_t in_shape[5], int64_t out_shape[5]) {
+  LTX2_REQUIRE(e && in_shape && out_shape, "vae_output_shape: null argument");
+  int64_t T = in_shape[2], H = in_shape[3], W = in_shape[4];
+  for (auto& st : e->stages)
+    if (st.kind == 1) {
+      T = T * st.ft - (st.ft > 1 ? 1 : 0);
+      H *= st.fh;
+      W *= st.fw;
+    }
+  out_shape[0] = in_shape[0]; out_shape[1] = 3; out_shape[2] = T; out_shape[3] = H * 4; out_shape[4] = W * 4;
+  return LTX2_OK;
+}
+
+int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
+                    float noise_scale, const float* noise, int32_t causal, float* out, void* stream) {
+  LTX2_REQUIRE(e && latent && shape && out, "vae_decode: null argument");
+  const int B = (int)shape[0], Cl = (int)shape[1];
+  LTX2_REQUIRE(Cl == e->cfg.latent_channels, "vae_decode: latent has %d channels, decoder expects %d", Cl,
+               e->cfg.latent_channels);
+  LTX2_REQUIRE(B >= 1 && shape[2] >= 1 && shape[3] >= 2 && shape[4] >= 2, "vae_decode: latent grid too small");
+  const bool use_t = e->cfg.timestep_conditioning && timestep >= 0.f;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      // the reference loader treats the timestep embedders as optional (simple_decoder.py:620-636, 661-671)
+      const bool optional = kv.first.find("time_embedder") != std::string::npos ||
+                            kv.first.find("timestep_scale_multiplier") != std::string::npos;
+      if (!optional || use_t) {
+        set_error("vae_decode: weight '%s' has not been set", kv.first.c_str());
+        return LTX2_ERR_STATE;
+      }
+    }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  // ---- workspace sizing: walk the stages ----
+  Dims d{(int)shape[2], (int)shape[3], (int)shape[4], e->conv_in.Cout};
+  size_t max_act = size_t(B) * d.T * d.H * d.W * d.C;
+  size_t max_pad = size_t(B) * (d.T + 2) * (d.H + 2) * (d.W + 2) * std::max(d.C, Cl);
+  size_t max_mod = 0;
+  for (auto& s : e->stages) {
+    if (s.kind == 0) {
+      max_mod = std::max(max_mod, size_t(s.num_layers) * B * 4 * s.C);
+    } else {
+      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
+      max_act = std::max(max_act, size_t(B) * d.T * d.H * d.W * d.C);
+      max_pad = std::max(max_pad, size_t(B) * (d.T + 2) * (d.H + 2) * (d.W + 2) * d.C);
+    }
+  }
+  max_mod = std::max(max_mod, size_t(B) * 2 * e->Cf);
+  const int maxC = e->conv_in.Cout;
+  const size_t need = align256(max_act * 2) * 2 + align256(max_pad * 2) + align256(max_mod * 4) +
+                      align256(size_t(B) * (256 + 4 * maxC * 2 + 8) * 4) + 4096;
+  if (need > e->ws_bytes) {
+    if (e->ws) cudaFree(e->ws);
+    e->ws = nullptr; e->ws_bytes = 0;
+    if (cudaMalloc(&e->ws, need) != cudaSuccess) {
+      set_error("vae workspace allocation of %zu bytes failed", need);
+      return LTX2_ERR_NOMEM;
+    }
+    e->ws_bytes = need;
+  }
+  VArena ws;
+  ws.base = reinterpret_cast<uintptr_t>(e->ws);
+  bf16* cur = reinterpret_cast<bf16*>(ws.take(max_act * 2));
+  bf16* other = reinterpret_cast<bf16*>(ws.take(max_act * 2));
+  bf16* xp = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
+  float* mod = reinterpret_cast<float*>(ws.take(max_mod * 4));
+  float* tdev = reinterpret_cast<float*>(ws.take(size_t(B) * 4 + 16));
+  float* sinus = reinterpret_cast<float*>(ws.take(size_t(B) * 256 * 4));
+  float* hid = reinterpret_cast<float*>(ws.take(size_t(B) * 4 * maxC * 4));
+  float* temb = reinterpret_cast<float*>(ws.take(size_t(B) * 4 * maxC * 4));
+  LTX2_REQUIRE(B <= 8, "vae_decode: batch %d > 8 unsupported", B);
+
+  if (use_t) {
+    std::vector<float> tv(B, timestep);
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(tdev, tv.data(), size_t(B) * 4, cudaMemcpyHostToDevice, st));
+    LTX2_CUDA_CHECK(cudaStreamSynchronize(st));     // tv is a stack-owned staging buffer
+    LTX2_PROPAGATE(timestep_sinusoid(tdev, B, e->ts_multiplier, sinus, st));
+  }
+  auto run_mlp = [&](const MlpW& m) -> int {
+    LTX2_PROPAGATE(small_linear(sinus, B, 256, m.w1, m.b1, hid, m.hidden, 0, st));
+    return small_linear(hid, B, m.hidden, m.w2, m.b2, temb, m.out, 1, st);
+  };
+  auto conv = [&](const ConvW& w, const bf16* xin_padded, const Dims& dd, int mode, bf16* o, const bf16* residual,
+                  float* o32, const StageW* up) -> int {
+    ConvParams p;
+    p.B = B; p.T = dd.T; p.H = dd.H; p.W = dd.W;
+    p.Cin = w.Cin; p.Cout = w.Cout; p.Cout_pad = w.Cout_pad;
+    p.mode = mode; p.bias = w.b; p.out = o; p.out_f32 = o32; p.residual = residual;
+    if (up) {
+      p.ft = up->ft; p.fh = up->fh; p.fw = up->fw;
+      p.c_d2s = up->residual ? w.Cin / (up->ft * up->fh * up->fw) : 0;
+    }
+    return conv3d_bf16(xin_padded, w.w, p, st);
+  };
+
+  d = Dims{(int)shape[2], (int)shape[3], (int)shape[4], Cl};
+  const bool inject = use_t && noise != nullptr && noise_scale != 0.f;
+  LTX2_PROPAGATE(latent_to_padded(latent, dtype, e->stdv, e->mean, inject ? noise : nullptr, noise_scale, xp, B, Cl,
+                                  d.T, d.H, d.W, causal, st));
+  LTX2_PROPAGATE(conv(e->conv_in, xp, d, CONV_EPI_PLAIN, cur, nullptr, nullptr, nullptr));
+  d.C = e->conv_in.Cout;
+
+  for (auto& s : e->stages) {
+    if (s.kind == 0) {
+      const int C = s.C;
+      if (use_t && s.temb.present) {
+        LTX2_PROPAGATE(run_mlp(s.temb));
+        LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod,
+                                           int64_t(B) * 4 * C, int64_t(4) * C, s.num_layers, B, 4, C, st));
+      } else {
+        LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 4 * C * 4, st));
+        LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod,
+                                           int64_t(B) * 4 * C, int64_t(4) * C, s.num_layers, B, 4, C, st));
+      }
+      for (int j = 0; j < s.num_layers; ++j) {
+        const float* mj = mod + size_t(j) * B * 4 * C;
+        LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, 0, C, 1e-6f, causal, st));
+        LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, other, nullptr, nullptr, nullptr));
+        LTX2_PROPAGATE(norm_act_pad(other, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, int64_t(2) * C,
+                                    int64_t(3) * C, 1e-6f, causal, st));
+        LTX2_PROPAGATE(conv(s.conv2[j], xp, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr));
+      }
+    } else {
+      LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, s.C, 0, nullptr, 0, 0, 0, 1e-6f, causal, st));
+      LTX2_PROPAGATE(conv(s.up, xp, d, CONV_EPI_D2S, other, cur, nullptr, &s));
+      std::swap(cur, other);
+      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
+    }
+  }
+  // final norm + scale/shift + SiLU, conv_out, unpatchify (simple_decoder.py:528-552)
+  const int Cf = e->Cf;
+  if (use_t && e->last_temb.present) {
+    LTX2_PROPAGATE(run_mlp(e->last_temb));
+  } else {
+    LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 2 * Cf * 4, st));
+  }
+  LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod, 0, int64_t(2) * Cf, 1, B, 2, Cf, st));
+  LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, Cf, 1, mod, int64_t(2) * Cf, 0, Cf, 1e-6f, causal, st));
+  return conv(e->conv_out, xp, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+}
+
+int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, int32_t T_src, int32_t HW, int32_t t0,
+                     int32_t overlap, void* stream) {
+  return blend_chunk(dst, src, BC, T_dst, T_src, HW, t0, overlap, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ltx2_video_to_uint8(const float* video, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream) {
+  return video_to_uint8(video, out, T, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

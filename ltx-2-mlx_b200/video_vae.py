@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's video-VAE decode interface, backed by the sm_100a engine.
+
+Same names, argument meaning and defaults as ``LTX_2_MLX/model/video_vae/simple_decoder.py``:
+``SimpleVideoDecoder`` (:364-563; ``__call__(latent, timestep=0.05, show_progress=True, causal=False)``),
+``load_vae_decoder_weights(decoder, path)`` (:566-673) and
+``decode_latent(latent, decoder, timestep=0.05, key=None, temporal_chunk_size=7, temporal_overlap=2)`` (:676-800).
+Attributes pipelines touch from outside are kept: ``decode_noise_scale`` (tests/test_parity.py:359),
+``std_of_means`` / ``mean_of_means`` (pipelines/one_stage.py:980-981).
+
+All arithmetic (convs, norms, depth-to-space, unpatchify, chunk cross-fade, uint8 conversion) runs in the C-ABI
+library; this module only schedules chunks and moves buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import LtxVaeConfig, LtxVaeStage, check, dtype_code, lib, ptr, stream_ptr
+from .synthetic import DEFAULT_DECODER_BLOCKS, STRIDES
+from .transformer import to_device
+
+_STRIDE_MAP = STRIDES
+
+
+class SimpleVideoDecoder:
+    """Config-driven VAE decoder (V2.0 and V2.3 stacks) -- drop-in for simple_decoder.py:364-563."""
+
+    def __init__(self, decoder_blocks: Optional[List] = None, base_channels: int = 128,
+                 timestep_conditioning: bool = True, compute_dtype: Any = None, device="cuda"):
+        self.device = torch.device(device)
+        self.compute_dtype = compute_dtype
+        self.timestep_conditioning = timestep_conditioning
+        self.decode_noise_scale = 0.025                       # simple_decoder.py:391
+        self.decoder_blocks = [list(b) for b in (decoder_blocks or DEFAULT_DECODER_BLOCKS)]
+        self.base_channels = base_channels
+        self.mean_of_means = torch.zeros(128)
+        self.std_of_means = torch.zeros(128)
+        self._noise_generator: Optional[torch.Generator] = None
+
+        cfg = LtxVaeConfig()
+        cfg.base_channels, cfg.latent_channels = base_channels, 128
+        cfg.timestep_conditioning = int(timestep_conditioning)
+        self.block_types: List[str] = []
+        feature = base_channels * 8
+        n = 0
+        for name, params in reversed(self.decoder_blocks):
+            p = {"num_layers": params} if isinstance(params, int) else dict(params)
+            st = LtxVaeStage()
+            if name == "res_x":
+                st.kind, st.num_layers = 0, int(p["num_layers"])
+                st.stride_t = st.stride_h = st.stride_w = st.multiplier = 1
+                self.block_types.append("res")
+            elif name in _STRIDE_MAP:
+                st.kind = 1
+                st.stride_t, st.stride_h, st.stride_w = _STRIDE_MAP[name]
+                st.multiplier = int(p.get("multiplier", 1))
+                st.residual = int(bool(p.get("residual", False)))
+                feature //= st.multiplier
+                self.block_types.append("upsample")
+            else:
+                raise ValueError(f"Unknown decoder block: {name}")           # simple_decoder.py:427
+            cfg.stages[n] = st
+            n += 1
+        cfg.num_stages = n
+        self.final_channels = feature
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().ltx2_vae_create(C.byref(cfg), C.byref(self._h)), "ltx2_vae_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                lib().ltx2_vae_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    # ---- weights ------------------------------------------------------------------------------
+    def load_weights(self, weights: Iterable[Tuple[str, Any]]) -> int:
+        """(checkpoint_key, tensor) pairs with the names simple_decoder.py:592-671 reads; others are skipped."""
+        n = 0
+        with torch.cuda.device(self.device):
+            for key, value in (weights.items() if isinstance(weights, dict) else weights):
+                if not key.startswith("vae."):
+                    continue
+                t = to_device(value, self.device)
+                shape = (C.c_int64 * max(t.ndim, 1))(*(t.shape if t.ndim else (1,)))
+                st = lib().ltx2_vae_set_weight(self._h, key.encode(), ptr(t), dtype_code(t), shape, max(t.ndim, 1),
+                                               stream_ptr())
+                if st == -2:       # LTX2_ERR_NOKEY: encoder / unused tensors
+                    continue
+                check(st, f"vae set_weight({key})")
+                if key.endswith("mean-of-means"):
+                    self.mean_of_means = t.float().cpu()
+                elif key.endswith("std-of-means"):
+                    self.std_of_means = t.float().cpu()
+                n += 1
+            torch.cuda.current_stream().synchronize()
+        return n
+
+    def missing_weights(self) -> List[str]:
+        buf = C.create_string_buffer(8192)
+        n = lib().ltx2_vae_missing_weights(self._h, buf, C.c_int64(len(buf)))
+        return [s for s in buf.value.decode().split("\n") if s] if n else []
+
+    def output_shape(self, latent_shape) -> Tuple[int, ...]:
+        i = (C.c_int64 * 5)(*latent_shape)
+        o = (C.c_int64 * 5)()
+        check(lib().ltx2_vae_output_shape(self._h, i, o))
+        return tuple(o)
+
+    # ---- forward ------------------------------------------------------------------------------
+    def __call__(self, latent, timestep: Optional[float] = 0.05, show_progress: bool = True, causal: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """latent (B,128,T,H,W) -> video (B,3,8(T-1)+1,32H,32W) fp32 on the GPU (simple_decoder.py:446-563)."""
+        with torch.cuda.device(self.device):
+            x = to_device(latent, self.device)
+            if x.ndim != 5:
+                raise ValueError(f"latent must be (B, C, T, H, W); got {tuple(x.shape)}")
+            oshape = self.output_shape(x.shape)
+            if out is None:
+                out = torch.empty(oshape, device=self.device, dtype=torch.float32)
+            noise = None
+            s = float(self.decode_noise_scale)
+            if self.timestep_conditioning and timestep is not None and s != 0.0:
+                # the reference draws mx.random.normal here (:497); the draw is host plumbing, the blend is in-kernel
+                noise = torch.randn(x.shape, device=self.device, dtype=torch.float32, generator=self._noise_generator)
+            shape = (C.c_int64 * 5)(*x.shape)
+            check(lib().ltx2_vae_decode(self._h, ptr(x), dtype_code(x), shape,
+                                        C.c_float(-1.0 if timestep is None else float(timestep)), C.c_float(s),
+                                        ptr(noise), int(bool(causal)), ptr(out), stream_ptr()), "ltx2_vae_decode")
+        return out
+
+
+def load_vae_decoder_weights(decoder: SimpleVideoDecoder, weights_path: str) -> None:
+    """Drop-in for simple_decoder.load_vae_decoder_weights: safetensors file -> engine."""
+    from safetensors import safe_open
+
+    print(f"Loading VAE decoder weights from {weights_path}...")
+    with safe_open(weights_path, framework="pt") as f:
+        def gen():
+            for k in f.keys():
+                if k.startswith("vae.decoder.") or k.startswith("vae.per_channel_statistics."):
+                    yield k, f.get_tensor(k)
+        n = decoder.load_weights(gen())
+    print(f"  Loaded {n} weight tensors")
+
+
+def chunk_plan(T: int, chunk: int = 7, overlap: int = 2) -> List[Tuple[int, int]]:
+    """Temporal chunk schedule of decode_latent (simple_decoder.py:728-747)."""
+    out, stride, t = [], chunk - overlap, 0
+    while t < T:
+        end = min(t + chunk, T)
+        if end - t < overlap + 1 and t > 0:
+            t = max(0, end - chunk)
+            end = min(t + chunk, T)
+        out.append((t, end))
+        if end >= T:
+            break
+        t += stride
+    return out
+
+
+def _pix_t(lt: int) -> int:
+    for _ in range(3):
+        lt = lt * 2 - 1
+    return lt
+
+
+def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[float] = 0.05,
+                        temporal_chunk_size: int = 7, temporal_overlap: int = 2) -> torch.Tensor:
+    """The float video (B,3,T,H,W) decode_latent builds before its uint8 conversion (:704-790)."""
+    x = to_device(latent, decoder.device)
+    if x.ndim == 4:
+        x = x[None]
+    T = x.shape[2]
+    if T <= temporal_chunk_size:
+        return decoder(x, timestep=timestep, show_progress=False)
+    total = _pix_t(T)
+    plan = chunk_plan(T, temporal_chunk_size, temporal_overlap)
+    ref_overlap = _pix_t(temporal_overlap)
+    B, _, _, H, W = decoder.output_shape(x.shape)
+    # chunks land at frame (len_so_far - overlap); the reference concatenates, we blend into one buffer
+    pieces = []
+    length = 0
+    for (a, b) in plan:
+        v = decoder(x[:, :, a:b].contiguous(), timestep=timestep, show_progress=False)
+        ov = 0 if not pieces else min(ref_overlap, v.shape[2], length)
+        if ov <= 1:
+            ov = 0
+        pieces.append((v, length - ov, ov))
+        length = length - ov + v.shape[2]
+    video = torch.empty(B, 3, length, H, W, device=decoder.device, dtype=torch.float32)
+    with torch.cuda.device(decoder.device):
+        for v, t0, ov in pieces:
+            check(lib().ltx2_blend_chunk(ptr(video), ptr(v), B * 3, length, v.shape[2], H * W, t0, ov, stream_ptr()),
+                  "ltx2_blend_chunk")
+    return video[:, :, :total]
+
+
+def decode_latent(latent, decoder: SimpleVideoDecoder, timestep: Optional[float] = 0.05, key=None,
+                  temporal_chunk_size: int = 7, temporal_overlap: int = 2) -> torch.Tensor:
+    """Decode latent to uint8 frames (T,H,W,3) -- drop-in for simple_decoder.decode_latent (:676-800)."""
+    video = decode_latent_video(latent, decoder, timestep, temporal_chunk_size, temporal_overlap).contiguous()
+    B, _, T, H, W = video.shape
+    out = torch.empty(T, H, W, 3, device=decoder.device, dtype=torch.uint8)
+    with torch.cuda.device(decoder.device):
+        check(lib().ltx2_video_to_uint8(ptr(video[0].contiguous()), ptr(out), T, H, W, stream_ptr()),
+              "ltx2_video_to_uint8")
+    return out

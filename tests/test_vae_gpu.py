@@ -1,0 +1,127 @@
+"""GPU parity of the video-VAE decode path (SimpleVideoDecoder / decode_latent mirrors -> C ABI) against the
+oracle on the same seeded synthetic checkpoint.  The oracle runs fp32 on bf16-rounded conv weights; the engine keeps
+activations in bf16 between convs (fp32 accumulation), so the tolerance is a relative L2 error of 3e-2 plus the
+reference's own metric, Pearson r (tests/test_parity.py:53-59; its gate is r >= 0.95), >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BLOCKS_V20 = [["res_x", {"num_layers": 2}], ["compress_all", {"multiplier": 2, "residual": True}],
+              ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 2, "residual": True}],
+              ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 2, "residual": True}],
+              ["res_x", {"num_layers": 1}]]
+BLOCKS_V23 = [["res_x", {"num_layers": 1}], ["compress_space", {"multiplier": 2, "residual": True}],
+              ["res_x", {"num_layers": 1}], ["compress_time", {"multiplier": 2, "residual": False}],
+              ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 1, "residual": True}],
+              ["res_x", {"num_layers": 1}]]
+
+
+def pearson(a, b):
+    return float(np.corrcoef(a.double().flatten().cpu().numpy(), b.double().flatten().cpu().numpy())[0, 1])
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm())
+
+
+def bf16_round(w):
+    return {k: (v.to(torch.bfloat16).float() if v.ndim >= 2 and "scale_shift_table" not in k else v) for k, v in w.items()}
+
+
+def build(blocks, base, tc, seed):
+    from ltx2_b200 import synthetic
+    from ltx2_b200.video_vae import SimpleVideoDecoder
+    cfg = synthetic.VaeConfig(decoder_blocks=blocks, base_channels=base, timestep_conditioning=tc)
+    w = synthetic.vae_weights(cfg, seed=seed)
+    dec = SimpleVideoDecoder(decoder_blocks=blocks, base_channels=base, timestep_conditioning=tc)
+    dec.load_weights(w)
+    assert dec.missing_weights() == []
+    dec.decode_noise_scale = 0.0          # deterministic, as tests/test_parity.py:359
+    return dec, bf16_round(w)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_vae_v20_decode_matches_oracle(causal):
+    from ltx2_b200 import synthetic
+    from oracle import vae_oracle as V
+    dec, w = build(BLOCKS_V20, 64, True, seed=21)
+    lat = synthetic.latents((1, 128, 3, 2, 3), seed=200)
+    ref = V.vae_decode(w, lat, decoder_blocks=BLOCKS_V20, base_channels=64, timestep=0.05, causal=causal)
+    out = dec(lat, timestep=0.05, causal=causal)
+    assert out.shape == ref.shape == (1, 3, 17, 64, 96) and out.dtype == torch.float32
+    assert rel(out, ref) < 3e-2, rel(out, ref)
+    assert pearson(out, ref) > 0.999
+
+
+def test_vae_no_timestep_and_batch2():
+    from ltx2_b200 import synthetic
+    from oracle import vae_oracle as V
+    dec, w = build(BLOCKS_V20, 64, True, seed=22)
+    lat = synthetic.latents((2, 128, 2, 3, 2), seed=201)
+    ref = V.vae_decode(w, lat, decoder_blocks=BLOCKS_V20, base_channels=64, timestep=None)
+    out = dec(lat, timestep=None)
+    assert rel(out, ref) < 3e-2 and pearson(out, ref) > 0.999
+    # bf16 / numpy latents are accepted
+    out2 = dec(lat.numpy(), timestep=None)
+    assert torch.equal(out2, out)
+    # noise injection changes the result and is reproducible with a seeded generator
+    dec.decode_noise_scale = 0.025
+    dec._noise_generator = torch.Generator(device="cuda").manual_seed(5)
+    n1 = dec(lat, timestep=0.05)
+    dec._noise_generator = torch.Generator(device="cuda").manual_seed(5)
+    n2 = dec(lat, timestep=0.05)
+    assert torch.equal(n1, n2) and not torch.allclose(n1, dec(lat, timestep=None))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    noise = torch.randn(lat.shape, device="cuda", generator=g)
+    ref_n = V.vae_decode(w, lat, decoder_blocks=BLOCKS_V20, base_channels=64, timestep=0.05, decode_noise_scale=0.025,
+                         noise=noise.cpu())
+    assert rel(n1, ref_n) < 3e-2
+
+
+def test_vae_v23_style_stack_matches_oracle():
+    from ltx2_b200 import synthetic
+    from oracle import vae_oracle as V
+    dec, w = build(BLOCKS_V23, 64, False, seed=23)
+    lat = synthetic.latents((1, 128, 2, 2, 2), seed=202)
+    ref = V.vae_decode(w, lat, decoder_blocks=BLOCKS_V23, base_channels=64, timestep=None, timestep_conditioning=False)
+    out = dec(lat, timestep=None)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 3e-2 and pearson(out, ref) > 0.999
+
+
+def test_decode_latent_chunked_blend_and_uint8():
+    from ltx2_b200 import synthetic
+    from ltx2_b200.video_vae import chunk_plan, decode_latent, decode_latent_video
+    from oracle import vae_oracle as V
+    dec, w = build(BLOCKS_V20, 64, True, seed=24)
+    assert chunk_plan(9) == V.chunk_plan(9) == [(0, 7), (5, 9)]
+    assert chunk_plan(16) == V.chunk_plan(16) and chunk_plan(31) == V.chunk_plan(31)
+    lat = synthetic.latents((1, 128, 9, 2, 2), seed=203)
+    kw = dict(decoder_blocks=BLOCKS_V20, base_channels=64)
+    parts = [V.vae_decode(w, lat[:, :, a:b], timestep=0.05, **kw) for a, b in V.chunk_plan(9)]
+    ref_video = V.blend_chunks(parts, 9)
+    video = decode_latent_video(lat, dec)
+    assert video.shape == ref_video.shape == (1, 3, 65, 64, 64)
+    assert rel(video, ref_video) < 3e-2
+    frames = decode_latent(lat[0], dec)                 # 4-D latent, like generate.py:2085
+    assert frames.shape == (65, 64, 64, 3) and frames.dtype == torch.uint8
+    ref_frames = V.to_uint8_frames(ref_video)
+    d = (frames.cpu().int() - ref_frames.int()).abs()
+    assert d.float().mean() < 2.0 and d.max() <= 24      # uint8 of bf16-path pixels: a few grey levels
+    # uint8 conversion itself is exact on identical input (truncation, not rounding)
+    assert torch.equal(V.to_uint8_frames(video.cpu()), frames.cpu())
+    # single-pass path (T <= 7)
+    short = decode_latent(lat[:, :, :3], dec)
+    assert short.shape == (17, 64, 64, 3)
+
+
+def test_vae_errors():
+    from ltx2_b200._lib import Ltx2Error
+    from ltx2_b200.video_vae import SimpleVideoDecoder
+    with pytest.raises(ValueError, match="Unknown decoder block"):
+        SimpleVideoDecoder(decoder_blocks=[["bogus", 1]], base_channels=64)
+    dec = SimpleVideoDecoder(decoder_blocks=BLOCKS_V20, base_channels=64)
+    with pytest.raises(Ltx2Error, match="has not been set"):
+        dec(torch.zeros(1, 128, 2, 2, 2))
