@@ -6,12 +6,12 @@
 //
 // One CTA per (128-query tile, batch*head).  6 warps:
 //   warp 0   TMA producer: Q once, then K_j / V^T_j tiles (128 keys) through 2-stage rings
-//   warp 1   MMA issuer:   S_j = Q K_j^T  (tcgen05, fp32 in TMEM, double-buffered) and
-//                          O_j = P_j V_j  (fresh accumulator per block, double-buffered)
-//   warps 2-5 softmax:     one thread per query row; two TMEM passes over S_j (row max, then
-//                          exp2/sum), P_j written as bf16 into a 128B-swizzled smem tile that is the
-//                          A operand of the second MMA; running output kept in registers and
-//                          rescaled by exp2(m_old - m_new) when O_{j-1} is folded in.
+//   warp 1   MMA issuer:   S_j = Q K_j^T  (fp32 in TMEM, double-buffered) and O += P_j V_j (one TMEM accumulator)
+//   warps 2-5 softmax:     one thread per query row.  S_j is read from TMEM ONCE into registers; p = exp2(s*c - m*c)
+//                          is written as bf16 into a 128B-swizzled smem tile (the A operand of the second MMA).
+//                          The running output stays in TMEM; it is rescaled only when the row maximum grew by more
+//                          than 2^8 since the scale in use (lazy rescale: the stale maximum only changes the common
+//                          factor of P and l, which cancels in O / l).
 // K is consumed [keys, d] (K-major for S), V is consumed TRANSPOSED [d, keys] (K-major for P V), so
 // both MMAs use the same K-major/128B-swizzle descriptor form as the GEMM.
 #include "common.cuh"
@@ -33,7 +33,7 @@ struct AttnCfg {
   static constexpr int kPBytes = BQ * BKV * 2;
   static constexpr int kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256;
   static constexpr int kTmemCols = 512;
-  static constexpr int kOCol = 256;  // O accumulators start after the two S buffers
+  static constexpr int kOCol = 256;  // the O accumulator starts after the two S buffers
 };
 
 template <int DH>
@@ -54,13 +54,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* k_empty = bars + 3;     // 2
   uint64_t* v_full = bars + 5;      // 2
   uint64_t* v_empty = bars + 7;     // 2
-  uint64_t* s_full = bars + 9;      // 2
-  uint64_t* s_empty = bars + 11;    // 2
-  uint64_t* o_full = bars + 13;     // 2
-  uint64_t* o_empty = bars + 15;    // 2
-  uint64_t* p_full = bars + 17;     // 1
-  uint64_t* p_empty = bars + 18;    // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* s_full = bars + 9;      // 2   MMA -> softmax: S_j in TMEM
+  uint64_t* s_empty = bars + 11;    // 2   softmax -> MMA: S buffer read into registers
+  uint64_t* p_full = bars + 13;     // 1   softmax -> MMA: P_j in smem (and O rescaled if needed)
+  uint64_t* pv_done = bars + 14;    // 1   MMA -> softmax: P_j V_j retired (sP reusable, O up to date)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,11 +78,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
     }
     mbar_init(p_full, 128);
-    mbar_init(p_empty, 1);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -145,17 +141,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[b], ph);
-        mbar_wait(&o_empty[b], ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
           const uint64_t ad = umma_desc_k_sw128(smem_u32(sP + (ks / 4) * (BQ * 128))) + 2 * (ks % 4);
           const uint64_t bd = umma_desc_k_sw128(smem_u32(sV + b * Cfg::kVBytes + (ks / 4) * (DH * 128))) + 2 * (ks % 4);
-          umma_bf16_ss(tmem_base + Cfg::kOCol + b * DH, ad, bd, idesc_o, ks != 0);
+          umma_bf16_ss(tmem_base + Cfg::kOCol, ad, bd, idesc_o, (j | ks) != 0);
         }
-        umma_commit(&o_full[b]);
         umma_commit(&v_empty[b]);
-        umma_commit(p_empty);
+        umma_commit(pv_done);
       }
     }
   } else {
@@ -163,10 +157,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                 // query row inside the tile
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    float m = -INFINITY, l = 0.f;
-    float acc[DH];
-#pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+    const uint32_t t_o = t_lane + Cfg::kOCol;
+    float m_run = -INFINITY;                            // true running row maximum (raw scores)
+    float m_used = 0.f;                                 // maximum the current scale of P, l and O refers to
+    float l = 0.f;
+    uint8_t* prow0 = sP + r * 128;
+    const int sw = r & 7;
 
     for (int j = 0; j < nkv; ++j) {
       const int b = j & 1;
@@ -174,79 +170,84 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const int kv_valid = Tk - j * BKV;                // >= 1
       mbar_wait(&s_full[b], ph);
       tc_fence_after();
-      // ---- pass 1: row max ----
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + b * BKV + c, v);
+      uint32_t s[BKV];
+      {
+        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
+        uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
+        tmem_ld_32x32(t_lane + b * BKV + 0, s0);
+        tmem_ld_32x32(t_lane + b * BKV + 32, s1);
+        tmem_ld_32x32(t_lane + b * BKV + 64, s2);
+        tmem_ld_32x32(t_lane + b * BKV + 96, s3);
         tmem_ld_wait();
-        if (kv_valid >= c + 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float alpha = exp2f((m - mx) * scale_log2);   // m = -inf on the first block -> 0
-      const float mb = mx * scale_log2;
-      // ---- pass 2: p = exp2(s*c - m*c), row sum, P -> smem (bf16, 128B swizzle) ----
-      mbar_wait(p_empty, (j & 1) ^ 1);                   // P V_{j-1} has finished reading sP
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + b * BKV + c, v);
-        tmem_ld_wait();
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(v[i]), scale_log2, -mb));
-          if (c + i >= kv_valid) e = 0.f;
-          p[i] = e;
-          rowsum += e;
-        }
-        uint8_t* prow = sP + (c / 64) * (BQ * 128) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w;
-          w.x = pack_bf16x2(p[q * 8 + 0], p[q * 8 + 1]);
-          w.y = pack_bf16x2(p[q * 8 + 2], p[q * 8 + 3]);
-          w.z = pack_bf16x2(p[q * 8 + 4], p[q * 8 + 5]);
-          w.w = pack_bf16x2(p[q * 8 + 6], p[q * 8 + 7]);
-          const int chunk = ((c % 64) / 8 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = w;
-        }
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[b]);
-      fence_proxy_async_smem();
-      mbar_arrive(p_full);
-      l = l * alpha + rowsum;
-      m = mx;
-      // ---- fold in O_{j-1} (scaled to the previous max) and rescale to the new max ----
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
+      mbar_arrive(&s_empty[b]);                         // S_j now lives in registers
+      if (kv_valid < BKV) {
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_valid) s[i] = 0xff800000u;        // -inf
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+            mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int i = 4; i < BKV; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      m_run = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = m_run;
+      } else if ((m_run - m_used) * scale_log2 > 8.0f) {
+        alpha = ex2_approx((m_used - m_run) * scale_log2);
+        m_used = m_run;
+        need = true;
+      }
+      const float mb = m_used * scale_log2;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int i = 0; i < BKV; i += 4) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, -mb));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, -mb));
+        const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, -mb));
+        const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, -mb));
+        sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
+        pk[i / 2] = pack_bf16x2(e0, e1);
+        pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+      }
+      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);       // P V_{j-1} retired: sP is free, O is complete
+      if (__any_sync(0xffffffffu, need)) {
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < DH; c += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(t_lane + Cfg::kOCol + pb * DH + c, v);
+          tmem_ld_32x32(t_o + c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c + i] = (acc[c + i] + __uint_as_float(v[i])) * alpha;
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32(t_o + c, v);
         }
-        tc_fence_before();
-        mbar_arrive(&o_empty[pb]);
+        tmem_st_wait();
       }
+#pragma unroll
+      for (int c = 0; c < BKV / 8; ++c) {               // 16 chunks of 8 bf16
+        uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(prow0 + (c / 8) * (BQ * 128) + (((c % 8) ^ sw) << 4)) = w;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
     }
-    // ---- last block's O, normalise, gate, store ----
+    // ---- normalise, gate, store ----
     {
-      const int pb = (nkv - 1) & 1;
-      mbar_wait(&o_full[pb], ((nkv - 1) >> 1) & 1);
+      mbar_wait(pv_done, (nkv - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const int row = q0 + r;
@@ -261,22 +262,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
       for (int c = 0; c < DH; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(t_lane + Cfg::kOCol + pb * DH + c, v);
+        tmem_ld_32x32(t_o + c, v);
         tmem_ld_wait();
         if (row < Tq) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 w;
-            w.x = pack_bf16x2((acc[c + i + 0] + __uint_as_float(v[i + 0])) * f, (acc[c + i + 1] + __uint_as_float(v[i + 1])) * f);
-            w.y = pack_bf16x2((acc[c + i + 2] + __uint_as_float(v[i + 2])) * f, (acc[c + i + 3] + __uint_as_float(v[i + 3])) * f);
-            w.z = pack_bf16x2((acc[c + i + 4] + __uint_as_float(v[i + 4])) * f, (acc[c + i + 5] + __uint_as_float(v[i + 5])) * f);
-            w.w = pack_bf16x2((acc[c + i + 6] + __uint_as_float(v[i + 6])) * f, (acc[c + i + 7] + __uint_as_float(v[i + 7])) * f);
+            w.x = pack_bf16x2(__uint_as_float(v[i + 0]) * f, __uint_as_float(v[i + 1]) * f);
+            w.y = pack_bf16x2(__uint_as_float(v[i + 2]) * f, __uint_as_float(v[i + 3]) * f);
+            w.z = pack_bf16x2(__uint_as_float(v[i + 4]) * f, __uint_as_float(v[i + 5]) * f);
+            w.w = pack_bf16x2(__uint_as_float(v[i + 6]) * f, __uint_as_float(v[i + 7]) * f);
             *reinterpret_cast<uint4*>(o + c + i) = w;
           }
         }
       }
       if (lse_out != nullptr && row < Tq)
-        lse_out[static_cast<int64_t>(bh) * Tq + row] = m * scale + logf(l);
+        lse_out[static_cast<int64_t>(bh) * Tq + row] = m_used * scale + logf(l);
       tc_fence_before();
     }
   }
