@@ -5,10 +5,14 @@
 // (B,H,T,D)->(B,T,H*D) (:34) and the V2 per-head gate 2*sigmoid(logits) (:243-250).
 //
 // One CTA per (128-query tile, batch*head).  6 warps:
-//   warp 0   TMA producer: Q once, then K_j / V^T_j tiles (128 keys) through 2-stage rings
-//   warp 1   MMA issuer:   S_j = Q K_j^T  (fp32 in TMEM, double-buffered) and O += P_j V_j (one TMEM accumulator)
-//   warps 2-5 softmax:     one thread per query row.  S_j is read from TMEM ONCE into registers; p = exp2(s*c - m*c)
-//                          is written as bf16 into a 128B-swizzled smem tile (the A operand of the second MMA).
+//   warp 0   TMA producer: K_j / V^T_j tiles (128 keys) through 3-stage smem rings
+//   warp 1   MMA issuer:   S_j = Q K_j^T  (fp32 in TMEM, double-buffered) and O += P_j V_j (one TMEM accumulator).
+//                          BOTH A operands (Q and P) are read from tensor memory (tcgen05.mma with a TMEM A operand),
+//                          so shared memory only carries K and V: an SS-mode M=128,N=128 MMA would need the full
+//                          128 B/clk of shared-memory bandwidth and starve next to the TMA writes.
+//   warps 2-5 softmax:     one thread per query row.  Q's row is loaded from global and parked in TMEM once.
+//                          S_j is read from TMEM ONCE into registers; p = exp2(s*c - m*c) is written back to TMEM
+//                          as packed bf16 (64 columns).
 //                          The running output stays in TMEM; it is rescaled only when the row maximum grew by more
 //                          than 2^8 since the scale in use (lazy rescale: the stale maximum only changes the common
 //                          factor of P and l, which cancels in O / l).
@@ -25,40 +29,40 @@ constexpr int kAttnThreads = 192;
 constexpr int BQ = 128;    // queries per CTA
 constexpr int BKV = 128;   // keys per block
 
+constexpr int kKVStages = 3;
+
 template <int DH>
 struct AttnCfg {
-  static constexpr int kQBytes = BQ * DH * 2;
   static constexpr int kKBytes = BKV * DH * 2;
   static constexpr int kVBytes = DH * BKV * 2;
-  static constexpr int kPBytes = BQ * BKV * 2;
-  static constexpr int kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kKVStages * (kKBytes + kVBytes) + 1024 + 256;
   static constexpr int kTmemCols = 512;
-  static constexpr int kOCol = 256;  // the O accumulator starts after the two S buffers
+  static constexpr int kOCol = 256;            // O accumulator (DH fp32 columns) after the two S buffers
+  static constexpr int kPCol = 384;            // P: 128 x 128 bf16 = 64 columns
+  static constexpr int kQCol = 448;            // Q: 128 x DH bf16 = DH/2 columns
 };
 
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
                  float scale_log2, float scale, const float* __restrict__ gate_logits, float* __restrict__ lse_out) {
   using Cfg = AttnCfg<DH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::kQBytes;
-  uint8_t* sV = sK + 2 * Cfg::kKBytes;
-  uint8_t* sP = sV + 2 * Cfg::kVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* k_full = bars + 1;      // 2
-  uint64_t* k_empty = bars + 3;     // 2
-  uint64_t* v_full = bars + 5;      // 2
-  uint64_t* v_empty = bars + 7;     // 2
-  uint64_t* s_full = bars + 9;      // 2   MMA -> softmax: S_j in TMEM
-  uint64_t* s_empty = bars + 11;    // 2   softmax -> MMA: S buffer read into registers
-  uint64_t* p_full = bars + 13;     // 1   softmax -> MMA: P_j in smem (and O rescaled if needed)
-  uint64_t* pv_done = bars + 14;    // 1   MMA -> softmax: P_j V_j retired (sP reusable, O up to date)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kKVStages * Cfg::kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * Cfg::kVBytes);
+  uint64_t* q_ready = bars;                        // 1   softmax -> MMA: Q parked in TMEM
+  uint64_t* k_full = bars + 1;                     // kKVStages
+  uint64_t* k_empty = k_full + kKVStages;
+  uint64_t* v_full = k_empty + kKVStages;
+  uint64_t* v_empty = v_full + kKVStages;
+  uint64_t* s_full = v_empty + kKVStages;          // 2   MMA -> softmax: S_j in TMEM
+  uint64_t* s_empty = s_full + 2;                  // 2   softmax -> MMA: S buffer read into registers
+  uint64_t* p_full = s_empty + 2;                  // 1   softmax -> MMA: P_j in TMEM (and O rescaled if needed)
+  uint64_t* pv_done = p_full + 1;                  // 1   MMA -> softmax: P_j V_j retired (P reusable, O up to date)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -67,15 +71,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int nkv = (Tk + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    mbar_init(q_ready, 128);
+    for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
     }
@@ -95,12 +100,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, Cfg::kQBytes);
-#pragma unroll
-      for (int i = 0; i < DH / 64; ++i) tma_load_3d(sQ + i * (BQ * 128), &tmap_q, q_full, i * 64, q0, bh);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::kKBytes);
 #pragma unroll
@@ -111,6 +113,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int i = 0; i < BKV / 64; ++i)
           tma_load_3d(sV + st * Cfg::kVBytes + i * (DH * 128), &tmap_v, &v_full[st], j * BKV + i * 64, 0, bh);
+        if (++st == kKVStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -118,38 +121,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH);
+      int ks_st = 0, vs_st = 0;                 // K / V ring positions
+      uint32_t ks_ph = 0, vs_ph = 0;
       auto issue_s = [&](int j) {
         const int b = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_full[b], ph);
-        mbar_wait(&s_empty[b], ph ^ 1);
+        mbar_wait(&k_full[ks_st], ks_ph);
+        mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(sQ + (ks / 4) * (BQ * 128))) + 2 * (ks % 4);
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(sK + b * Cfg::kKBytes + (ks / 4) * (BKV * 128))) + 2 * (ks % 4);
-          umma_bf16_ss(tmem_base + b * BKV, ad, bd, idesc_s, ks != 0);
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(sK + ks_st * Cfg::kKBytes + (ks / 4) * (BKV * 128))) + 2 * (ks % 4);
+          umma_bf16_ts(tmem_base + b * BKV, tmem_base + Cfg::kQCol + ks * 8, bd, idesc_s, ks != 0);
         }
         umma_commit(&s_full[b]);
-        umma_commit(&k_empty[b]);
+        umma_commit(&k_empty[ks_st]);
+        if (++ks_st == kKVStages) { ks_st = 0; ks_ph ^= 1; }
       };
-      mbar_wait(q_full, 0);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_s(j + 1);
-        const int b = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
         mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[b], ph);
+        mbar_wait(&v_full[vs_st], vs_ph);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(sP + (ks / 4) * (BQ * 128))) + 2 * (ks % 4);
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(sV + b * Cfg::kVBytes + (ks / 4) * (DH * 128))) + 2 * (ks % 4);
-          umma_bf16_ss(tmem_base + Cfg::kOCol, ad, bd, idesc_o, (j | ks) != 0);
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(sV + vs_st * Cfg::kVBytes + (ks / 4) * (DH * 128))) + 2 * (ks % 4);
+          umma_bf16_ts(tmem_base + Cfg::kOCol, tmem_base + Cfg::kPCol + ks * 8, bd, idesc_o, (j | ks) != 0);
         }
-        umma_commit(&v_empty[b]);
+        umma_commit(&v_empty[vs_st]);
         umma_commit(pv_done);
+        if (++vs_st == kKVStages) { vs_st = 0; vs_ph ^= 1; }
       }
     }
   } else {
@@ -161,8 +164,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float m_run = -INFINITY;                            // true running row maximum (raw scores)
     float m_used = 0.f;                                 // maximum the current scale of P, l and O refers to
     float l = 0.f;
-    uint8_t* prow0 = sP + r * 128;
-    const int sw = r & 7;
+    {
+      // park this row of Q in tensor memory: column c of the Q region holds elements (2c, 2c+1)
+      const int row = q0 + r;
+      const uint4* qrow = reinterpret_cast<const uint4*>(q + (static_cast<int64_t>(bh) * Tq + (row < Tq ? row : 0)) * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 2; c += 32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 u = make_uint4(0u, 0u, 0u, 0u);
+          if (row < Tq) u = __ldg(qrow + c / 4 + i);
+          v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+        }
+        tmem_st_32x32(t_lane + Cfg::kQCol + c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
 
     for (int j = 0; j < nkv; ++j) {
       const int b = j & 1;
@@ -236,12 +256,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         tmem_st_wait();
       }
-#pragma unroll
-      for (int c = 0; c < BKV / 8; ++c) {               // 16 chunks of 8 bf16
-        uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(prow0 + (c / 8) * (BQ * 128) + (((c % 8) ^ sw) << 4)) = w;
+      {
+        uint32_t (&p0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+        uint32_t (&p1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+        tmem_st_32x32(t_lane + Cfg::kPCol, p0);
+        tmem_st_32x32(t_lane + Cfg::kPCol + 32, p1);
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
@@ -300,13 +321,7 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
     configured = true;
   }
   const uint64_t BH = static_cast<uint64_t>(B) * H;
-  CUtensorMap mq, mk, mv;
-  {
-    uint64_t dims[3] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(Tq), BH};
-    uint64_t str[2] = {static_cast<uint64_t>(DH) * 2, static_cast<uint64_t>(Tq) * DH * 2};
-    uint32_t box[3] = {64, BQ, 1};
-    LTX2_PROPAGATE(make_tensor_map_bf16(&mq, q, 3, dims, str, box));
-  }
+  CUtensorMap mk, mv;
   {
     uint64_t dims[3] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(Tk), BH};
     uint64_t str[2] = {static_cast<uint64_t>(DH) * 2, static_cast<uint64_t>(Tk) * DH * 2};
@@ -322,7 +337,8 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
   dim3 grid((Tq + BQ - 1) / BQ, static_cast<unsigned>(BH));
   const float kLog2e = 1.4426950408889634f;
   attention_kernel<DH><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
-      mq, mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk, scale * kLog2e, scale, gate_logits, lse_out);
+      reinterpret_cast<const __nv_bfloat16*>(q), mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk,
+      scale * kLog2e, scale, gate_logits, lse_out);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
