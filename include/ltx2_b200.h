@@ -194,6 +194,12 @@ int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int3
                    int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
                    void* stream);
 
+/* Diagnostics: ltx2_attention plus a clock64 timeline of CTA (0,0): trace[j*8 + e], e = 0 QK_j issued, 1 P_j seen by
+ * the MMA thread, 2 PV_j issued, 3 S_j seen by softmax, 4 S_j in registers, 5 exps done, 6 PV_{j-1} retired,
+ * 7 P_j published (tools/attn_trace.py). */
+int ltx2_attention_trace(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
+                         int32_t Tk, int32_t Tkp, int32_t Dh, float scale, long long* trace, void* stream);
+
 /* _compiled_adaln_forward / rms_norm / LayerNorm+modulate (transformer.py:16-31, model.py:744-758).
  * norm_kind 0 none, 1 RMS, 2 LayerNorm(no affine). */
 int ltx2_norm_modulate(const void* x, int32_t x_dtype, int64_t ldx, void* out_bf16, int64_t ldo, int32_t M, int32_t D,

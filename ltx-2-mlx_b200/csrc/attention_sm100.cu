@@ -10,7 +10,10 @@
 //                          BOTH A operands (Q and P) are read from tensor memory (tcgen05.mma with a TMEM A operand),
 //                          so shared memory only carries K and V: an SS-mode M=128,N=128 MMA would need the full
 //                          128 B/clk of shared-memory bandwidth and starve next to the TMA writes.
-//   warps 2-5 softmax:     one thread per query row.  Q's row is loaded from global and parked in TMEM once.
+//   warps 2-9 softmax:     TWO threads per query row (warps w and w+4 share a TMEM lane quarter and split the 128
+//                          key columns), so every SM sub-partition has two softmax warps to hide latencies; the
+//                          pair exchanges its block maximum through shared memory (named barrier of 64 threads).
+//                          Q's row is loaded from global and parked in TMEM once.
 //                          S_j is read from TMEM ONCE into registers; p = exp2(s*c - m*c) is written back to TMEM
 //                          as packed bf16 (64 columns).
 //                          The running output stays in TMEM; it is rescaled only when the row maximum grew by more
@@ -25,7 +28,7 @@ namespace ltx2 {
 
 namespace {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;   // TMA warp, MMA warp, 8 softmax warps
 constexpr int BQ = 128;    // queries per CTA
 constexpr int BKV = 128;   // keys per block
 
@@ -35,7 +38,7 @@ template <int DH>
 struct AttnCfg {
   static constexpr int kKBytes = BKV * DH * 2;
   static constexpr int kVBytes = DH * BKV * 2;
-  static constexpr int kSmemBytes = kKVStages * (kKBytes + kVBytes) + 1024 + 256;
+  static constexpr int kSmemBytes = kKVStages * (kKBytes + kVBytes) + 1024 + 256 + 3072;
   static constexpr int kTmemCols = 512;
   static constexpr int kOCol = 256;            // O accumulator (DH fp32 columns) after the two S buffers
   static constexpr int kPCol = 384;            // P: 128 x 128 bf16 = 64 columns
@@ -46,8 +49,11 @@ template <int DH>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
-                 float scale_log2, float scale, const float* __restrict__ gate_logits, float* __restrict__ lse_out) {
+                 float scale_log2, float scale, const float* __restrict__ gate_logits, float* __restrict__ lse_out,
+                 long long* __restrict__ trace) {
   using Cfg = AttnCfg<DH>;
+  // optional timeline trace of CTA (0,0): trace[j*8 + k] = clock64 at event k of block j (diagnostics only)
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -63,8 +69,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
   uint64_t* p_full = s_empty + 2;                  // 1   softmax -> MMA: P_j in TMEM (and O rescaled if needed)
   uint64_t* pv_done = p_full + 1;                  // 1   MMA -> softmax: P_j V_j retired (P reusable, O up to date)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 parity][2 half][128 rows]
+  float* xsum = xmax + 512;                                                          // [2 half][128 rows]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform role (see gemm_sm100.cu)
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int bh = blockIdx.y;
@@ -73,7 +81,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    mbar_init(q_ready, 128);
+    mbar_init(q_ready, 256);
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -82,9 +90,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
+      mbar_init(&s_empty[i], 256);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -98,73 +106,88 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&k_empty[st], ph ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    const bool leader = elect_one();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (leader) {
         mbar_expect_tx(&k_full[st], Cfg::kKBytes);
 #pragma unroll
         for (int i = 0; i < DH / 64; ++i)
           tma_load_3d(sK + st * Cfg::kKBytes + i * (BKV * 128), &tmap_k, &k_full[st], i * 64, j * BKV, bh);
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (leader) {
         mbar_expect_tx(&v_full[st], Cfg::kVBytes);
 #pragma unroll
         for (int i = 0; i < BKV / 64; ++i)
           tma_load_3d(sV + st * Cfg::kVBytes + i * (DH * 128), &tmap_v, &v_full[st], j * BKV + i * 64, 0, bh);
-        if (++st == kKVStages) { st = 0; ph ^= 1; }
       }
+      if (++st == kKVStages) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH);
-      int ks_st = 0, vs_st = 0;                 // K / V ring positions
-      uint32_t ks_ph = 0, vs_ph = 0;
-      auto issue_s = [&](int j) {
-        const int b = j & 1;
-        mbar_wait(&k_full[ks_st], ks_ph);
-        mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH);
+    int ks_st = 0, vs_st = 0;                 // K / V ring positions
+    uint32_t ks_ph = 0, vs_ph = 0;
+    auto issue_s = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(&k_full[ks_st], ks_ph);
+      mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t kd = umma_desc_k_sw128(smem_u32(sK + ks_st * Cfg::kKBytes));
+      if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(sK + ks_st * Cfg::kKBytes + (ks / 4) * (BKV * 128))) + 2 * (ks % 4);
-          umma_bf16_ts(tmem_base + b * BKV, tmem_base + Cfg::kQCol + ks * 8, bd, idesc_s, ks != 0);
-        }
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16_ts(tmem_base + b * BKV, tmem_base + Cfg::kQCol + ks * 8,
+                       kd + ((ks / 4) * (BKV * 128) >> 4) + 2 * (ks % 4), idesc_s, ks != 0);
         umma_commit(&s_full[b]);
         umma_commit(&k_empty[ks_st]);
-        if (++ks_st == kKVStages) { ks_st = 0; ks_ph ^= 1; }
-      };
-      mbar_wait(q_ready, 0);
+        if (tr) trace[j * 8 + 0] = clock64();
+      }
+      __syncwarp();
+      if (++ks_st == kKVStages) { ks_st = 0; ks_ph ^= 1; }
+    };
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_s(j + 1);
+      mbar_wait(p_full, j & 1);
+      if (tr && leader) trace[j * 8 + 1] = clock64();
+      mbar_wait(&v_full[vs_st], vs_ph);
       tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) issue_s(j + 1);
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[vs_st], vs_ph);
-        tc_fence_after();
+      const uint64_t vd = umma_desc_k_sw128(smem_u32(sV + vs_st * Cfg::kVBytes));
+      if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(sV + vs_st * Cfg::kVBytes + (ks / 4) * (DH * 128))) + 2 * (ks % 4);
-          umma_bf16_ts(tmem_base + Cfg::kOCol, tmem_base + Cfg::kPCol + ks * 8, bd, idesc_o, (j | ks) != 0);
-        }
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          umma_bf16_ts(tmem_base + Cfg::kOCol, tmem_base + Cfg::kPCol + ks * 8,
+                       vd + ((ks / 4) * (DH * 128) >> 4) + 2 * (ks % 4), idesc_o, (j | ks) != 0);
         umma_commit(&v_empty[vs_st]);
         umma_commit(pv_done);
-        if (++vs_st == kKVStages) { vs_st = 0; vs_ph ^= 1; }
+        if (tr) trace[j * 8 + 2] = clock64();
       }
+      __syncwarp();
+      if (++vs_st == kKVStages) { vs_st = 0; vs_ph ^= 1; }
     }
   } else {
-    // ===================== softmax + output (warps 2..5) =====================
+    // ===================== softmax + output (warps 2..9) =====================
+    constexpr int HC = BKV / 2;                         // key columns per thread
+    constexpr int OC = DH / 2;                          // output columns per thread
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                 // query row inside the tile
+    const int half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;                  // query row inside the tile
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t t_o = t_lane + Cfg::kOCol;
+    const uint32_t t_o = t_lane + Cfg::kOCol + half * OC;
+    const uint32_t bar_id = 1 + quarter;                // named barrier shared by the two warps of a row group
     float m_run = -INFINITY;                            // true running row maximum (raw scores)
     float m_used = 0.f;                                 // maximum the current scale of P, l and O refers to
-    float l = 0.f;
-    {
+    float l = 0.f;                                      // this thread's half of the row sum
+    if (half == 0) {
       // park this row of Q in tensor memory: column c of the Q region holds elements (2c, 2c+1)
       const int row = q0 + r;
       const uint4* qrow = reinterpret_cast<const uint4*>(q + (static_cast<int64_t>(bh) * Tq + (row < Tq ? row : 0)) * DH);
@@ -181,44 +204,49 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(q_ready);
     }
+    mbar_arrive(q_ready);
 
     for (int j = 0; j < nkv; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      const int kv_valid = Tk - j * BKV;                // >= 1
+      const int kv_valid = Tk - j * BKV - half * HC;    // valid columns of this thread's half (may be <= 0)
       mbar_wait(&s_full[b], ph);
+      const bool trs = tr && warp == 2 && lane == 0;
+      if (trs) trace[j * 8 + 3] = clock64();
       tc_fence_after();
-      uint32_t s[BKV];
+      uint32_t s[HC];
       {
         uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
         uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-        uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
-        uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
-        tmem_ld_32x32(t_lane + b * BKV + 0, s0);
-        tmem_ld_32x32(t_lane + b * BKV + 32, s1);
-        tmem_ld_32x32(t_lane + b * BKV + 64, s2);
-        tmem_ld_32x32(t_lane + b * BKV + 96, s3);
+        tmem_ld_32x32(t_lane + b * BKV + half * HC + 0, s0);
+        tmem_ld_32x32(t_lane + b * BKV + half * HC + 32, s1);
         tmem_ld_wait();
       }
       tc_fence_before();
       mbar_arrive(&s_empty[b]);                         // S_j now lives in registers
-      if (kv_valid < BKV) {
+      if (trs) trace[j * 8 + 4] = clock64();
+      if (kv_valid < HC) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
+        for (int i = 0; i < HC; ++i)
           if (i >= kv_valid) s[i] = 0xff800000u;        // -inf
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
             mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int i = 4; i < BKV; i += 4) {
+      for (int i = 4; i < HC; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(s[i]));
         mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
       }
-      m_run = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      float bm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // exchange the block maximum with the thread that owns the other half of this row
+      float* xm = xmax + (j & 1) * 256;
+      xm[half * 128 + r] = bm;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      bm = fmaxf(bm, xm[(half ^ 1) * 128 + r]);
+      m_run = fmaxf(m_run, bm);
       float alpha = 1.f;
       bool need = false;
       if (j == 0) {
@@ -230,9 +258,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
       }
       const float mb = m_used * scale_log2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk[BKV / 2];
+      uint32_t pk[HC / 2];
 #pragma unroll
-      for (int i = 0; i < BKV; i += 4) {
+      for (int i = 0; i < HC; i += 4) {
         const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, -mb));
         const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, -mb));
         const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, -mb));
@@ -242,11 +270,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
         pk[i / 2 + 1] = pack_bf16x2(e2, e3);
       }
       l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);       // P V_{j-1} retired: sP is free, O is complete
+      if (trs) trace[j * 8 + 5] = clock64();
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);       // P V_{j-1} retired: P is free, O is complete
+      if (trs) trace[j * 8 + 6] = clock64();
       if (__any_sync(0xffffffffu, need)) {
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < DH; c += 32) {
+        for (int c = 0; c < OC; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(t_o + c, v);
           tmem_ld_wait();
@@ -254,20 +284,18 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
           for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
           tmem_st_32x32(t_o + c, v);
         }
-        tmem_st_wait();
       }
-      {
-        uint32_t (&p0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
-        uint32_t (&p1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
-        tmem_st_32x32(t_lane + Cfg::kPCol, p0);
-        tmem_st_32x32(t_lane + Cfg::kPCol + 32, p1);
-        tmem_st_wait();
-      }
+      tmem_st_32x32(t_lane + Cfg::kPCol + half * (HC / 2), pk);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
+      if (trs) trace[j * 8 + 7] = clock64();
     }
     // ---- normalise, gate, store ----
     {
+      xsum[half * 128 + r] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      l += xsum[(half ^ 1) * 128 + r];
       mbar_wait(pv_done, (nkv - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.0f / l;
@@ -279,9 +307,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
         g = 2.0f / (1.0f + __expf(-z));
       }
       const float f = inv_l * g;
-      __nv_bfloat16* o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DH) + h_idx * DH;
+      __nv_bfloat16* o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DH) + h_idx * DH +
+                         half * OC;
 #pragma unroll
-      for (int c = 0; c < DH; c += 32) {
+      for (int c = 0; c < OC; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_o + c, v);
         tmem_ld_wait();
@@ -297,7 +326,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
           }
         }
       }
-      if (lse_out != nullptr && row < Tq)
+      if (half == 0 && lse_out != nullptr && row < Tq)
         lse_out[static_cast<int64_t>(bh) * Tq + row] = m_used * scale + logf(l);
       tc_fence_before();
     }
@@ -312,7 +341,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
 
 template <int DH>
 int launch_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
-                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream) {
+                     float scale, const float* gate_logits, float* lse_out, long long* trace, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
   static bool configured = false;
   if (!configured) {
@@ -338,7 +367,7 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
   const float kLog2e = 1.4426950408889634f;
   attention_kernel<DH><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk,
-      scale * kLog2e, scale, gate_logits, lse_out);
+      scale * kLog2e, scale, gate_logits, lse_out, trace);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
@@ -347,13 +376,13 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
 }  // namespace
 
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
-                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream) {
+                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace) {
   LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
   LTX2_REQUIRE(Tkp >= Tk && Tkp % 8 == 0, "attention: V^T pitch %d must be >= Tk=%d and a multiple of 8", Tkp, Tk);
   LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
   switch (Dh) {
-    case 128: return launch_attention<128>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, stream);
-    case 64: return launch_attention<64>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, stream);
+    case 128: return launch_attention<128>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, trace, stream);
+    case 64: return launch_attention<64>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, trace, stream);
     default:
       set_error("attention: head_dim %d unsupported (64 or 128)", Dh);
       return LTX2_ERR_INVALID;

@@ -41,6 +41,12 @@ int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int3
   return attention_bf16(q, k, vt, out, B, H, Tq, Tk, Tkp, Dh, scale, gate_logits, lse_out, S(stream));
 }
 
+// diagnostics: same as ltx2_attention, and CTA (0,0) writes clock64 stamps of its pipeline events to trace[nkv*8]
+int ltx2_attention_trace(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
+                         int32_t Tk, int32_t Tkp, int32_t Dh, float scale, long long* trace, void* stream) {
+  return attention_bf16(q, k, vt, out, B, H, Tq, Tk, Tkp, Dh, scale, nullptr, nullptr, S(stream), trace);
+}
+
 int ltx2_norm_modulate(const void* x, int32_t x_dtype, int64_t ldx, void* out, int64_t ldo, int32_t M, int32_t D,
                        int32_t norm_kind, float eps, const float* mod, int64_t mod_stride, int64_t shift_off,
                        int64_t scale_off, const int32_t* row_cls, void* stream) {

@@ -47,7 +47,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform role (see gemm_sm100.cu)
   const int lane = threadIdx.x & 31;
   const int tiles_w = (p.W + CTW - 1) / CTW;
   const int tiles_h = (p.H + CTH - 1) / CTH;
@@ -80,52 +80,57 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % num_m, nt = tile / num_m;
-        const int wx = mt % tiles_w;
-        const int hy = (mt / tiles_w) % tiles_h;
-        const int bt = mt / (tiles_w * tiles_h);          // b*T + t
-        const int b = bt / p.T, t = bt % p.T;
-        const int plane0 = b * (p.T + 2) + t;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / cchunks, cc = kb % cchunks;
-          const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile % num_m, nt = tile / num_m;
+      const int wx = mt % tiles_w;
+      const int hy = (mt / tiles_w) % tiles_h;
+      const int bt = mt / (tiles_w * tiles_h);          // b*T + t
+      const int b = bt / p.T, t = bt % p.T;
+      const int plane0 = b * (p.T + 2) + t;
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw,
                       hy * CTH + kh, plane0 + kt);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * CBK, nt * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        if (++cc == cchunks) { cc = 0; ++tap; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CBM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(CBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < CBK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int quarter = warp & 3;

@@ -47,7 +47,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* acc_empty = acc_full + 2;               // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (the shuffle makes the uniformity visible to the compiler, so the producer / MMA loops
+  // below run on the uniform datapath and tcgen05.mma is issued without a per-lane election loop)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
@@ -77,50 +79,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BM;
-        const int n0 = (tile / num_m) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BM;
+      const int n0 = (tile / num_m) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m0);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128B swizzle atom (descriptor address is in 16 B units)
             umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

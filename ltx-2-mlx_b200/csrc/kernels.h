@@ -40,7 +40,8 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
 //   log-sum-exp (natural log, scaled scores) per row to lse_out [B,H,Tq] fp32.
 // ---------------------------------------------------------------------------------
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
-                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream);
+                   int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
+                   long long* trace = nullptr);
 
 // ---------------------------------------------------------------------------------
 // row kernels (rowops.cu)
