@@ -198,6 +198,85 @@ def run_reference(args, c):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def vae_conv_flops(T, H, W, blocks=None, base=128):
+    """sum over convs of 2*Cin*Cout*27*T*H*W for one SimpleVideoDecoder pass."""
+    from ltx2_b200 import synthetic
+    cfg = synthetic.VaeConfig(decoder_blocks=blocks or synthetic.DEFAULT_DECODER_BLOCKS, base_channels=base)
+    total, C = 2 * 128 * (base * 8) * 27 * T * H * W, base * 8
+    for kind, p, c in cfg.stages():
+        if kind == "res":
+            total += p["num_layers"] * 2 * (2 * c * c * 27 * T * H * W)
+        else:
+            s = p["stride"]
+            total += 2 * c * (s[0] * s[1] * s[2] * c // p["multiplier"]) * 27 * T * H * W
+            T, H, W, C = T * s[0] - (1 if s[0] > 1 else 0), H * s[1], W * s[2], c // p["multiplier"]
+    return total + 2 * C * 48 * 27 * T * H * W
+
+
+def bench_vae(args, dev, rank):
+    """decode_latent of a 9x16x24 latent (65 frames @ 512x768) exactly as the reference schedules it
+    (7-frame chunks, overlap 2, cross-fade, uint8), device-timed; plus the conv kernel's roofline."""
+    import ctypes as C
+    import torch
+    from ltx2_b200 import _lib, synthetic
+    from ltx2_b200.video_vae import SimpleVideoDecoder, chunk_plan, decode_latent
+    vcfg = synthetic.VaeConfig()
+    dec = SimpleVideoDecoder(device=dev)
+    dec.load_weights(synthetic.iter_vae_weights(vcfg, seed=0, device=dev, dtype=torch.bfloat16))
+    assert not dec.missing_weights()
+    lat = synthetic.latents((1, 128, 9, 16, 24), seed=43 + rank).to(dev)
+    frames = 65
+    for _ in range(2):
+        out = decode_latent(lat, dec)
+    torch.cuda.synchronize()
+    n = max(3, min(args.steps, 8))
+    l0 = _lib.lib().ltx2_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out = decode_latent(lat, dec)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    launches = (_lib.lib().ltx2_launch_count() - l0) // n
+    assert out.shape == (frames, 512, 768, 3)
+    # e2e: host latent in, uint8 frames on the host out
+    lat_h = lat.cpu().pin_memory()
+    out_h = torch.empty(frames, 512, 768, 3, dtype=torch.uint8).pin_memory()
+    e0.record()
+    for _ in range(n):
+        out_h.copy_(decode_latent(lat_h, dec), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / n
+    # roofline of the conv kernel: one profiled pass over the first (7 latent frame) chunk
+    L = _lib.lib()
+    _lib.check(L.ltx2_vae_set_profile(dec._h, 1))
+    dec(lat[:, :, :7].contiguous(), timestep=0.05)
+    pm, pf, pl = C.c_double(), C.c_double(), C.c_int64()
+    _lib.check(L.ltx2_vae_profile_read(dec._h, C.byref(pm), C.byref(pf), C.byref(pl)))
+    _lib.check(L.ltx2_vae_set_profile(dec._h, 0))
+    pk = peaks()
+    tf = pf.value / (pm.value * 1e-3) / 1e12 if pm.value > 0 else 0.0
+    plan = chunk_plan(9)
+    alg = sum(vae_conv_flops(b - a, 16, 24) for a, b in plan)
+    return {
+        "metric": "VAE decode frames/sec", "value": frames * 1000.0 / ms, "unit": "frames/s", "ms_per_decode": ms,
+        "config": {"workload": "decode_latent, latent 1x128x9x16x24 -> 65 frames @ 512x768, V2.0 decoder stack "
+                               "(base 128, 5 res blocks/group), reference chunking 7/2 -> chunks " + str(plan),
+                   "noise": "decode_noise_scale 0.025 (reference default), timestep 0.05"},
+        "gpu_launches": int(launches),
+        "e2e": {"value": frames * 1000.0 / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(lat_h.numel() * 4),
+                "d2h_bytes_per_step": int(out_h.numel())},
+        "roofline": {"bound": "tensor", "kernel": "conv3d_kernel (tcgen05 implicit GEMM, all convs of one 7-frame chunk)",
+                     "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"], "traffic": None,
+                     "launches": int(pl.value), "ms_in_decode": pm.value, "flops_in_decode": pf.value,
+                     "decode": {"algorithmic_flops": alg, "achieved": alg / (ms * 1e-3) / 1e12,
+                                "frac": alg / (ms * 1e-3) / 1e12 / pk["tf"]}},
+    }
+
+
 def run_ours(args, c):
     import ctypes as C
     import torch
@@ -295,6 +374,13 @@ def run_ours(args, c):
     _lib.check(L.ltx2_dit_profile_read(model._h, pm, pf, pl, 2))
     _lib.check(L.ltx2_dit_set_profile(model._h, 0))
 
+    # ---- second half of the metric: VAE decode frames/s (65 frames @ 512x768, BASELINE.json configs[4]) ----
+    vae = None
+    if args.config == "19b" and not args.no_vae:
+        del x0model, model
+        torch.cuda.empty_cache()
+        vae = bench_vae(args, dev, rank)
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +416,8 @@ def run_ours(args, c):
                      "step": {"algorithmic_flops": fl, "achieved": fl / (ms_step * 1e-3) / 1e12,
                               "frac": fl / (ms_step * 1e-3) / 1e12 / pk["tf"]}},
     }
+    if vae is not None:
+        out["vae"] = vae
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(c)
     print(json.dumps(out))
@@ -346,6 +434,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="19b", choices=list(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     c = CONFIGS[args.config]

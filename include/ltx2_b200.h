@@ -170,6 +170,10 @@ int ltx2_vae_output_shape(LtxVae* vae, const int64_t in_shape[5], int64_t out_sh
 int ltx2_vae_decode(LtxVae* vae, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream);
 
+/* Measurement hooks (bench.py): CUDA-event timing of the conv launches of one decode. */
+int ltx2_vae_set_profile(LtxVae* vae, int32_t on);
+int ltx2_vae_profile_read(LtxVae* vae, double* ms_out, double* flops_out, int64_t* launches_out);
+
 /* decode_latent's chunk stitching (:749-790): dst [BC,T_dst,HW] <- cross-fade of src [BC,T_src,HW] placed at frame t0,
  * linear ramp over the first `overlap` frames, plain copy after; and the uint8 conversion (:793-798):
  * video [1,3,T,H,W] fp32 in [-1,1] -> uint8 [T,H,W,3]. */

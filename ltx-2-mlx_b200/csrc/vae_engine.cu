@@ -71,7 +71,15 @@ struct VArena {
 
 }  // namespace
 
+struct VaeProfiler {                 // CUDA events around every conv launch (bench.py roofline leg); off by default
+  bool on = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<double> flops;
+  size_t used = 0;
+};
+
 struct LtxVae {
+  VaeProfiler prof;
   LtxVaeConfig cfg;
   std::unordered_map<std::string, VSlot> slots;
   char* arena = nullptr;
@@ -248,6 +256,7 @@ void ltx2_vae_destroy(LtxVae* e) {
   if (!e) return;
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
+  for (auto ev : e->prof.events) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -403,8 +412,25 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
       p.ft = up->ft; p.fh = up->fh; p.fw = up->fw;
       p.c_d2s = up->residual ? w.Cin / (up->ft * up->fh * up->fw) : 0;
     }
-    return conv3d_bf16(xin_padded, w.w, p, st);
+    VaeProfiler& pf = e->prof;
+    if (pf.on) {
+      if (pf.used + 2 > pf.events.size()) {
+        const size_t old = pf.events.size();
+        pf.events.resize(old + 256);
+        for (size_t i = old; i < pf.events.size(); ++i) cudaEventCreate(&pf.events[i]);
+      }
+      pf.flops.push_back(2.0 * w.Cin * double(w.Cout) * 27.0 * B * dd.T * double(dd.H) * dd.W);
+      cudaEventRecord(pf.events[pf.used], st);
+    }
+    const int r = conv3d_bf16(xin_padded, w.w, p, st);
+    if (pf.on) {
+      cudaEventRecord(pf.events[pf.used + 1], st);
+      pf.used += 2;
+    }
+    return r;
   };
+  e->prof.used = 0;
+  e->prof.flops.clear();
 
   d = Dims{(int)shape[2], (int)shape[3], (int)shape[4], Cl};
   const bool inject = use_t && noise != nullptr && noise_scale != 0.f;
@@ -450,6 +476,27 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod, 0, int64_t(2) * Cf, 1, B, 2, Cf, st));
   LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, Cf, 1, mod, int64_t(2) * Cf, 0, Cf, 1e-6f, causal, st));
   return conv(e->conv_out, xp, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+}
+
+int ltx2_vae_set_profile(LtxVae* e, int32_t on) {
+  LTX2_REQUIRE(e != nullptr, "vae_set_profile: null handle");
+  e->prof.on = on != 0;
+  return LTX2_OK;
+}
+
+// after a profiled decode: device sync, then summed conv kernel time (ms), algorithmic conv FLOPs and launch count
+int ltx2_vae_profile_read(LtxVae* e, double* ms_out, double* flops_out, int64_t* launches_out) {
+  LTX2_REQUIRE(e && ms_out && flops_out && launches_out, "vae_profile_read: null argument");
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  *ms_out = 0; *flops_out = 0; *launches_out = 0;
+  for (size_t i = 0; i * 2 < e->prof.used; ++i) {
+    float ms = 0.f;
+    LTX2_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof.events[2 * i], e->prof.events[2 * i + 1]));
+    *ms_out += ms;
+    *flops_out += e->prof.flops[i];
+    *launches_out += 1;
+  }
+  return LTX2_OK;
 }
 
 int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, int32_t T_src, int32_t HW, int32_t t0,
