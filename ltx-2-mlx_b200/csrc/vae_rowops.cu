@@ -51,75 +51,88 @@ __global__ void latent_to_padded_kernel(const Tin* __restrict__ lat, const float
   }
 }
 
-// one warp per padded output position; the source row (C <= 1024 channels) lives in registers
-constexpr int kMaxCPerLane = 32;   // C <= 1024
+// One CTA per padded output row (b, tp, hp); P = min(C/8, 32) lanes cooperate on one position (16 B per lane and
+// unit), so a warp handles 32/P positions per step.  A lane's channels are the same for every position of the row:
+// its shift/scale values are loaded once.  All index math is 32-bit and done once per row.
+constexpr int kPadMaxU = 4;        // units of 8 channels per lane: C <= 32 * 8 * 4 = 1024
 
+template <int U>
 __global__ void __launch_bounds__(256)
-norm_act_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int T, int H, int W,
-                    int C, int act, const float* __restrict__ mod, int64_t mod_stride, int64_t shift_off,
-                    int64_t scale_off, float eps, int causal) {
-  const int64_t npos = static_cast<int64_t>(B) * (T + 2) * (H + 2) * (W + 2);
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int units = C / 8;                     // 16-byte units per row
-  for (int64_t pi = warp0; pi < npos; pi += nwarps) {
-    int64_t r = pi;
-    const int wp = r % (W + 2); r /= (W + 2);
-    const int hp = r % (H + 2); r /= (H + 2);
-    const int tp = r % (T + 2);
-    const int b = r / (T + 2);
-    const int t = src_t(tp, T, causal), h = reflect1(hp - 1, H), w = reflect1(wp - 1, W);
-    const __nv_bfloat16* src = x + (((static_cast<int64_t>(b) * T + t) * H + h) * W + w) * C;
-    __nv_bfloat16* dst = out + pi * C;
-    if (!act) {
-      for (int u = lane; u < units; u += 32)
-        *reinterpret_cast<uint4*>(dst + u * 8) = *reinterpret_cast<const uint4*>(src + u * 8);
-      continue;
-    }
-    float v[kMaxCPerLane];
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxCPerLane / 8; ++k) {
-      const int u = lane + k * 32;
-      if (u < units) {
-        const uint4 q = *reinterpret_cast<const uint4*>(src + u * 8);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(hh[j]);
-          v[k * 8 + 2 * j] = f.x;
-          v[k * 8 + 2 * j + 1] = f.y;
-          ss += f.x * f.x + f.y * f.y;
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / C + eps);
+norm_act_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, int H, int W, int C,
+                    int P, int act, const float* __restrict__ mod, int mod_stride, int shift_off, int scale_off,
+                    float eps, int causal) {
+  const int row = blockIdx.x;                       // (b*(T+2) + tp)*(H+2) + hp
+  const int hp = row % (H + 2);
+  const int tp = (row / (H + 2)) % (T + 2);
+  const int b = row / ((H + 2) * (T + 2));
+  const int t = src_t(tp, T, causal), h = reflect1(hp - 1, H);
+  const __nv_bfloat16* src_row = x + (static_cast<int64_t>(b) * T + t) * H * static_cast<int64_t>(W) * C +
+                                 static_cast<int64_t>(h) * W * C;
+  __nv_bfloat16* dst_row = out + static_cast<int64_t>(row) * (W + 2) * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / P, pl = lane % P;          // position slot inside the warp, lane inside the position group
+  const int per_warp = 32 / P;
+  float sh[U][8], sc[U][8];
+  if (act) {
     const float* mrow = mod + static_cast<int64_t>(b) * mod_stride;
 #pragma unroll
-    for (int k = 0; k < kMaxCPerLane / 8; ++k) {
-      const int u = lane + k * 32;
-      if (u < units) {
+    for (int u = 0; u < U; ++u) {
+      const int c0 = (pl + u * P) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; j += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(mrow + shift_off + c0 + j);
+        const float4 d = *reinterpret_cast<const float4*>(mrow + scale_off + c0 + j);
+        sh[u][j] = a.x; sh[u][j + 1] = a.y; sh[u][j + 2] = a.z; sh[u][j + 3] = a.w;
+        sc[u][j] = 1.f + d.x; sc[u][j + 1] = 1.f + d.y; sc[u][j + 2] = 1.f + d.z; sc[u][j + 3] = 1.f + d.w;
+      }
+    }
+  }
+  const float inv_c = 1.0f / C;
+  for (int wp0 = warp * per_warp; wp0 < W + 2; wp0 += 8 * per_warp) {
+    const int wp = wp0 + sub;
+    const bool ok = wp < W + 2;
+    const int w = reflect1((ok ? wp : 0) - 1, W);
+    const __nv_bfloat16* src = src_row + static_cast<int64_t>(w) * C;
+    uint4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = ok ? *reinterpret_cast<const uint4*>(src + (pl + u * P) * 8) : make_uint4(0, 0, 0, 0);
+    if (!act) {
+      if (ok) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) *reinterpret_cast<uint4*>(dst_row + static_cast<int64_t>(wp) * C + (pl + u * P) * 8) = q[u];
+      }
+      continue;
+    }
+    float v[U][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(hh[j]);
+        v[u][2 * j] = f.x;
+        v[u][2 * j + 1] = f.y;
+        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+      }
+    }
+    for (int o = P >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_c + eps);
+    if (ok) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         float o8[8];
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 sh = *reinterpret_cast<const float4*>(mrow + shift_off + u * 8 + j);
-          const float4 sc = *reinterpret_cast<const float4*>(mrow + scale_off + u * 8 + j);
-          const float shv[4] = {sh.x, sh.y, sh.z, sh.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float y = v[k * 8 + j + q] * rstd * (1.f + scv[q]) + shv[q];
-            o8[j + q] = y / (1.f + __expf(-y));
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(v[u][j] * rstd, sc[u][j], sh[u][j]);
+          o8[j] = __fdividef(y, 1.f + __expf(-y));
         }
-        uint4 q;
-        q.x = pack_bf16x2(o8[0], o8[1]);
-        q.y = pack_bf16x2(o8[2], o8[3]);
-        q.z = pack_bf16x2(o8[4], o8[5]);
-        q.w = pack_bf16x2(o8[6], o8[7]);
-        *reinterpret_cast<uint4*>(dst + u * 8) = q;
+        uint4 w4;
+        w4.x = pack_bf16x2(o8[0], o8[1]);
+        w4.y = pack_bf16x2(o8[2], o8[3]);
+        w4.z = pack_bf16x2(o8[4], o8[5]);
+        w4.w = pack_bf16x2(o8[6], o8[7]);
+        *reinterpret_cast<uint4*>(dst_row + static_cast<int64_t>(wp) * C + (pl + u * P) * 8) = w4;
       }
     }
   }
@@ -225,14 +238,24 @@ int latent_to_padded(const void* latent, int dtype, const float* std_, const flo
 
 int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, int act, const float* mod,
                  int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream) {
-  LTX2_REQUIRE(C % 8 == 0 && C <= 32 * kMaxCPerLane, "norm_act_pad: C=%d unsupported", C);
+  LTX2_REQUIRE(C % 64 == 0 && C <= 32 * 8 * kPadMaxU && (C / 8 >= 32 ? (C / 8) % 32 == 0 : (32 % (C / 8)) == 0),
+               "norm_act_pad: C=%d unsupported (64, 128, 256, 512, 768 or 1024)", C);
   LTX2_REQUIRE(H >= 2 && W >= 2, "reflect padding needs H, W >= 2 (got %d x %d)", H, W);
   LTX2_REQUIRE(!act || mod != nullptr, "norm_act_pad: modulation table required");
-  const int64_t npos = static_cast<int64_t>(B) * (T + 2) * (H + 2) * (W + 2);
-  const int g = grid_for(npos * 32, 256);
-  norm_act_pad_kernel<<<g, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                             reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, C, act, mod, mod_stride,
-                                             shift_off, scale_off, eps, causal);
+  const int units = C / 8;
+  const int P = units >= 32 ? 32 : units;
+  const int U = units / P;
+  const unsigned rows = static_cast<unsigned>(B) * (T + 2) * (H + 2);
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+  const int ms = static_cast<int>(mod_stride), so = static_cast<int>(shift_off), sc = static_cast<int>(scale_off);
+  switch (U) {
+    case 1: norm_act_pad_kernel<1><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
+    case 2: norm_act_pad_kernel<2><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
+    case 3: norm_act_pad_kernel<3><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
+    case 4: norm_act_pad_kernel<4><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
+    default: set_error("norm_act_pad: C=%d unsupported", C); return LTX2_ERR_INVALID;
+  }
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
