@@ -198,6 +198,12 @@ int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int3
                    int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
                    void* stream);
 
+/* Same attention with V in row form (no transpose pass): element (b,h,t,d) at v + b*stride_b + h*stride_h +
+ * t*stride_t + d, e.g. the V third of a fused QKV projection output (stride_t = 3*inner, stride_h = Dh). */
+int ltx2_attention_vrows(const void* q, const void* k, const void* v, int64_t v_stride_t, int64_t v_stride_h,
+                         int64_t v_stride_b, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t Dh,
+                         float scale, const float* gate_logits, float* lse_out, void* stream);
+
 /* Diagnostics: ltx2_attention plus a clock64 timeline of CTA (0,0): trace[j*8 + e], e = 0 QK_j issued, 1 P_j seen by
  * the MMA thread, 2 PV_j issued, 3 S_j seen by softmax, 4 S_j in registers, 5 exps done, 6 PV_{j-1} retired,
  * 7 P_j published (tools/attn_trace.py). */

@@ -45,7 +45,7 @@ struct AttnCfg {
   static constexpr int kQCol = 448;            // Q: 128 x DH bf16 = DH/2 columns
 };
 
-template <int DH>
+template <int DH, bool VROWS>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
@@ -121,9 +121,15 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
       mbar_wait(&v_empty[st], ph ^ 1);
       if (leader) {
         mbar_expect_tx(&v_full[st], Cfg::kVBytes);
+        if (VROWS) {   // V rows [keys, d]: one 128-key x 64-channel box per 64 channels (MN-major B operand)
 #pragma unroll
-        for (int i = 0; i < BKV / 64; ++i)
-          tma_load_3d(sV + st * Cfg::kVBytes + i * (DH * 128), &tmap_v, &v_full[st], j * BKV + i * 64, 0, bh);
+          for (int i = 0; i < DH / 64; ++i)
+            tma_load_4d(sV + st * Cfg::kVBytes + i * (BKV * 128), &tmap_v, &v_full[st], i * 64, j * BKV, bh % H, bh / H);
+        } else {       // V^T [d, keys]: one DH x 64-key box per 64 keys (K-major B operand)
+#pragma unroll
+          for (int i = 0; i < BKV / 64; ++i)
+            tma_load_3d(sV + st * Cfg::kVBytes + i * (DH * 128), &tmap_v, &v_full[st], j * BKV + i * 64, 0, bh);
+        }
       }
       if (++st == kKVStages) { st = 0; ph ^= 1; }
     }
@@ -131,7 +137,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, DH, VROWS);
     int ks_st = 0, vs_st = 0;                 // K / V ring positions
     uint32_t ks_ph = 0, vs_ph = 0;
     auto issue_s = [&](int j) {
@@ -161,12 +167,15 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
       if (tr && leader) trace[j * 8 + 1] = clock64();
       mbar_wait(&v_full[vs_st], vs_ph);
       tc_fence_after();
-      const uint64_t vd = umma_desc_k_sw128(smem_u32(sV + vs_st * Cfg::kVBytes));
+      const uint32_t v_addr = smem_u32(sV + vs_st * Cfg::kVBytes);
+      // K-major V^T: 64-key boxes of DH rows; MN-major V: 16 keys = 2048 B per K step, 64-channel boxes 16 KB apart
+      const uint64_t vd = VROWS ? umma_desc_mn_sw128(v_addr, BKV * 128, 1024) : umma_desc_k_sw128(v_addr);
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks)
           umma_bf16_ts(tmem_base + Cfg::kOCol, tmem_base + Cfg::kPCol + ks * 8,
-                       vd + ((ks / 4) * (DH * 128) >> 4) + 2 * (ks % 4), idesc_o, (j | ks) != 0);
+                       vd + (VROWS ? ks * (2048 >> 4) : ((ks / 4) * (DH * 128) >> 4) + 2 * (ks % 4)), idesc_o,
+                       (j | ks) != 0);
         umma_commit(&v_empty[vs_st]);
         umma_commit(pv_done);
         if (tr) trace[j * 8 + 2] = clock64();
@@ -339,13 +348,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
   }
 }
 
-template <int DH>
-int launch_attention(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
+template <int DH, bool VROWS>
+int launch_attention(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
                      float scale, const float* gate_logits, float* lse_out, long long* trace, cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
   static bool configured = false;
   if (!configured) {
-    LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DH, VROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     configured = true;
   }
@@ -357,15 +366,22 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
     uint32_t box[3] = {64, BKV, 1};
     LTX2_PROPAGATE(make_tensor_map_bf16(&mk, k, 3, dims, str, box));
   }
-  {
+  if (VROWS) {
+    uint64_t dims[4] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(Tk), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(B)};
+    uint64_t str[3] = {static_cast<uint64_t>(v.stride_t) * 2, static_cast<uint64_t>(v.stride_h) * 2,
+                       static_cast<uint64_t>(v.stride_b) * 2};
+    uint32_t box[4] = {64, BKV, 1, 1};
+    LTX2_PROPAGATE(make_tensor_map_bf16(&mv, v.ptr, 4, dims, str, box));
+  } else {
     uint64_t dims[3] = {static_cast<uint64_t>(Tk), static_cast<uint64_t>(DH), BH};
-    uint64_t str[2] = {static_cast<uint64_t>(Tkp) * 2, static_cast<uint64_t>(Tkp) * DH * 2};
+    uint64_t str[2] = {static_cast<uint64_t>(v.Tkp) * 2, static_cast<uint64_t>(v.Tkp) * DH * 2};
     uint32_t box[3] = {64, static_cast<uint32_t>(DH), 1};
-    LTX2_PROPAGATE(make_tensor_map_bf16(&mv, vt, 3, dims, str, box));
+    LTX2_PROPAGATE(make_tensor_map_bf16(&mv, v.ptr, 3, dims, str, box));
   }
   dim3 grid((Tq + BQ - 1) / BQ, static_cast<unsigned>(BH));
   const float kLog2e = 1.4426950408889634f;
-  attention_kernel<DH><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
+  attention_kernel<DH, VROWS><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk,
       scale * kLog2e, scale, gate_logits, lse_out, trace);
   LTX2_CUDA_CHECK(cudaGetLastError());
@@ -375,18 +391,30 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
 
 }  // namespace
 
+int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk, int Dh,
+                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace) {
+  LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
+  LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
+  LTX2_REQUIRE(Dh == 64 || Dh == 128, "attention: head_dim %d unsupported (64 or 128)", Dh);
+  if (v.rows) {
+    LTX2_REQUIRE(v.stride_t % 8 == 0 && v.stride_h % 8 == 0 && v.stride_b % 8 == 0,
+                 "attention: V strides must be multiples of 8 elements (16 B)");
+    return Dh == 128 ? launch_attention<128, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream)
+                     : launch_attention<64, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream);
+  }
+  LTX2_REQUIRE(v.Tkp >= Tk && v.Tkp % 8 == 0, "attention: V^T pitch %lld must be >= Tk=%d and a multiple of 8",
+               (long long)v.Tkp, Tk);
+  return Dh == 128 ? launch_attention<128, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream)
+                   : launch_attention<64, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream);
+}
+
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
                    int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace) {
-  LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
-  LTX2_REQUIRE(Tkp >= Tk && Tkp % 8 == 0, "attention: V^T pitch %d must be >= Tk=%d and a multiple of 8", Tkp, Tk);
-  LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
-  switch (Dh) {
-    case 128: return launch_attention<128>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, trace, stream);
-    case 64: return launch_attention<64>(q, k, vt, out, B, H, Tq, Tk, Tkp, scale, gate_logits, lse_out, trace, stream);
-    default:
-      set_error("attention: head_dim %d unsupported (64 or 128)", Dh);
-      return LTX2_ERR_INVALID;
-  }
+  AttnV v;
+  v.ptr = vt;
+  v.rows = 0;
+  v.Tkp = Tkp;
+  return attention_bf16_v(q, k, v, out, B, H, Tq, Tk, Dh, scale, gate_logits, lse_out, stream, trace);
 }
 
 }  // namespace ltx2

@@ -523,7 +523,6 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
   const AttnW& w = *c.w;
   const int inner = w.inner, H = w.heads, Dh = w.dh;
   const float eps = e->cfg.norm_eps;
-  const int Tkp = (c.Tk + 63) / 64 * 64;
   const bf16 *qp, *kp, *vp;
   int64_t ldq, ldk;
   if (w.fused_qkv) {
@@ -538,7 +537,13 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
   }
   LTX2_PROPAGATE(headnorm_rope(qp, ldq, w.qnorm, c.qcos, c.qsin, sb.qh, B, c.Tq, H, Dh, eps, st));
   LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
-  LTX2_PROPAGATE(v_transpose(vp, ldk, sb.vt, B, c.Tk, Tkp, H, Dh, st));
+  // V is consumed in place from the projection output (row form, MN-major MMA operand): no transpose pass
+  AttnV av;
+  av.ptr = vp;
+  av.rows = 1;
+  av.stride_t = ldk;
+  av.stride_h = Dh;
+  av.stride_b = int64_t(c.Tk) * ldk;
   const float* gl = nullptr;
   if (w.gate.w != nullptr) {
     // to_gate_logits(x): [Mq, H]; H < 32 is padded by the GEMM's N%32 rule, so heads must be a multiple of 32
@@ -551,8 +556,7 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     gl = sb.gate_logits;
   }
   ProfScope ps(PROF_ATTN, 4.0 * B * H * double(c.Tq) * c.Tk * Dh, st);
-  return attention_bf16(sb.qh, sb.kh, sb.vt, sb.attn, B, H, c.Tq, c.Tk, Tkp, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr,
-                        st);
+  return attention_bf16_v(sb.qh, sb.kh, av, sb.attn, B, H, c.Tq, c.Tk, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr, st);
 }
 
 }  // namespace

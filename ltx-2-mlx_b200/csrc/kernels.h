@@ -39,6 +39,18 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
 //   partial (optional, for ring attention): when lse_out != null the kernel also writes the
 //   log-sum-exp (natural log, scaled scores) per row to lse_out [B,H,Tq] fp32.
 // ---------------------------------------------------------------------------------
+// V operand of the attention: either transposed [B,H,Dh,Tkp] (rows = 0) or in row form, element (b,h,t,d) at
+// ptr + b*stride_b + h*stride_h + t*stride_t + d (rows = 1) -- e.g. straight out of the fused QKV GEMM output
+// (stride_t = 3*inner, stride_h = Dh, stride_b = T*3*inner), consumed as an MN-major tcgen05 B operand.
+struct AttnV {
+  const void* ptr = nullptr;
+  int rows = 0;
+  int64_t Tkp = 0;
+  int64_t stride_t = 0, stride_h = 0, stride_b = 0;
+};
+int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk, int Dh,
+                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
+                     long long* trace = nullptr);
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
                    int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
                    long long* trace = nullptr);

@@ -223,3 +223,19 @@ def test_x0_and_reference_metal_kernels():
     assert ops.silu_mul(e, e).shape == (0, 8)
     with pytest.raises(AssertionError):
         ops.silu_mul(rnd(2, 4), rnd(2, 5))
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,Dh", [(1, 2, 256, 384, 128), (2, 3, 200, 333, 128), (1, 4, 130, 65, 64),
+                                          (1, 32, 3456, 3456, 128)])
+def test_attention_v_in_row_form_from_fused_qkv(B, H, Tq, Tk, Dh):
+    """V consumed directly from a token-major [B, T, 3*inner] buffer (MN-major tcgen05 operand), no transpose pass."""
+    from ltx2_b200 import ops
+    inner = H * Dh
+    q = rnd(B, H, Tq, Dh, seed=70, dtype=torch.bfloat16)
+    k = rnd(B, H, Tk, Dh, seed=71, dtype=torch.bfloat16)
+    qkv = rnd(B, Tk, 3 * inner, seed=72, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * inner:]
+    out = ops.attention_vrows(q, k, v_rows, H, Dh)
+    v = v_rows.reshape(B, Tk, H, Dh).permute(0, 2, 1, 3)
+    ref, _ = _attn_ref(q, k, v)
+    assert rel_err(out.float(), ref) < 1.2e-2
