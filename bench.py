@@ -17,8 +17,10 @@ seeded random-init checkpoint of that architecture and latents/context are synth
             on the host cores: one of the 48 blocks at the same N, extrapolated x48 -- a reported baseline only
   --impl reference  runs only that CPU arm (rank 0) with the same metric/config.
 
-N > 1 ranks (until context-parallel attention lands): independent replicas, one sample per
-GPU, no data-path collective, scaling = "weak", value = total steps/s over all ranks.
+N > 1 ranks: context parallel by default -- ONE sample, token axis sharded over the ranks,
+scaling = "strong", value = steps/s of that sample (max over ranks).  `--parallel replicas` runs independent samples
+(weak scaling, no data-path collective).  The VAE leg at N > 1 decodes on rank 0 only (its two temporal chunks do
+not fill more GPUs at 65 frames; multi-GPU VAE is next-round work).
 """
 from __future__ import annotations
 
@@ -305,7 +307,12 @@ def run_ours(args, c):
     x0model = X0Model(model)
 
     N, S = c["F"] * c["H"] * c["W"], c["S"]
-    lat0 = synthetic.latents((1, N, 128), seed=42 + rank)
+    cp = world > 1 and args.parallel == "cp"
+    if cp:
+        # ONE sample sharded over the ranks (context parallel): same inputs on every rank
+        from ltx2_b200 import context_parallel
+        context_parallel.enable(model, batch=1, n_total=N)
+    lat0 = synthetic.latents((1, N, 128), seed=42 + (0 if cp else rank))
     ctx0 = (synthetic.latents((1, S, c["caption"]), seed=7, std=0.1)).to(torch.bfloat16)
     pos0 = synthetic.video_positions(1, c["F"], c["H"], c["W"], fps=24.0)
     lat_d, ctx_d, pos_d = lat0.to(dev), ctx0.to(dev), pos0.to(dev)
@@ -376,10 +383,13 @@ def run_ours(args, c):
 
     # ---- second half of the metric: VAE decode frames/s (65 frames @ 512x768, BASELINE.json configs[4]) ----
     vae = None
-    if args.config == "19b" and not args.no_vae:
-        del x0model, model
-        torch.cuda.empty_cache()
+    if args.config == "19b" and not args.no_vae and rank == 0:
+        if world == 1:
+            del x0model, model
+            torch.cuda.empty_cache()
         vae = bench_vae(args, dev, rank)
+    if world > 1:
+        dist.barrier()
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -392,20 +402,25 @@ def run_ours(args, c):
 
     pk = peaks()
     ms_step = ms / args.steps
-    value = world * 1000.0 / ms_step
+    samples = 1 if cp else world
+    value = samples * 1000.0 / ms_step
     gemm_tf = pf[0] / (pm[0] * 1e-3) / 1e12 if pm[0] > 0 else 0.0
     attn_tf = pf[1] / (pm[1] * 1e-3) / 1e12 if pm[1] > 0 else 0.0
     fl = flops_per_step(c)
     out = {
         "metric": "denoising steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if cp else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": c["name"], "parallelism": "replicas" if world > 1 else "single",
+        "config": {"workload": c["name"],
+                   "parallelism": (f"cp{world}: token axis sharded, heads re-sharded for self-attention by peer-memory "
+                                   f"stores fused into the q/k-norm and attention kernels" if cp else
+                                   (f"replicas x{world}" if world > 1 else "single")),
                    "l2": "weights read per step (25.8 GB bf16) exceed the 126 MB L2; no flush needed",
                    "weights": "seeded random init, reference key names", "residual_stream": "fp32",
                    "gemm_operands": "bf16, fp32 accumulate"},
         "clocks": clocks, "gpu_launches": int(launches), "finite": finite,
-        "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": samples * 1000.0 * args.steps / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all DiT linears of one step)",
                      "achieved": gemm_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"],
@@ -435,6 +450,8 @@ def main():
     ap.add_argument("--config", default="19b", choices=list(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
+    ap.add_argument("--parallel", default="cp", choices=["cp", "replicas"],
+                    help="N>1: context-parallel single sample (strong scaling) or independent replicas (weak)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     c = CONFIGS[args.config]

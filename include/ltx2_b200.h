@@ -124,9 +124,17 @@ int ltx2_dit_set_profile(LtxDit* dit, int32_t on);
 int ltx2_dit_profile_read(LtxDit* dit, double* ms_out, double* flops_out, int64_t* launches_out, int32_t n_classes);
 int64_t ltx2_launch_count(void);
 
-/* Context-parallel (ring attention) setup, SURVEY.md section 8(e).  rank/world describe this
- * process' slice of the token axis; the K/V exchange itself is driven by the host layer
- * (torch.distributed NCCL P2P) through ltx2_dit_forward_cp hooks -- see DESIGN.md. */
+/* Context parallelism over the token axis (no reference counterpart -- the reference is
+ * single-device).  Rank r owns tokens [r*N/P, (r+1)*N/P) and, inside self-attention, heads [r*H/P, (r+1)*H/P).
+ * The two re-shards per block are fused into the producing kernels as stores to peer memory over NVLink (q/k-norm+
+ * RoPE kernel: token->head; attention epilogue: head->token) and ordered by flag barriers in peer memory.
+ *   1. every rank: ltx2_dit_cp_init(...) allocates its exchange region and returns a 64-byte CUDA IPC handle;
+ *   2. the host layer all-gathers the handles (any transport) and calls ltx2_dit_cp_connect on every rank,
+ *      followed by a host barrier;
+ *   3. ltx2_dit_forward is then called with the LOCAL token slice (tokens = N/P) on every rank, collectively.
+ * Round-1 limits: video-only, non-gated model (LTX-2 19B), N % P == 0, H % P == 0, P <= 8. */
+int ltx2_dit_cp_init(LtxDit* dit, int32_t rank, int32_t world, int32_t batch, int32_t n_total, char* handle_out);
+int ltx2_dit_cp_connect(LtxDit* dit, const char* handles);
 
 /* =====================================================================================
  * Video-VAE decoder engine -- replaces LTX_2_MLX/model/video_vae/simple_decoder.py:

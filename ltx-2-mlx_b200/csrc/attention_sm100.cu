@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
                  float scale_log2, float scale, const float* __restrict__ gate_logits, float* __restrict__ lse_out,
-                 long long* __restrict__ trace) {
+                 long long* __restrict__ trace, AttnOutScatter sc) {
   using Cfg = AttnCfg<DH>;
   // optional timeline trace of CTA (0,0): trace[j*8 + k] = clock64 at event k of block j (diagnostics only)
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -316,8 +316,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
         g = 2.0f / (1.0f + __expf(-z));
       }
       const float f = inv_l * g;
-      __nv_bfloat16* o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DH) + h_idx * DH +
-                         half * OC;
+      // context parallel: row `row` of head h belongs to the rank that owns that token; the store goes straight into
+      // that rank's buffer over NVLink (peer pointer), fusing the head->token re-shard into this epilogue
+      __nv_bfloat16* o;
+      if (sc.rows_per_rank > 0) {
+        const int dest = row / sc.rows_per_rank, row_l = row % sc.rows_per_rank;
+        o = sc.peer[row < Tq ? dest : 0] + (static_cast<int64_t>(b_idx) * sc.rows_per_rank + row_l) * sc.pitch +
+            (sc.head0 + h_idx) * DH + half * OC;
+      } else {
+        o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DH) + h_idx * DH + half * OC;
+      }
 #pragma unroll
       for (int c = 0; c < OC; c += 32) {
         uint32_t v[32];
@@ -350,7 +358,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
 
 template <int DH, bool VROWS>
 int launch_attention(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
-                     float scale, const float* gate_logits, float* lse_out, long long* trace, cudaStream_t stream) {
+                     float scale, const float* gate_logits, float* lse_out, long long* trace, const AttnOutScatter& sc,
+                     cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
   static bool configured = false;
   if (!configured) {
@@ -383,7 +392,7 @@ int launch_attention(const void* q, const void* k, const AttnV& v, void* out, in
   const float kLog2e = 1.4426950408889634f;
   attention_kernel<DH, VROWS><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), mk, mv, reinterpret_cast<__nv_bfloat16*>(out), H, Tq, Tk,
-      scale * kLog2e, scale, gate_logits, lse_out, trace);
+      scale * kLog2e, scale, gate_logits, lse_out, trace, sc);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
@@ -392,20 +401,23 @@ int launch_attention(const void* q, const void* k, const AttnV& v, void* out, in
 }  // namespace
 
 int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk, int Dh,
-                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace) {
+                     float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
+                     const AttnOutScatter* scatter) {
+  AttnOutScatter sc;
+  if (scatter) sc = *scatter;
   LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
   LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
   LTX2_REQUIRE(Dh == 64 || Dh == 128, "attention: head_dim %d unsupported (64 or 128)", Dh);
   if (v.rows) {
     LTX2_REQUIRE(v.stride_t % 8 == 0 && v.stride_h % 8 == 0 && v.stride_b % 8 == 0,
                  "attention: V strides must be multiples of 8 elements (16 B)");
-    return Dh == 128 ? launch_attention<128, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream)
-                     : launch_attention<64, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream);
+    return Dh == 128 ? launch_attention<128, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream)
+                     : launch_attention<64, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream);
   }
   LTX2_REQUIRE(v.Tkp >= Tk && v.Tkp % 8 == 0, "attention: V^T pitch %lld must be >= Tk=%d and a multiple of 8",
                (long long)v.Tkp, Tk);
-  return Dh == 128 ? launch_attention<128, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream)
-                   : launch_attention<64, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, stream);
+  return Dh == 128 ? launch_attention<128, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream)
+                   : launch_attention<64, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream);
 }
 
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
@@ -414,7 +426,7 @@ int attention_bf16(const void* q, const void* k, const void* vt, void* out, int 
   v.ptr = vt;
   v.rows = 0;
   v.Tkp = Tkp;
-  return attention_bf16_v(q, k, v, out, B, H, Tq, Tk, Dh, scale, gate_logits, lse_out, stream, trace);
+  return attention_bf16_v(q, k, v, out, B, H, Tq, Tk, Dh, scale, gate_logits, lse_out, stream, trace, nullptr);
 }
 
 }  // namespace ltx2

@@ -173,7 +173,23 @@ struct ProfScope {
 };
 enum { PROF_GEMM = 0, PROF_ATTN = 1 };
 
+// Context-parallel state: a cudaMalloc'ed exchange region with the same layout on every rank, mapped into each
+// process through CUDA IPC, so kernels can store into a peer's buffers over NVLink.
+struct CpState {
+  int rank = 0, world = 1;
+  int B = 0, n_total = 0, n_local = 0, heads_local = 0;
+  char* region = nullptr;
+  size_t region_bytes = 0;
+  char* peer_base[kMaxCpRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool opened[kMaxCpRanks] = {false, false, false, false, false, false, false, false};
+  size_t off_q = 0, off_k = 0, off_v = 0, off_o = 0, off_flags = 0;
+  uint32_t** peer_flags_dev = nullptr;
+  uint32_t epoch = 0;
+  bool connected = false;
+};
+
 struct LtxDit {
+  CpState cp;
   DitProfiler prof;
   LtxDitConfig cfg;
   int D = 0, Da = 0, n_ada = 6;
@@ -535,8 +551,16 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     qp = sb.qkv; kp = sb.kv; vp = sb.kv + inner;
     ldq = inner; ldk = 2 * inner;
   }
-  LTX2_PROPAGATE(headnorm_rope(qp, ldq, w.qnorm, c.qcos, c.qsin, sb.qh, B, c.Tq, H, Dh, eps, st));
-  LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
+  if (w.fused_qkv && c.qcos != nullptr && c.qcos == c.kcos) {
+    // self-attention: q and k share the token row and the RoPE table -> one pass over the QKV row
+    HeadScatter hs = {};
+    hs.q[0] = sb.qh; hs.k[0] = sb.kh; hs.v[0] = nullptr;
+    hs.heads_per_rank = H; hs.n_total = c.Tq; hs.t_offset = 0;
+    LTX2_PROPAGATE(qkv_head_scatter(sb.qkv, 3 * inner, w.qnorm, w.knorm, c.qcos, c.qsin, hs, B, c.Tq, H, Dh, eps, st));
+  } else {
+    LTX2_PROPAGATE(headnorm_rope(qp, ldq, w.qnorm, c.qcos, c.qsin, sb.qh, B, c.Tq, H, Dh, eps, st));
+    LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
+  }
   // V is consumed in place from the projection output (row form, MN-major MMA operand): no transpose pass
   AttnV av;
   av.ptr = vp;
@@ -616,6 +640,12 @@ int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out) {
 void ltx2_dit_destroy(LtxDit* e) {
   if (!e) return;
   for (auto ev : e->prof.events) cudaEventDestroy(ev);
+  if (e->cp.region) {
+    for (int r = 0; r < e->cp.world; ++r)
+      if (e->cp.opened[r]) cudaIpcCloseMemHandle(e->cp.peer_base[r]);
+    cudaFree(e->cp.region);
+    if (e->cp.peer_flags_dev) cudaFree(e->cp.peer_flags_dev);
+  }
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   if (e->fg_video) cudaFree(e->fg_video);
@@ -833,7 +863,41 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
   const bool v2 = c.cross_attention_adaln != 0;
   const float* mod = sb.mod + size_t(layer) * sb.n_cls * n * dim;
   const int64_t ms = int64_t(n) * dim;
-  if (!skip_self) {
+  if (!skip_self && e->cp.world > 1 && &sb == &e->vb) {
+    // ---- context-parallel self-attention: tokens are sharded, heads are re-sharded for the attention ----
+    CpState& cp = e->cp;
+    const AttnW& aw = w.attn1;
+    const int H = aw.heads, Dh = aw.dh, inner = aw.inner, Hl = cp.heads_local, Nt = cp.n_total;
+    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
+    LTX2_PROPAGATE(linear_bf16(sb.xn, dim, aw.q, M, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    HeadScatter hs = {};
+    for (int r = 0; r < cp.world; ++r) {
+      hs.q[r] = reinterpret_cast<bf16*>(cp.peer_base[r] + cp.off_q);
+      hs.k[r] = reinterpret_cast<bf16*>(cp.peer_base[r] + cp.off_k);
+      hs.v[r] = reinterpret_cast<bf16*>(cp.peer_base[r] + cp.off_v);
+    }
+    hs.heads_per_rank = Hl; hs.n_total = Nt; hs.t_offset = cp.rank * cp.n_local;
+    // q/k-norm + RoPE + the token->head all-to-all in one kernel: every head is stored into its owner's buffers
+    LTX2_PROPAGATE(qkv_head_scatter(sb.qkv, 3 * inner, aw.qnorm, aw.knorm, sb.cos, sb.sin, hs, B, N, H, Dh,
+                                    e->cfg.norm_eps, st));
+    uint32_t* my_flags = reinterpret_cast<uint32_t*>(cp.region + cp.off_flags);
+    LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, my_flags, cp.rank, cp.world, ++cp.epoch, st));
+    AttnV av;
+    av.ptr = cp.region + cp.off_v; av.rows = 1;
+    av.stride_t = Dh; av.stride_h = int64_t(Nt) * Dh; av.stride_b = int64_t(Hl) * Nt * Dh;
+    AttnOutScatter sc;
+    for (int r = 0; r < cp.world; ++r) sc.peer[r] = reinterpret_cast<bf16*>(cp.peer_base[r] + cp.off_o);
+    sc.rows_per_rank = cp.n_local; sc.pitch = inner; sc.head0 = cp.rank * Hl;
+    {
+      ProfScope ps(PROF_ATTN, 4.0 * B * Hl * double(Nt) * Nt * Dh, st);
+      // attention over all tokens for my heads; the epilogue stores each row into the token owner's buffer
+      LTX2_PROPAGATE(attention_bf16_v(cp.region + cp.off_q, cp.region + cp.off_k, av, nullptr, B, Hl, Nt, Nt, Dh,
+                                      1.0f / sqrtf((float)Dh), nullptr, nullptr, st, nullptr, &sc));
+    }
+    LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, my_flags, cp.rank, cp.world, ++cp.epoch, st));
+    LTX2_PROPAGATE(linear_residual(reinterpret_cast<const bf16*>(cp.region + cp.off_o), inner, aw.o, M, sb.x, dim,
+                                   mod + 2 * dim, ms, sb.row_cls, 1.0f, st));
+  } else if (!skip_self) {
     LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
     AttnCall a{&w.attn1, sb.xn, dim, M, N, sb.xn, dim, N, sb.cos, sb.sin, sb.cos, sb.sin};
     LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
@@ -914,6 +978,15 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     LTX2_PROPAGATE(check_view(audio, "audio", 1));
     LTX2_REQUIRE(audio->batch == video->batch, "audio/video batch mismatch");
     LTX2_REQUIRE(out_audio != nullptr, "dit_forward: audio modality given but out_audio is null");
+  }
+  if (e->cp.world > 1) {
+    LTX2_REQUIRE(e->cp.connected, "context parallel: ltx2_dit_cp_connect has not been called");
+    LTX2_REQUIRE(!has_audio && !c.apply_gated_attention,
+                 "context parallel supports the video-only, non-gated model in this round");
+    LTX2_REQUIRE(video->tokens == e->cp.n_local && video->batch == e->cp.B,
+                 "context parallel: expected the local slice of %d tokens (batch %d), got %d (batch %d)",
+                 e->cp.n_local, e->cp.B, video->tokens, video->batch);
+    LTX2_REQUIRE(skip == nullptr || skip->video_self_attn == 0, "context parallel: STG self-attention skips unsupported");
   }
   LtxDitSkip sk = {0, 0, 0, 0};
   if (skip) sk = *skip;
@@ -1016,3 +1089,65 @@ extern "C" int ltx2_dit_profile_read(LtxDit* e, double* ms_out, double* flops_ou
 }
 
 extern "C" int64_t ltx2_launch_count(void) { return ltx2::launch_count(); }
+
+// =====================================================================================
+// context parallel: exchange region + CUDA IPC plumbing
+// =====================================================================================
+extern "C" int ltx2_dit_cp_init(LtxDit* e, int32_t rank, int32_t world, int32_t batch, int32_t n_total,
+                                char* handle_out /* 64 bytes */) {
+  LTX2_REQUIRE(e && handle_out, "dit_cp_init: null argument");
+  LTX2_REQUIRE(world >= 1 && world <= kMaxCpRanks && rank >= 0 && rank < world, "dit_cp_init: bad rank %d / world %d",
+               rank, world);
+  const LtxDitConfig& c = e->cfg;
+  LTX2_REQUIRE(c.num_attention_heads % world == 0, "dit_cp_init: %d heads do not split over %d ranks",
+               c.num_attention_heads, world);
+  LTX2_REQUIRE(n_total % world == 0 && batch >= 1, "dit_cp_init: %d tokens do not split over %d ranks", n_total, world);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CpState& cp = e->cp;
+  if (cp.region) {
+    for (int r = 0; r < cp.world; ++r)
+      if (cp.opened[r]) cudaIpcCloseMemHandle(cp.peer_base[r]);
+    cudaFree(cp.region);
+    if (cp.peer_flags_dev) cudaFree(cp.peer_flags_dev);
+    cp = CpState();
+  }
+  cp.rank = rank; cp.world = world; cp.B = batch; cp.n_total = n_total; cp.n_local = n_total / world;
+  cp.heads_local = c.num_attention_heads / world;
+  const size_t Dh = c.attention_head_dim;
+  const size_t qkv_bytes = (size_t(batch) * cp.heads_local * n_total * Dh * 2 + 255) & ~size_t(255);
+  const size_t o_bytes = (size_t(batch) * cp.n_local * e->D * 2 + 255) & ~size_t(255);
+  cp.off_q = 0; cp.off_k = qkv_bytes; cp.off_v = 2 * qkv_bytes; cp.off_o = 3 * qkv_bytes;
+  cp.off_flags = cp.off_o + o_bytes;
+  cp.region_bytes = cp.off_flags + 256;
+  LTX2_CUDA_CHECK(cudaMalloc(&cp.region, cp.region_bytes));
+  LTX2_CUDA_CHECK(cudaMemset(cp.region, 0, cp.region_bytes));
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  LTX2_CUDA_CHECK(cudaIpcGetMemHandle(&h, cp.region));
+  memcpy(handle_out, &h, 64);
+  return LTX2_OK;
+}
+
+extern "C" int ltx2_dit_cp_connect(LtxDit* e, const char* handles /* world x 64 bytes, rank order */) {
+  LTX2_REQUIRE(e && handles && e->cp.region, "dit_cp_connect: call ltx2_dit_cp_init first");
+  CpState& cp = e->cp;
+  std::vector<uint32_t*> flags(cp.world);
+  for (int r = 0; r < cp.world; ++r) {
+    if (r == cp.rank) {
+      cp.peer_base[r] = cp.region;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + size_t(r) * 64, 64);
+      void* p = nullptr;
+      LTX2_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      cp.peer_base[r] = reinterpret_cast<char*>(p);
+      cp.opened[r] = true;
+    }
+    flags[r] = reinterpret_cast<uint32_t*>(cp.peer_base[r] + cp.off_flags);
+  }
+  LTX2_CUDA_CHECK(cudaMalloc(&cp.peer_flags_dev, sizeof(uint32_t*) * kMaxCpRanks));
+  LTX2_CUDA_CHECK(cudaMemcpy(cp.peer_flags_dev, flags.data(), sizeof(uint32_t*) * cp.world, cudaMemcpyHostToDevice));
+  cp.epoch = 0;
+  cp.connected = true;
+  return LTX2_OK;
+}

@@ -48,9 +48,38 @@ struct AttnV {
   int64_t Tkp = 0;
   int64_t stride_t = 0, stride_h = 0, stride_b = 0;
 };
+// Context-parallel output re-shard fused into the attention epilogue: query row t of (local) head h is stored to
+// peer[t / rows_per_rank] at [(b*rows_per_rank + t % rows_per_rank) * pitch + (head0 + h)*Dh] (rows_per_rank = 0: off).
+constexpr int kMaxCpRanks = 8;
+struct AttnOutScatter {
+  __nv_bfloat16* peer[kMaxCpRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rows_per_rank = 0;
+  int pitch = 0;
+  int head0 = 0;
+};
 int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk, int Dh,
                      float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
-                     long long* trace = nullptr);
+                     long long* trace = nullptr, const AttnOutScatter* scatter = nullptr);
+
+// Self-attention head preparation in ONE pass over a token row of the fused QKV projection (pitch ld):
+//   q,k: RMSNorm over the full row (learned weight) + split RoPE;  v: copy (skipped when dst.v[0] == null);
+// each head h is written to dst.{q,k,v}[h / heads_per_rank] at [(b*heads_per_rank + h % heads_per_rank) * n_total +
+// t_offset + t] * Dh.  With one rank this is the plain (B,T,H*D)->(B,H,T,D) split; with context parallelism the
+// destinations are peer pointers, i.e. the token->head re-shard (all-to-all) is fused into this kernel's stores.
+struct HeadScatter {
+  __nv_bfloat16* q[kMaxCpRanks];
+  __nv_bfloat16* k[kMaxCpRanks];
+  __nv_bfloat16* v[kMaxCpRanks];
+  int heads_per_rank;
+  int n_total;
+  int t_offset;
+};
+int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* wk, const float* cos, const float* sin,
+                     const HeadScatter& dst, int B, int T, int H, int Dh, float eps, cudaStream_t stream);
+
+// cross-GPU barrier on flag words in peer memory: signal epoch to every rank's flags[rank], wait for all of mine
+int cp_barrier(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+               cudaStream_t stream);
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
                    int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
                    long long* trace = nullptr);

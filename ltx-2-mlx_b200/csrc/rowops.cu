@@ -198,6 +198,101 @@ headnorm_rope_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld, const flo
 }
 
 // ---------------------------------------------------------------------------------
+// qkv_head_scatter: one CTA per token row of the fused QKV output; q/k norm + RoPE, v copy, per-head destinations
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowThreads)
+qkv_head_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ wq,
+                        const float* __restrict__ wk, const float* __restrict__ cosb, const float* __restrict__ sinb,
+                        HeadScatter dst, int T, int H, int Dh, float eps) {
+  const int row = blockIdx.x;             // b*T + t (local tokens)
+  const int b = row / T, t = row % T;
+  const int inner = H * Dh, half = Dh / 2;
+  const int units = inner / 16;
+  const int upr = half / 8;
+  const __nv_bfloat16* base = qkv + row * ld;
+  float q1[kHeadUnits][8], q2[kHeadUnits][8], k1[kHeadUnits][8], k2[kHeadUnits][8];
+  float sq = 0.f, sk = 0.f;
+#pragma unroll
+  for (int u = 0; u < kHeadUnits; ++u) {
+    const int idx = threadIdx.x + u * kRowThreads;
+    if (idx < units) {
+      const int h = idx / upr, j0 = (idx % upr) * 8;
+      const __nv_bfloat16* p = base + h * Dh + j0;
+      load8_bf16(p, q1[u]);
+      load8_bf16(p + half, q2[u]);
+      load8_bf16(p + inner, k1[u]);
+      load8_bf16(p + inner + half, k2[u]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sq += q1[u][i] * q1[u][i] + q2[u][i] * q2[u][i];
+        sk += k1[u][i] * k1[u][i] + k2[u][i] * k2[u][i];
+      }
+    }
+  }
+  const float2 s = block_sum2<kRowThreads>(sq, sk);
+  const float rq = rsqrtf(s.x / inner + eps), rk = rsqrtf(s.y / inner + eps);
+#pragma unroll
+  for (int u = 0; u < kHeadUnits; ++u) {
+    const int idx = threadIdx.x + u * kRowThreads;
+    if (idx < units) {
+      const int h = idx / upr, j0 = (idx % upr) * 8;
+      float a1[8], a2[8], c[8], sn[8], o1[8], o2[8];
+      const int64_t off = static_cast<int64_t>(row) * (inner / 2) + h * half + j0;
+      load8_f32(cosb + off, c);
+      load8_f32(sinb + off, sn);
+      const int dr = h / dst.heads_per_rank, hl = h % dst.heads_per_rank;
+      const int64_t o = ((static_cast<int64_t>(b) * dst.heads_per_rank + hl) * dst.n_total + dst.t_offset + t) * Dh + j0;
+      load8_f32(wq + h * Dh + j0, a1);
+      load8_f32(wq + h * Dh + half + j0, a2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x1 = q1[u][i] * rq * a1[i], x2 = q2[u][i] * rq * a2[i];
+        o1[i] = x1 * c[i] - x2 * sn[i];
+        o2[i] = x2 * c[i] + x1 * sn[i];
+      }
+      store8_bf16(dst.q[dr] + o, o1);
+      store8_bf16(dst.q[dr] + o + half, o2);
+      load8_f32(wk + h * Dh + j0, a1);
+      load8_f32(wk + h * Dh + half + j0, a2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x1 = k1[u][i] * rk * a1[i], x2 = k2[u][i] * rk * a2[i];
+        o1[i] = x1 * c[i] - x2 * sn[i];
+        o2[i] = x2 * c[i] + x1 * sn[i];
+      }
+      store8_bf16(dst.k[dr] + o, o1);
+      store8_bf16(dst.k[dr] + o + half, o2);
+      if (dst.v[0] != nullptr) {
+        const __nv_bfloat16* pv = base + 2 * inner + h * Dh + j0;
+        *reinterpret_cast<uint4*>(dst.v[dr] + o) = *reinterpret_cast<const uint4*>(pv);
+        *reinterpret_cast<uint4*>(dst.v[dr] + o + half) = *reinterpret_cast<const uint4*>(pv + half);
+      }
+    }
+  }
+}
+
+// signal `epoch` into every rank's flag array (slot = my rank), then wait until all my slots reached it
+__global__ void cp_barrier_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t* my_flags, int rank, int world,
+                                  uint32_t epoch) {
+  const int i = threadIdx.x;
+  if (i < world) {
+    __threadfence_system();
+    volatile uint32_t* f = peer_flags[i] + rank;
+    *f = epoch;
+    volatile uint32_t* m = my_flags + i;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(*m - epoch) < 0) {
+      if (clock64() - t0 > 40000000000LL) {      // ~20 s: a lost peer becomes an error, not a hung GPU
+        printf("ltx2: context-parallel barrier timeout (rank %d waiting for rank %d, epoch %u, have %u)\n", rank, i,
+               epoch, *m);
+        __trap();
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // v_transpose: [B*T, inner] -> [B,H,Dh,Tp], 64x64 tiles through shared memory
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -416,6 +511,29 @@ int headnorm_rope(const void* in, int64_t ld, const float* weight, const float* 
   LTX2_REQUIRE(ld % 8 == 0, "headnorm_rope: pitch must be a multiple of 8");
   headnorm_rope_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, weight, cos,
                                                           sin, reinterpret_cast<__nv_bfloat16*>(out), T, H, Dh, eps);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* wk, const float* cos, const float* sin,
+                     const HeadScatter& dst, int B, int T, int H, int Dh, float eps, cudaStream_t stream) {
+  if (B * T == 0) return LTX2_OK;
+  const int inner = H * Dh;
+  LTX2_REQUIRE(Dh % 16 == 0 && inner <= kRowThreads * 16 * kHeadUnits, "qkv_head_scatter: H=%d Dh=%d unsupported", H, Dh);
+  LTX2_REQUIRE(ld % 8 == 0 && cos != nullptr && sin != nullptr, "qkv_head_scatter: bad pitch or missing RoPE tables");
+  LTX2_REQUIRE(dst.heads_per_rank > 0 && H % dst.heads_per_rank == 0 && H / dst.heads_per_rank <= kMaxCpRanks,
+               "qkv_head_scatter: %d heads cannot be split %d per rank", H, dst.heads_per_rank);
+  qkv_head_scatter_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, wq, wk,
+                                                             cos, sin, dst, T, H, Dh, eps);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int cp_barrier(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int world, uint32_t epoch,
+               cudaStream_t stream) {
+  cp_barrier_kernel<<<1, 32, 0, stream>>>(peer_flags_dev, my_flags, rank, world, epoch);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

@@ -250,6 +250,7 @@ class LTXModel:
         cfg.timestep_scale_multiplier = float(timestep_scale_multiplier)
         cfg.av_ca_timestep_scale_multiplier = float(av_ca_timestep_scale_multiplier)
         self._cfg = cfg
+        self._cp = None                      # (rank, world, group, batch, n_total) once context_parallel.enable() ran
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib().ltx2_dit_create(C.byref(cfg), C.byref(self._h)), "ltx2_dit_create")
@@ -342,6 +343,13 @@ class LTXModel:
             sigma = to_device(m.sigma, dev, torch.float32).reshape(-1)
             if sigma.numel() == 1 and B > 1:
                 sigma = sigma.expand(B).contiguous()
+        if self._cp is not None and n_dims == 3:
+            from .context_parallel import slice_tokens
+            rank, world, _, cp_b, cp_n = self._cp
+            if (B, N) != (cp_b, cp_n):
+                raise ValueError(f"context parallel was enabled for batch {cp_b} x {cp_n} tokens, got {B} x {N}")
+            latent, ts, pos = slice_tokens(latent, ts, pos, rank, world)
+            N = latent.shape[1]
         keep.extend([latent, context, ts, pos, sigma])
         v = LtxModalityView()
         v.latent, v.latent_dtype = latent.data_ptr(), dtype_code(latent)
@@ -373,6 +381,9 @@ class LTXModel:
             check(lib().ltx2_dit_forward(self._h, C.byref(vv), C.byref(av) if av is not None else None,
                                          C.byref(sk) if sk is not None else None, int(x0), ptr(out_v), ptr(out_a),
                                          stream_ptr()), "ltx2_dit_forward")
+        if self._cp is not None:
+            from .context_parallel import gather_tokens
+            out_v = gather_tokens(out_v, self._cp[2])
         if self.model_type == LTXModelType.VideoOnly:
             return out_v
         if out_a is None:
