@@ -266,19 +266,33 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
         need = true;
       }
       const float mb = m_used * scale_log2;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      // p = exp2(s*c - m*c) on pairs with packed fp32 FMA/ADD (FFMA2/FADD2); 3 of every 8 pairs take the polynomial
+      // exp2 on the FMA pipe, the other 5 the MUFU unit, so neither pipe alone bounds the loop
+      const float2 sl2 = make_float2(scale_log2, scale_log2), nmb = make_float2(-mb, -mb);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t pk[HC / 2];
 #pragma unroll
-      for (int i = 0; i < HC; i += 4) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, -mb));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, -mb));
-        const float e2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, -mb));
-        const float e3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, -mb));
-        sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-        pk[i / 2] = pack_bf16x2(e0, e1);
-        pk[i / 2 + 1] = pack_bf16x2(e2, e3);
+      for (int i = 0; i < HC / 2; i += 2) {
+        float2 a = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sl2, nmb);
+        float2 b2 = __ffma2_rn(make_float2(__uint_as_float(s[2 * i + 2]), __uint_as_float(s[2 * i + 3])), sl2, nmb);
+        if ((i & 7) == 2) {
+          a = ex2_poly2(a);
+        } else {
+          a.x = ex2_approx(a.x);
+          a.y = ex2_approx(a.y);
+        }
+        if (((i + 1) & 7) == 5 || ((i + 1) & 7) == 7) {
+          b2 = ex2_poly2(b2);
+        } else {
+          b2.x = ex2_approx(b2.x);
+          b2.y = ex2_approx(b2.y);
+        }
+        acc0 = __fadd2_rn(acc0, a);
+        acc1 = __fadd2_rn(acc1, b2);
+        pk[i] = pack_bf16x2(a.x, a.y);
+        pk[i + 1] = pack_bf16x2(b2.x, b2.y);
       }
-      l = l * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
       if (trs) trace[j * 8 + 5] = clock64();
       if (j > 0) mbar_wait(pv_done, (j - 1) & 1);       // P V_{j-1} retired: P is free, O is complete
       if (trs) trace[j * 8 + 6] = clock64();

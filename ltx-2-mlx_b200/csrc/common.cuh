@@ -97,16 +97,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint elapses),
+// so waiting warps do not burn issue slots of the SM sub-partition they share with compute warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.b32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -114,7 +116,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 22)) {
       printf("ltx2: mbarrier watchdog (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
@@ -262,6 +264,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f
+// (relative error < 8e-5, far below the 4e-3 bf16 rounding of P), exponent inserted with an integer add.
+// Used for a fraction of the softmax exponentials so the 16-per-clock MUFU unit is not the only exp2 engine.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float magic = 12582912.0f;                  // 1.5 * 2^23: the low mantissa bits of (x + magic) hold round(x)
+  const float xr = x + magic;
+  const float f = x - (xr - magic);
+  float p = fmaf(f, 0.05523786f, 0.24261300f);      // minimax cubic for 2^f on [-0.5, 0.5]: max rel. error 7.7e-5
+  p = fmaf(f, p, 0.69324332f);
+  p = fmaf(f, p, 0.99992591f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
+// the same on two values at once with the sm_100 packed-fp32 instructions (FFMA2/FADD2)
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 xr = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(xr, nmagic);
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(f, make_float2(0.05523786f, 0.05523786f), make_float2(0.24261300f, 0.24261300f));
+  p = __ffma2_rn(f, p, make_float2(0.69324332f, 0.69324332f));
+  p = __ffma2_rn(f, p, make_float2(0.99992591f, 0.99992591f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23));
+  return p;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
