@@ -97,6 +97,12 @@ void ltx2_dit_destroy(LtxDit* dit);
  * control of `data` to the caller on `stream`. */
 int ltx2_dit_set_weight(LtxDit* dit, const char* key, const void* data, int32_t dtype, const int64_t* shape,
                         int32_t ndim, void* stream);
+/* Read-back of the flat {reference_key: tensor} view the LoRA fuse/restore code needs (`velocity_model.parameters()`,
+ * scripts/generate.py:1198-1200; pipelines/two_stage.py:180-186): list of keys, shape of one key (returns ndim), and
+ * a copy of its values converted to dst_dtype (matrices are stored as bf16, so that is their precision). */
+int64_t ltx2_dit_weight_keys(LtxDit* dit, char* names_out, int64_t names_cap);
+int ltx2_dit_weight_shape(LtxDit* dit, const char* key, int64_t* shape_out /* [2] */);
+int ltx2_dit_get_weight(LtxDit* dit, const char* key, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 /* number of weight tensors still missing; forward refuses to run until it is 0 */
 int ltx2_dit_missing_weights(LtxDit* dit, char* names_out, int64_t names_cap);
 
@@ -188,6 +194,13 @@ int ltx2_vae_profile_read(LtxVae* vae, double* ms_out, double* flops_out, int64_
 int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, int32_t T_src, int32_t HW, int32_t t0,
                      int32_t overlap, void* stream);
 int ltx2_video_to_uint8(const float* video, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream);
+
+/* decode_tiled's blend (model/video_vae/tiling.py:354-412): out [BC,To,Ho,Wo] += tile[:, :tt, :th, :tw] * mask_t x mask_h x
+ * mask_w placed at (t0,h0,w0) (tile has pitch dt,dh,dw), wsum [To,Ho,Wo] += mask; then out /= max(wsum, 1e-8). */
+int ltx2_tile_accumulate(float* out, float* wsum, const float* tile, int32_t BC, int32_t To, int32_t Ho, int32_t Wo,
+                         int32_t dt, int32_t dh, int32_t dw, int32_t t0, int32_t h0, int32_t w0, int32_t tt, int32_t th,
+                         int32_t tw, const float* mask_t, const float* mask_h, const float* mask_w, void* stream);
+int ltx2_tile_normalize(float* out, const float* wsum, int32_t BC, int64_t plane, void* stream);
 
 /* =====================================================================================
  * Per-op entry points (unit parity against the oracle)

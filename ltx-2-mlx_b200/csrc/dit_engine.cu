@@ -679,6 +679,47 @@ int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dt
   return r;
 }
 
+// read a tensor back (engine storage -> dst_dtype); used by the LoRA fuse/restore flows that read
+// velocity_model.parameters() (scripts/generate.py:1198-1200, pipelines/two_stage.py:180-186)
+int ltx2_dit_get_weight(LtxDit* e, const char* key, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  LTX2_REQUIRE(e && key && dst, "dit_get_weight: null argument");
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) {
+    set_error("dit_get_weight: unknown key '%s'", key);
+    return LTX2_ERR_NOKEY;
+  }
+  const Slot& s = it->second;
+  const int64_t expect = s.rows * (s.cols ? s.cols : 1);
+  LTX2_REQUIRE(n == expect, "dit_get_weight: '%s' has %lld elements, buffer holds %lld", key, (long long)expect, (long long)n);
+  LTX2_REQUIRE(s.loaded, "dit_get_weight: '%s' has not been set", key);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_dtype == LTX2_F32) return cast_to_f32(s.dst, s.storage, reinterpret_cast<float*>(dst), n, st);
+  if (dst_dtype == LTX2_BF16) return cast_to_bf16(s.dst, s.storage, dst, n, st);
+  set_error("dit_get_weight: destination dtype %d unsupported", dst_dtype);
+  return LTX2_ERR_INVALID;
+}
+
+// shape of a weight slot: returns ndim (1 or 2) and fills shape_out[2]; negative status on unknown key
+int ltx2_dit_weight_shape(LtxDit* e, const char* key, int64_t* shape_out) {
+  LTX2_REQUIRE(e && key && shape_out, "dit_weight_shape: null argument");
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) return LTX2_ERR_NOKEY;
+  shape_out[0] = it->second.rows;
+  shape_out[1] = it->second.cols;
+  return it->second.cols ? 2 : 1;
+}
+
+// newline-separated list of every weight key of this configuration
+int64_t ltx2_dit_weight_keys(LtxDit* e, char* names_out, int64_t names_cap) {
+  std::string acc;
+  for (auto& kv : e->slots) acc += kv.first + "\n";
+  if (names_out && names_cap > 0) {
+    strncpy(names_out, acc.c_str(), names_cap - 1);
+    names_out[names_cap - 1] = 0;
+  }
+  return static_cast<int64_t>(acc.size()) + 1;
+}
+
 int ltx2_dit_missing_weights(LtxDit* e, char* names_out, int64_t names_cap) {
   int missing = 0;
   std::string acc;

@@ -192,6 +192,11 @@ int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, in
 //   blend: dst[:, :, t0+i] = dst*(1-r_i) + src[:, :, i]*r_i for i < overlap (r = linspace(0,1,overlap)), then copy tail
 int blend_chunk(float* dst, const float* src, int BC, int T_dst, int T_src, int HW, int t0, int overlap,
                 cudaStream_t stream);
+// decode_tiled (tiling.py:354-412): weighted accumulation of one decoded tile and the final normalisation
+int tile_accumulate(float* out, float* wsum, const float* tile, int BC, int To, int Ho, int Wo, int dt, int dh, int dw,
+                    int t0, int h0, int w0, int tt, int th, int tw, const float* mt, const float* mh, const float* mw,
+                    cudaStream_t stream);
+int tile_normalize(float* out, const float* wsum, int BC, int64_t plane, cudaStream_t stream);
 //   video [1,3,T,H,W] fp32 in [-1,1] -> uint8 [T,H,W,3]
 int video_to_uint8(const float* video, uint8_t* out, int T, int H, int W, cudaStream_t stream);
 

@@ -504,6 +504,17 @@ int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, in
   return blend_chunk(dst, src, BC, T_dst, T_src, HW, t0, overlap, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ltx2_tile_accumulate(float* out, float* wsum, const float* tile, int32_t BC, int32_t To, int32_t Ho, int32_t Wo,
+                         int32_t dt, int32_t dh, int32_t dw, int32_t t0, int32_t h0, int32_t w0, int32_t tt, int32_t th,
+                         int32_t tw, const float* mask_t, const float* mask_h, const float* mask_w, void* stream) {
+  return tile_accumulate(out, wsum, tile, BC, To, Ho, Wo, dt, dh, dw, t0, h0, w0, tt, th, tw, mask_t, mask_h, mask_w,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ltx2_tile_normalize(float* out, const float* wsum, int32_t BC, int64_t plane, void* stream) {
+  return tile_normalize(out, wsum, BC, plane, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ltx2_video_to_uint8(const float* video, uint8_t* out, int32_t T, int32_t H, int32_t W, void* stream) {
   return video_to_uint8(video, out, T, H, W, reinterpret_cast<cudaStream_t>(stream));
 }

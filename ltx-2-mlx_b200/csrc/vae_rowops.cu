@@ -188,6 +188,34 @@ __global__ void blend_chunk_kernel(float* __restrict__ dst, const float* __restr
   }
 }
 
+// decode_tiled accumulation (tiling.py:354-407): out[b,c,t0+t,h0+h,w0+w] += tile[b,c,t,h,w] * mt[t]*mh[h]*mw[w];
+// weights[t0+t,h0+h,w0+w] += mt[t]*mh[h]*mw[w]   (weights has no batch/channel axis, tiling.py:357)
+__global__ void tile_accumulate_kernel(float* __restrict__ out, float* __restrict__ wsum, const float* __restrict__ tile,
+                                       int BC, int To, int Ho, int Wo, int dt, int dh, int dw, int t0, int h0, int w0,
+                                       int tt, int th, int tw, const float* __restrict__ mt, const float* __restrict__ mh,
+                                       const float* __restrict__ mw) {
+  const int64_t n = static_cast<int64_t>(tt) * th * tw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = i % tw;
+    const int h = (i / tw) % th;
+    const int t = i / (static_cast<int64_t>(tw) * th);
+    const float m = mt[t] * mh[h] * mw[w];
+    const int64_t o = (static_cast<int64_t>(t0 + t) * Ho + (h0 + h)) * Wo + (w0 + w);
+    wsum[o] += m;
+    for (int bc = 0; bc < BC; ++bc)
+      out[static_cast<int64_t>(bc) * To * Ho * Wo + o] += tile[((static_cast<int64_t>(bc) * dt + t) * dh + h) * dw + w] * m;
+  }
+}
+
+__global__ void tile_normalize_kernel(float* __restrict__ out, const float* __restrict__ wsum, int BC, int64_t plane) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float inv = 1.0f / fmaxf(wsum[i], 1e-8f);
+    for (int bc = 0; bc < BC; ++bc) out[static_cast<int64_t>(bc) * plane + i] *= inv;
+  }
+}
+
 __global__ void video_to_uint8_kernel(const float* __restrict__ v, uint8_t* __restrict__ out, int T, int H, int W) {
   const int64_t total = static_cast<int64_t>(T) * H * W;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -295,6 +323,30 @@ int blend_chunk(float* dst, const float* src, int BC, int T_dst, int T_src, int 
   const int64_t total = static_cast<int64_t>(BC) * T_src * HW;
   if (total == 0) return LTX2_OK;
   blend_chunk_kernel<<<grid_for(total, 256), 256, 0, stream>>>(dst, src, T_dst, T_src, HW, t0, overlap, total);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int tile_accumulate(float* out, float* wsum, const float* tile, int BC, int To, int Ho, int Wo, int dt, int dh, int dw,
+                    int t0, int h0, int w0, int tt, int th, int tw, const float* mt, const float* mh, const float* mw,
+                    cudaStream_t stream) {
+  LTX2_REQUIRE(t0 >= 0 && h0 >= 0 && w0 >= 0 && t0 + tt <= To && h0 + th <= Ho && w0 + tw <= Wo && tt <= dt &&
+                   th <= dh && tw <= dw,
+               "tile_accumulate: tile [%d,%d,%d]+[%d,%d,%d] does not fit output [%d,%d,%d]", t0, h0, w0, tt, th, tw, To,
+               Ho, Wo);
+  const int64_t n = static_cast<int64_t>(tt) * th * tw;
+  if (n == 0) return LTX2_OK;
+  tile_accumulate_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, wsum, tile, BC, To, Ho, Wo, dt, dh, dw, t0, h0, w0,
+                                                                tt, th, tw, mt, mh, mw);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int tile_normalize(float* out, const float* wsum, int BC, int64_t plane, cudaStream_t stream) {
+  if (plane == 0) return LTX2_OK;
+  tile_normalize_kernel<<<grid_for(plane, 256), 256, 0, stream>>>(out, wsum, BC, plane);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

@@ -302,6 +302,48 @@ class LTXModel:
         self.load_weights(flat)
         return self
 
+    def weight_keys(self) -> List[str]:
+        n = lib().ltx2_dit_weight_keys(self._h, None, C.c_int64(0))
+        buf = C.create_string_buffer(int(n) + 16)
+        lib().ltx2_dit_weight_keys(self._h, buf, C.c_int64(len(buf)))
+        return sorted(k for k in buf.value.decode().split("\n") if k)
+
+    def get_weight(self, key: str, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """One tensor of the flat {reference_key: array} view (engine storage converted to `dtype`)."""
+        shape = (C.c_int64 * 2)()
+        nd = lib().ltx2_dit_weight_shape(self._h, key.encode(), shape)
+        if nd < 0:
+            raise KeyError(key)
+        dims = tuple(shape[:nd])
+        out = torch.empty(dims, device=self.device, dtype=dtype)
+        with torch.cuda.device(self.device):
+            check(lib().ltx2_dit_get_weight(self._h, key.encode(), ptr(out), dtype_code(out), C.c_int64(out.numel()),
+                                            stream_ptr()), f"get_weight({key})")
+        return out
+
+    def parameters(self) -> Dict[str, torch.Tensor]:
+        """Flat {reference_key: tensor} view, materialised lazily per key (the reference returns a nested dict that
+        callers immediately flatten with mlx.utils.tree_flatten)."""
+        model = self
+
+        class _Lazy(dict):
+            def __missing__(self, key):
+                return model.get_weight(key)
+
+            def keys(self):
+                return model.weight_keys()
+
+            def __iter__(self):
+                return iter(model.weight_keys())
+
+            def __len__(self):
+                return len(model.weight_keys())
+
+            def items(self):
+                return ((k, model.get_weight(k)) for k in model.weight_keys())
+
+        return _Lazy()
+
     def missing_weights(self) -> List[str]:
         buf = C.create_string_buffer(8192)
         n = lib().ltx2_dit_missing_weights(self._h, buf, C.c_int64(len(buf)))

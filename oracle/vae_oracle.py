@@ -241,3 +241,48 @@ def trapezoid_mask_1d(length: int, ramp_left: int, ramp_right: int, left_starts_
     if ramp_right > 0:
         m = torch.cat([m[:-ramp_right], torch.linspace(1.0, 0.0, ramp_right + 2)[1:-1]])
     return m.clamp(0, 1)
+
+
+def tiles_1d(length: int, tile: int, overlap: int):
+    """gen_tiles_1d of generate_tile_specs (tiling.py:203-226)."""
+    if length <= tile:
+        return [(0, length, 0, 0)]
+    out, pos, stride = [], 0, tile - overlap
+    while pos < length:
+        end = min(pos + tile, length)
+        start = max(0, end - tile)
+        out.append((start, end, overlap if start > 0 else 0, overlap if end < length else 0))
+        if end >= length:
+            break
+        pos += stride
+    return out
+
+
+def decode_tiled(decode_fn, latent: torch.Tensor, *, tile_px: Optional[int], overlap_px: int = 0,
+                 tile_frames: Optional[int] = None, overlap_frames: int = 0) -> torch.Tensor:
+    """decode_tiled (tiling.py:252-412): trapezoid-weighted blend of independently decoded tiles.
+    decode_fn(latent_tile) -> (B,3,T',H',W')."""
+    b, _, t, h, w = latent.shape
+    th, oh = (tile_px // 32, overlap_px // 32) if tile_px else (max(h, w), 0)
+    tt, ot = (tile_frames // 8, overlap_frames // 8) if tile_frames else (t, 0)
+    To, Ho, Wo = (t - 1) * 8 + 1, h * 32, w * 32
+    out = torch.zeros(b, 3, To, Ho, Wo)
+    ws = torch.zeros(1, 1, To, Ho, Wo)
+    h_tiles = tiles_1d(h, th, oh) if tile_px else [(0, h, 0, 0)]
+    w_tiles = tiles_1d(w, th, oh) if tile_px else [(0, w, 0, 0)]
+    for (t0, t1, rtl, rtr) in tiles_1d(t, tt, ot):
+        for (h0, h1, rhl, rhr) in h_tiles:
+            for (w0, w1, rwl, rwr) in w_tiles:
+                tile = decode_fn(latent[:, :, t0:t1, h0:h1, w0:w1])
+                ot0 = t0 * 8 if t0 > 0 else 0
+                ot1 = (t1 - 1) * 8 + 1 if t1 > 1 else 1
+                nt = min(tile.shape[2], ot1 - ot0)
+                nh = min(tile.shape[3], (h1 - h0) * 32)
+                nw = min(tile.shape[4], (w1 - w0) * 32)
+                mt = trapezoid_mask_1d(nt, min(rtl * 8, nt), min(rtr * 8, nt), left_starts_from_0=(ot0 == 0))
+                mh = trapezoid_mask_1d(nh, min(rhl * 32, nh), min(rhr * 32, nh))
+                mw = trapezoid_mask_1d(nw, min(rwl * 32, nw), min(rwr * 32, nw))
+                m = mt[None, None, :, None, None] * mh[None, None, None, :, None] * mw[None, None, None, None, :]
+                out[:, :, ot0:ot0 + nt, h0 * 32:h0 * 32 + nh, w0 * 32:w0 * 32 + nw] += tile[:, :, :nt, :nh, :nw] * m
+                ws[:, :, ot0:ot0 + nt, h0 * 32:h0 * 32 + nh, w0 * 32:w0 * 32 + nw] += m
+    return out / torch.clamp(ws, min=1e-8)

@@ -234,6 +234,21 @@ def golden_vae():
                         weight_checksum=cs, decoder_blocks=repr(blocks))
     print("vae_v20", out.shape, frames.shape, frames3.shape)
 
+    # decode_tiled (tiling.py:252-412) over the small V2.0 decoder above: 3x3 spatial tiles of 64 px / 32 px overlap
+    lat_t = rnd((1, 128, 2, 4, 4), 44)
+    cfg_t = ref_tiling.TilingConfig(spatial_config=ref_tiling.SpatialTilingConfig(64, 32), temporal_config=None)
+    tiled = A(next(ref_tiling.decode_tiled(mx.array(lat_t), lambda x, timestep=None: dec(x, timestep=timestep,
+                                           show_progress=False), cfg_t, timestep=0.05, show_progress=False)))
+    # temporal tiling needs >= 16-frame tiles: 5 latent frames, tiles of 2 latent frames (16 px frames), overlap 1
+    lat_tt = rnd((1, 128, 5, 2, 2), 45)
+    cfg_tt = ref_tiling.TilingConfig(spatial_config=None,
+                                     temporal_config=ref_tiling.TemporalTilingConfig(16, 8))
+    tiled_t = A(next(ref_tiling.decode_tiled(mx.array(lat_tt), lambda x, timestep=None: dec(x, timestep=timestep,
+                                             show_progress=False), cfg_tt, timestep=0.05, show_progress=False)))
+    np.savez_compressed(os.path.join(HERE, "vae_tiled.npz"), latent_spatial=lat_t, video_spatial=tiled,
+                        latent_temporal=lat_tt, video_temporal=tiled_t, weight_checksum=cs,
+                        decoder_blocks=repr(blocks))
+    print("vae_tiled", tiled.shape, tiled_t.shape)
     # a V2.3-style stack: separate temporal / spatial upsamplers, no timestep conditioning
     blocks23 = [["res_x", {"num_layers": 1}], ["compress_space", {"multiplier": 2, "residual": True}],
                 ["res_x", {"num_layers": 1}], ["compress_time", {"multiplier": 2, "residual": False}],

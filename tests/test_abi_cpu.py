@@ -115,3 +115,28 @@ def test_chunk_schedule_and_positions_match_oracle():
     # causal_fix: first frame spans [0,1), later frames [8f-7, 8f+1) (patchifiers.py:228-238)
     assert pos[0, 0, 0].tolist() == [0.0, 1.0] and pos[0, 0, 4].tolist() == [1.0, 9.0] and pos[0, 0, 8].tolist() == [9.0, 17.0]
     assert pos[0, 1, 2].tolist() == [32.0, 64.0] and pos[0, 2, 1].tolist() == [32.0, 64.0]
+
+
+def test_tile_specs_and_masks_match_reference_semantics():
+    # tiling.py:154-249: default config on a 16x24x31 latent (768x512x241) and the error messages of :55-103
+    from ltx2_b200.tiling import (SpatialTilingConfig, TemporalTilingConfig, TilingConfig, compute_trapezoidal_mask_1d,
+                                  generate_tile_specs)
+    from oracle import vae_oracle as V
+    specs = generate_tile_specs((1, 128, 31, 16, 24), TilingConfig.default())
+    t_tiles = sorted({(s.in_t_start, s.in_t_end) for s in specs})
+    w_tiles = sorted({(s.in_w_start, s.in_w_end) for s in specs})
+    assert t_tiles == [(a, b) for a, b, _, _ in V.tiles_1d(31, 8, 3)] and t_tiles[-1] == (23, 31)
+    assert w_tiles == [(a, b) for a, b, _, _ in V.tiles_1d(24, 16, 2)] and sorted({(s.in_h_start, s.in_h_end) for s in specs}) == [(0, 16)]
+    first, last = specs[0], specs[-1]
+    assert (first.out_t_start, first.out_t_end) == (0, 57) and first.ramp_t_left == 0 and first.ramp_t_right == 24
+    assert last.out_t_end == 241 and last.ramp_w_left == 64 and last.ramp_w_right == 0
+    for (l, a, b, z) in [(16, 4, 4, False), (16, 4, 0, True), (8, 0, 3, False), (5, 8, 8, False)]:
+        assert torch.allclose(compute_trapezoidal_mask_1d(l, a, b, z), V.trapezoid_mask_1d(l, a, b, z))
+    with pytest.raises(ValueError, match="at least 64"):
+        SpatialTilingConfig(32)
+    with pytest.raises(ValueError, match="divisible by 8"):
+        TemporalTilingConfig(20)
+    with pytest.raises(ValueError, match="Overlap must be less"):
+        SpatialTilingConfig(64, 64)
+    with pytest.raises(ValueError, match="positive"):
+        compute_trapezoidal_mask_1d(0, 0, 0)

@@ -148,3 +148,29 @@ def test_dit_v2_audio_video_and_stg_match_oracle():
     half = BatchedPerturbationConfig([pc, PerturbationConfig.empty()])
     hv, _ = m(vm, am, perturbations=half)
     assert torch.equal(hv, ov)
+
+
+def test_weight_readback_and_lora_style_update():
+    """parameters()/load_weights round trip used by the LoRA fuse/restore flows (generate.py:1198-1200)."""
+    from ltx2_b200 import synthetic
+    from ltx2_b200.transformer import Modality
+    cfg = synthetic.DitConfig(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32,
+                              num_layers=1, cross_attention_dim=128, caption_channels=64)
+    m, w = build(cfg, seed=14)
+    params = m.parameters()
+    keys = list(params.keys())
+    assert "transformer_blocks.0.attn1.to_out.weight" in keys and len(keys) == len(w)
+    k = "transformer_blocks.0.ff.project_in.proj.weight"
+    base = params[k]
+    assert base.shape == (512, 128) and torch.equal(base.cpu(), w[k].to(torch.bfloat16).float())
+    assert torch.equal(params["transformer_blocks.0.scale_shift_table"].cpu(), w["transformer_blocks.0.scale_shift_table"])
+    lat, ctx, pos = video_inputs(cfg, 1, 2, 3, 4, 24, 140, 64)
+    mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.5]), positions=pos)
+    before = m(mod)
+    delta = torch.randn_like(base) * 0.05
+    m.load_weights([(k, base + delta)])                      # fuse
+    assert not torch.allclose(m(mod), before)
+    m.load_weights([(k, base)])                              # restore
+    assert torch.equal(m(mod), before)
+    with pytest.raises(KeyError):
+        m.get_weight("no.such.key")

@@ -149,3 +149,16 @@ def test_metal_kernel_formulas():
     y = D.interleaved_rope(a, cos, sin)
     z = torch.view_as_real(torch.view_as_complex(a.reshape(3, 5, 4, 2).contiguous()) * torch.polar(torch.ones_like(th), th))
     close(y, z.reshape(3, 5, 8), 1e-5, 1e-6)
+
+
+def test_vae_decode_tiled_spatial_and_temporal():
+    g = load("vae_tiled.npz")
+    blocks = ast.literal_eval(str(g["decoder_blocks"]))
+    cfg = synthetic.VaeConfig(decoder_blocks=blocks, base_channels=8)
+    w = synthetic.vae_weights(cfg, seed=3)
+    assert abs(checksum(w) - float(g["weight_checksum"])) < 1e-6 * float(g["weight_checksum"])
+    dec = lambda x: V.vae_decode(w, x, decoder_blocks=blocks, base_channels=8, timestep=0.05)  # noqa: E731
+    out = V.decode_tiled(dec, T(g["latent_spatial"]), tile_px=64, overlap_px=32)
+    close(out, g["video_spatial"], 2e-3, 2e-4)
+    out_t = V.decode_tiled(dec, T(g["latent_temporal"]), tile_px=None, tile_frames=16, overlap_frames=8)
+    close(out_t, g["video_temporal"], 2e-3, 2e-4)
