@@ -58,6 +58,23 @@ def peaks():
         return dict(tf=1400.0, tf_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def profiled_traffic(rep_suffix, kernel_substr, skip=0):
+    """Mean DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed
+    `ncu --set full` summary (profiles/r1b_kernels.json, produced by tools/summarize_profiles.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1b_kernels.json")) as f:
+            caps = json.load(f)
+        rows = [k for name, ks in caps.items() if rep_suffix in name for k in ks if kernel_substr in k["kernel"]][skip:]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in rows:
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(k[m]) * mult.get(k[m + " [unit]"], 1.0)
+        return tot / len(rows) if rows else None
+    except Exception:
+        return None
+
+
 def flops_per_step(c, B=1):
     """F_blk = 28 N D^2 + 4 S D^2 + 4 N^2 D + 4 N S D; + patchify, caption projection."""
     D = c["heads"] * c["head_dim"]
@@ -272,7 +289,10 @@ def bench_vae(args, dev, rank):
         "e2e": {"value": frames * 1000.0 / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(lat_h.numel() * 4),
                 "d2h_bytes_per_step": int(out_h.numel())},
         "roofline": {"bound": "tensor", "kernel": "conv3d_kernel (tcgen05 implicit GEMM, all convs of one 7-frame chunk)",
-                     "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"], "traffic": None,
+                     "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
+                     "traffic": profiled_traffic("prof_conv", "conv3d_kernel<128>"),
+                     "traffic_note": "DRAM bytes of one last-stage conv launch (128->128 ch, 49x128x192) from "
+                                     "profiles/r1b_kernels.json; algorithmic bytes 330 MB in + 308 MB out + 0.9 MB weights",
                      "launches": int(pl.value), "ms_in_decode": pm.value, "flops_in_decode": pf.value,
                      "decode": {"algorithmic_flops": alg, "achieved": alg / (ms * 1e-3) / 1e12,
                                 "frac": alg / (ms * 1e-3) / 1e12 / pk["tf"]}},
@@ -424,7 +444,10 @@ def run_ours(args, c):
                 "d2h_bytes_per_step": int(d2h)},
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all DiT linears of one step)",
                      "achieved": gemm_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"],
-                     "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "traffic": profiled_traffic("prof_gemm", "gemm_bf16_kernel", skip=3),
+                     "traffic_note": "mean DRAM bytes per launch over the 5 per-block GEMMs of one block (QKV, attn out, "
+                                     "text q, text kv, text out) from profiles/r1b_kernels.json; algorithmic bytes of "
+                                     "those launches average 128 MB", "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches": int(pl[0]), "ms_in_step": pm[0], "flops_in_step": pf[0],
                      "attention": {"achieved": attn_tf, "frac": attn_tf / pk["tf"], "launches": int(pl[1]),
                                    "ms_in_step": pm[1], "flops_in_step": pf[1]},
