@@ -160,9 +160,12 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CU
     };
     mbar_wait(q_ready, 0);
     tc_fence_after();
+    // Q*K^T runs TWO blocks ahead of the softmax: S_{j+2} is issued as soon as the softmax has pulled S_j out of the
+    // shared TMEM buffer (early in its iteration), so it executes during softmax_j instead of queueing behind P_j*V_j
     issue_s(0);
+    if (nkv > 1) issue_s(1);
     for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) issue_s(j + 1);
+      if (j + 2 < nkv) issue_s(j + 2);
       mbar_wait(p_full, j & 1);
       if (tr && leader) trace[j * 8 + 1] = clock64();
       mbar_wait(&v_full[vs_st], vs_ph);
