@@ -331,7 +331,7 @@ def run_ours(args, c):
     if cp:
         # ONE sample sharded over the ranks (context parallel): same inputs on every rank
         from ltx2_b200 import context_parallel
-        context_parallel.enable(model, batch=1, n_total=N)
+        context_parallel.enable(model, batch=1, n_total=N, context_tokens=S)
     lat0 = synthetic.latents((1, N, 128), seed=42 + (0 if cp else rank))
     ctx0 = (synthetic.latents((1, S, c["caption"]), seed=7, std=0.1)).to(torch.bfloat16)
     pos0 = synthetic.video_positions(1, c["F"], c["H"], c["W"], fps=24.0)
@@ -452,7 +452,8 @@ def run_ours(args, c):
                      "attention": {"achieved": attn_tf, "frac": attn_tf / pk["tf"], "launches": int(pl[1]),
                                    "ms_in_step": pm[1], "flops_in_step": pf[1]},
                      "step": {"algorithmic_flops": fl, "achieved": fl / (ms_step * 1e-3) / 1e12,
-                              "frac": fl / (ms_step * 1e-3) / 1e12 / pk["tf"]}},
+                              "frac": fl / (ms_step * 1e-3) / 1e12 / (pk["tf"] * world),
+                              "note": "whole-step FLOPs over all ranks / step time, against world x the per-GPU peak"}},
     }
     if vae is not None:
         out["vae"] = vae

@@ -138,8 +138,11 @@ int64_t ltx2_launch_count(void);
  *   2. the host layer all-gathers the handles (any transport) and calls ltx2_dit_cp_connect on every rank,
  *      followed by a host barrier;
  *   3. ltx2_dit_forward is then called with the LOCAL token slice (tokens = N/P) on every rank, collectively.
+ * When context_tokens (S) is given and S % P == 0, the text-context K/V projection of every block is also sharded:
+ * each rank projects S/P context rows and its GEMM epilogue stores them into all ranks' buffers.
  * Round-1 limits: video-only, non-gated model (LTX-2 19B), N % P == 0, H % P == 0, P <= 8. */
-int ltx2_dit_cp_init(LtxDit* dit, int32_t rank, int32_t world, int32_t batch, int32_t n_total, char* handle_out);
+int ltx2_dit_cp_init(LtxDit* dit, int32_t rank, int32_t world, int32_t batch, int32_t n_total, int32_t context_tokens,
+                     char* handle_out);
 int ltx2_dit_cp_connect(LtxDit* dit, const char* handles);
 
 /* =====================================================================================
@@ -212,6 +215,12 @@ int ltx2_tile_normalize(float* out, const float* wsum, int32_t BC, int64_t plane
 int ltx2_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
                    int32_t mode, const float* bias, void* out, int64_t ldo, const float* gate, int64_t gate_stride,
                    const int32_t* row_cls, float alpha, void* stream);
+
+/* Mode 3 with split-K allowed (up to max_splits K slices accumulate into `out` with vector reductions).  Used by the
+ * context-parallel ranks, whose M = N/P rows do not fill the SMs otherwise; accumulation order is not deterministic. */
+int ltx2_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                          const float* bias, float* out, int64_t ldo, const float* gate, int64_t gate_stride,
+                          const int32_t* row_cls, float alpha, int32_t max_splits, void* stream);
 
 /* mx.fast.scaled_dot_product_attention + head merge + V2 gate (attention.py:12-34, 243-250).
  * q [B,H,Tq,Dh], k [B,H,Tk,Dh], vt [B,H,Dh,Tkp] (V transposed), out [B,Tq,H*Dh]; all bf16. */

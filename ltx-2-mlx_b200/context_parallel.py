@@ -54,7 +54,7 @@ def exchange_handles(handle: bytes, group=None) -> bytes:
     return b"".join(out)
 
 
-def enable(model, batch: int, n_total: int, group=None) -> None:
+def enable(model, batch: int, n_total: int, context_tokens: int = 0, group=None) -> None:
     """Turn on context parallelism for an ltx2_b200 LTXModel across `group` (default: the world)."""
     from ._lib import check, lib
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -62,7 +62,7 @@ def enable(model, batch: int, n_total: int, group=None) -> None:
         return
     buf = C.create_string_buffer(64)
     with torch.cuda.device(model.device):
-        check(lib().ltx2_dit_cp_init(model._h, rank, world, batch, n_total, buf), "ltx2_dit_cp_init")
+        check(lib().ltx2_dit_cp_init(model._h, rank, world, batch, n_total, context_tokens, buf), "ltx2_dit_cp_init")
         handles = exchange_handles(buf.raw, group)
         check(lib().ltx2_dit_cp_connect(model._h, handles), "ltx2_dit_cp_connect")
         torch.cuda.synchronize()

@@ -35,6 +35,22 @@ int ltx2_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32
   return gemm_bf16(A, lda, W, ldw, M, N, K, ep, S(stream));
 }
 
+int ltx2_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                          const float* bias, float* out, int64_t ldo, const float* gate, int64_t gate_stride,
+                          const int32_t* row_cls, float alpha, int32_t max_splits, void* stream) {
+  GemmEpilogue ep;
+  ep.mode = GEMM_EPI_F32_RESIDUAL;
+  ep.bias = bias;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.gate = gate;
+  ep.gate_stride = gate_stride;
+  ep.row_cls = row_cls;
+  ep.alpha = alpha;
+  ep.max_splits = max_splits;
+  return gemm_bf16(A, lda, W, ldw, M, N, K, ep, S(stream));
+}
+
 int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
                    int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
                    void* stream) {

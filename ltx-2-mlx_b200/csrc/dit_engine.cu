@@ -21,7 +21,9 @@
 #include "../../include/ltx2_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 #include <map>
 #include <string>
@@ -160,6 +162,7 @@ struct DitProfiler {
   void end(size_t e0, cudaStream_t st) { cudaEventRecord(events[e0 + 1], st); }
 };
 static thread_local DitProfiler* g_prof = nullptr;
+static thread_local int g_split_k = 1;
 struct ProfScope {
   size_t e0 = 0;
   cudaStream_t st;
@@ -183,6 +186,9 @@ struct CpState {
   char* peer_base[kMaxCpRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool opened[kMaxCpRanks] = {false, false, false, false, false, false, false, false};
   size_t off_q = 0, off_k = 0, off_v = 0, off_o = 0, off_flags = 0;
+  size_t off_ckv[2] = {0, 0};      // text-context K/V of the current / next block, [B*S, 2*D] bf16 each
+  int split_k = 8;                  // split-K cap of the residual GEMMs on sharded ranks (LTX2_CP_SPLIT_K, 1 = off)
+  int ctx_tokens = 0;               // > 0: every rank projects S/P context rows and broadcasts them to all peers
   uint32_t** peer_flags_dev = nullptr;
   uint32_t epoch = 0;
   bool connected = false;
@@ -495,6 +501,7 @@ inline int linear_residual(const bf16* A, int64_t lda, const LinearW& L, int M, 
   ep.gate_stride = gate_stride;
   ep.row_cls = row_cls;
   ep.alpha = alpha;
+  ep.max_splits = g_split_k;        // > 1 only for context-parallel ranks (small M): see gemm_sm100.cu
   ProfScope ps(PROF_GEMM, 2.0 * M * double(L.out) * L.in, st);
   return gemm_bf16(A, lda, L.w, L.in, M, L.out, L.in, ep, st);
 }
@@ -532,6 +539,7 @@ struct AttnCall {
   const bf16* xq; int64_t ldq; int Mq; int Tq;          // query-side input [B*Tq, query_dim]
   const bf16* xkv; int64_t ldkv; int Tk;               // key/value-side input [B*Tk, ctx_dim] (== xq for self)
   const float *qcos, *qsin, *kcos, *ksin;              // rope tables or null
+  const bf16* kv_pre = nullptr;                        // K|V projection already available ([B*Tk, 2*inner]): skip that GEMM
 };
 
 // Attention.__call__ up to (not including) to_out: writes sb.attn [B*Tq, inner]
@@ -547,8 +555,12 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     ldq = ldk = 3 * inner;
   } else {
     LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, inner, false, st));
-    LTX2_PROPAGATE(linear_bf16(c.xkv, c.ldkv, w.kv, B * c.Tk, sb.kv, 2 * inner, false, st));
-    qp = sb.qkv; kp = sb.kv; vp = sb.kv + inner;
+    const bf16* kvp = c.kv_pre;
+    if (kvp == nullptr) {
+      LTX2_PROPAGATE(linear_bf16(c.xkv, c.ldkv, w.kv, B * c.Tk, sb.kv, 2 * inner, false, st));
+      kvp = sb.kv;
+    }
+    qp = sb.qkv; kp = kvp; vp = kvp + inner;
     ldq = inner; ldk = 2 * inner;
   }
   if (w.fused_qkv && c.qcos != nullptr && c.qcos == c.kcos) {
@@ -921,6 +933,23 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     // q/k-norm + RoPE + the token->head all-to-all in one kernel: every head is stored into its owner's buffers
     LTX2_PROPAGATE(qkv_head_scatter(sb.qkv, 3 * inner, aw.qnorm, aw.knorm, sb.cos, sb.sin, hs, B, N, H, Dh,
                                     e->cfg.norm_eps, st));
+    if (cp.ctx_tokens == S && !v2) {
+      // text-context K/V for this block: each rank projects S/P context rows and stores the result into EVERY rank's
+      // buffer (GEMM epilogue with peer destinations) instead of all ranks repeating the full projection
+      const int Sl = S / cp.world;
+      const AttnW& cw = w.attn2;
+      for (int b = 0; b < B; ++b) {
+        const size_t row0 = size_t(b) * S + size_t(cp.rank) * Sl;
+        const size_t byte0 = cp.off_ckv[layer & 1] + row0 * 2 * cw.inner * sizeof(bf16);
+        bf16* mine = reinterpret_cast<bf16*>(cp.region + byte0);
+        LTX2_PROPAGATE(linear_bf16(sb.ctx + row0 * dim, dim, cw.kv, Sl, mine, 2 * cw.inner, false, st));
+        void* peers[kMaxCpRanks];
+        int np = 0;
+        for (int r = 0; r < cp.world; ++r)
+          if (r != cp.rank) peers[np++] = cp.peer_base[r] + byte0;
+        LTX2_PROPAGATE(peer_broadcast(mine, peers, np, int64_t(Sl) * 2 * cw.inner * sizeof(bf16), st));
+      }
+    }
     uint32_t* my_flags = reinterpret_cast<uint32_t*>(cp.region + cp.off_flags);
     LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, my_flags, cp.rank, cp.world, ++cp.epoch, st));
     AttnV av;
@@ -956,6 +985,8 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, nullptr, 0, 0, 0, nullptr, st));
   }
   AttnCall a{&w.attn2, sb.xn, dim, M, N, ctx, dim, S, nullptr, nullptr, nullptr, nullptr};
+  if (e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !v2 && !skip_self)
+    a.kv_pre = reinterpret_cast<const bf16*>(e->cp.region + e->cp.off_ckv[layer & 1]);
   LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
   return linear_residual(sb.attn, w.attn2.inner, w.attn2.o, M, sb.x, dim, v2 ? mod + 8 * dim : nullptr, ms,
                          sb.row_cls, ca_scale, st);
@@ -1032,6 +1063,7 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   LtxDitSkip sk = {0, 0, 0, 0};
   if (skip) sk = *skip;
   g_prof = &e->prof;
+  g_split_k = e->cp.world > 1 ? e->cp.split_k : 1;
   e->prof.used = 0;
   e->prof.recs.clear();
 
@@ -1135,7 +1167,7 @@ extern "C" int64_t ltx2_launch_count(void) { return ltx2::launch_count(); }
 // context parallel: exchange region + CUDA IPC plumbing
 // =====================================================================================
 extern "C" int ltx2_dit_cp_init(LtxDit* e, int32_t rank, int32_t world, int32_t batch, int32_t n_total,
-                                char* handle_out /* 64 bytes */) {
+                                int32_t context_tokens, char* handle_out /* 64 bytes */) {
   LTX2_REQUIRE(e && handle_out, "dit_cp_init: null argument");
   LTX2_REQUIRE(world >= 1 && world <= kMaxCpRanks && rank >= 0 && rank < world, "dit_cp_init: bad rank %d / world %d",
                rank, world);
@@ -1154,11 +1186,20 @@ extern "C" int ltx2_dit_cp_init(LtxDit* e, int32_t rank, int32_t world, int32_t 
   }
   cp.rank = rank; cp.world = world; cp.B = batch; cp.n_total = n_total; cp.n_local = n_total / world;
   cp.heads_local = c.num_attention_heads / world;
+  if (const char* sk = getenv("LTX2_CP_SPLIT_K")) cp.split_k = std::min(16, std::max(1, atoi(sk)));
   const size_t Dh = c.attention_head_dim;
   const size_t qkv_bytes = (size_t(batch) * cp.heads_local * n_total * Dh * 2 + 255) & ~size_t(255);
   const size_t o_bytes = (size_t(batch) * cp.n_local * e->D * 2 + 255) & ~size_t(255);
   cp.off_q = 0; cp.off_k = qkv_bytes; cp.off_v = 2 * qkv_bytes; cp.off_o = 3 * qkv_bytes;
-  cp.off_flags = cp.off_o + o_bytes;
+  size_t end = cp.off_o + o_bytes;
+  if (context_tokens > 0 && context_tokens % world == 0 && (context_tokens / world) % 8 == 0) {
+    cp.ctx_tokens = context_tokens;
+    const size_t ckv_bytes = (size_t(batch) * context_tokens * 2 * e->D * 2 + 255) & ~size_t(255);
+    cp.off_ckv[0] = end;
+    cp.off_ckv[1] = end + ckv_bytes;
+    end += 2 * ckv_bytes;
+  }
+  cp.off_flags = end;
   cp.region_bytes = cp.off_flags + 256;
   LTX2_CUDA_CHECK(cudaMalloc(&cp.region, cp.region_bytes));
   LTX2_CUDA_CHECK(cudaMemset(cp.region, 0, cp.region_bytes));

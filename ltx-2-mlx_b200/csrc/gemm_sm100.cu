@@ -34,7 +34,7 @@ struct GemmCfg {
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 int M, int N, int K, GemmEpilogue ep) {
+                 int M, int N, int K, int splits, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -53,8 +53,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  // split-K (residual-accumulate epilogue only): work item = (m tile, n tile, K slice); slices add into the fp32
+  // output with vector reductions, so small-M GEMMs (context-parallel ranks) still fill the SMs
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * splits;
   const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -85,8 +89,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % num_m) * BM;
-      const int n0 = (tile / num_m) * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int n0 = ((tile / num_m) % num_n) * BN;
+      const int kb0 = (tile / num_mn) * kb_per;
+      const int kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -108,7 +114,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = (tile / num_mn) * kb_per;
+      const int kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
@@ -117,7 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128B swizzle atom (descriptor address is in 16 B units)
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -135,7 +143,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % num_m) * BM;
-      const int n0 = (tile / num_m) * BN;
+      const int n0 = ((tile / num_m) % num_n) * BN;
+      const bool first_slice = tile < num_mn;          // the bias is added by K slice 0 only
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
@@ -153,7 +162,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias != nullptr) {
+          if (ep.bias != nullptr && first_slice) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
@@ -165,15 +174,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
             }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+            uint4 q[4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]);
-              q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
+            for (int j = 0; j < 4; ++j) {
+              q[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              q[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              q[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              q[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            }
+            const int64_t off = static_cast<int64_t>(row) * ep.ldo + col0;
+            if (ep.n_out_peers == 0) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + off;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
+            } else {
+              // context parallel: the same tile is stored into every rank's buffer (stores to peer memory over NVLink)
+              for (int pr = 0; pr < ep.n_out_peers; ++pr) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out_peers[pr]) + off;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
+              }
             }
           } else if (ep.mode == GEMM_EPI_F32) {
             float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
@@ -181,17 +201,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {  // GEMM_EPI_F32_RESIDUAL: out += alpha * gate[cls, col] * (acc + bias)
+            // the add is performed by the L2 (red.global.add.v4.f32): no read of the residual on the SM, and K slices
+            // of a split-K launch can accumulate into the same rows
             float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
             const float* g = ep.gate ? ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col0 : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 x = *reinterpret_cast<float4*>(o + j);
               float4 gg = g ? __ldg(reinterpret_cast<const float4*>(g + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
-              x.x += ep.alpha * gg.x * v[j];
-              x.y += ep.alpha * gg.y * v[j + 1];
-              x.z += ep.alpha * gg.z * v[j + 2];
-              x.w += ep.alpha * gg.w * v[j + 3];
-              *reinterpret_cast<float4*>(o + j) = x;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * gg.x * v[j]),
+                           "f"(ep.alpha * gg.y * v[j + 1]), "f"(ep.alpha * gg.z * v[j + 2]),
+                           "f"(ep.alpha * gg.w * v[j + 3])
+                           : "memory");
             }
           }
         }
@@ -212,7 +232,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int K, const GemmEpilogue& ep,
+int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int K, int splits, const GemmEpilogue& ep,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
@@ -221,9 +241,9 @@ int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int 
                                          Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ta, *tb, M, N, K, ep);
+  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ta, *tb, M, N, K, splits, ep);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
@@ -238,22 +258,31 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
   LTX2_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16 B rows)");
   LTX2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
-  LTX2_REQUIRE(ep.out != nullptr, "gemm: null output");
-  // BN=256 fills the tensor pipe best; fall back to narrower tiles when N is small or when
-  // 128x256 tiles would leave most SMs idle.
-  int bn = 256;
+  LTX2_REQUIRE(ep.out != nullptr || ep.n_out_peers > 0, "gemm: null output");
+  // BN=256 fills the tensor pipe best; fall back to narrower tiles when N is small or when 128x256 tiles would
+  // leave most SMs idle.  The residual epilogue accumulates with reductions, so there the K loop is split instead.
+  int bn = 256, splits = 1;
+  const int num_kb = (K + BK - 1) / BK;
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
-  if (N % 256 != 0 || tiles256 < num_sms() / 2) bn = 128;
-  if (N % 128 != 0 || (bn == 128 && ((M + BM - 1) / BM) * ((N + 127) / 128) < num_sms() / 2)) bn = 64;
-  if (N % 64 != 0) bn = 32;
+  if (N % 256 == 0 && ep.mode == GEMM_EPI_F32_RESIDUAL && ep.max_splits > 1 && tiles256 < num_sms()) {
+    splits = num_sms() / tiles256;
+    if (splits > ep.max_splits) splits = ep.max_splits;
+    if (splits > 8) splits = 8;
+    while (splits > 1 && num_kb / splits < 8) --splits;     // keep >= 8 K blocks (512 of K) per slice
+    if (splits < 1) splits = 1;
+  } else {
+    if (N % 256 != 0 || tiles256 < num_sms() / 2) bn = 128;
+    if (N % 128 != 0 || (bn == 128 && ((M + BM - 1) / BM) * ((N + 127) / 128) < num_sms() / 2)) bn = 64;
+    if (N % 64 != 0) bn = 32;
+  }
   const CUtensorMap *ta, *tb;
   LTX2_PROPAGATE(get_tensor_map_2d(&ta, A, M, K, lda, BM));
   LTX2_PROPAGATE(get_tensor_map_2d(&tb, W, N, K, ldw, bn));
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, M, N, K, ep, stream);
-    case 128: return launch_gemm<128>(ta, tb, M, N, K, ep, stream);
-    case 64: return launch_gemm<64>(ta, tb, M, N, K, ep, stream);
-    default: return launch_gemm<32>(ta, tb, M, N, K, ep, stream);
+    case 256: return launch_gemm<256>(ta, tb, M, N, K, splits, ep, stream);
+    case 128: return launch_gemm<128>(ta, tb, M, N, K, splits, ep, stream);
+    case 64: return launch_gemm<64>(ta, tb, M, N, K, splits, ep, stream);
+    default: return launch_gemm<32>(ta, tb, M, N, K, splits, ep, stream);
   }
 }
 

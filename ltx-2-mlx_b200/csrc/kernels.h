@@ -27,6 +27,9 @@ struct GemmEpilogue {
   int64_t gate_stride = 0;
   const int* row_cls = nullptr;    // [M] modulation class of each row, or null (= 0)
   float alpha = 1.0f;
+  void* out_peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_out_peers = 0;             // bf16 modes: > 0 replicates the store into every out_peers[i] (peer-memory broadcast)
+  int max_splits = 1;              // > 1 allows split-K for the residual mode (accumulation order then varies run to run)
 };
 
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
@@ -76,6 +79,9 @@ struct HeadScatter {
 };
 int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* wk, const float* cos, const float* sin,
                      const HeadScatter& dst, int B, int T, int H, int Dh, float eps, cudaStream_t stream);
+
+// copy `bytes` from src to dst_peers[0..n_peers) (peer pointers), coalesced
+int peer_broadcast(const void* src, void* const* dst_peers, int n_peers, int64_t bytes, cudaStream_t stream);
 
 // cross-GPU barrier on flag words in peer memory: signal epoch to every rank's flags[rank], wait for all of mine
 int cp_barrier(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int world, uint32_t epoch,

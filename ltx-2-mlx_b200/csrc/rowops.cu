@@ -271,6 +271,17 @@ qkv_head_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const
   }
 }
 
+// coalesced copy of a contiguous block to the same offset of every peer buffer (consecutive threads write
+// consecutive 16 B, so NVLink sees full-size write packets -- row-strided 16 B stores from a GEMM epilogue do not)
+struct PeerList { uint4* p[kMaxCpRanks]; };
+__global__ void peer_broadcast_kernel(const uint4* __restrict__ src, PeerList dst, int n_peers, int64_t n16) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = src[i];
+    for (int r = 0; r < n_peers; ++r) dst.p[r][i] = v;
+  }
+}
+
 // signal `epoch` into every rank's flag array (slot = my rank), then wait until all my slots reached it
 __global__ void cp_barrier_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t* my_flags, int rank, int world,
                                   uint32_t epoch) {
@@ -526,6 +537,20 @@ int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* 
                "qkv_head_scatter: %d heads cannot be split %d per rank", H, dst.heads_per_rank);
   qkv_head_scatter_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, wq, wk,
                                                              cos, sin, dst, T, H, Dh, eps);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int peer_broadcast(const void* src, void* const* dst_peers, int n_peers, int64_t bytes, cudaStream_t stream) {
+  LTX2_REQUIRE(bytes % 16 == 0 && n_peers <= kMaxCpRanks, "peer_broadcast: size must be a multiple of 16 bytes");
+  if (bytes == 0 || n_peers == 0) return LTX2_OK;
+  PeerList pl;
+  for (int r = 0; r < n_peers; ++r) pl.p[r] = reinterpret_cast<uint4*>(dst_peers[r]);
+  const int64_t n16 = bytes / 16;
+  int grid = static_cast<int>((n16 + 255) / 256);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  peer_broadcast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), pl, n_peers, n16);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

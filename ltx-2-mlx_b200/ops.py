@@ -27,7 +27,7 @@ def _cuda(*ts):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, mode: int = EPI_BF16,
          out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
-         row_cls: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+         row_cls: Optional[torch.Tensor] = None, alpha: float = 1.0, max_splits: int = 1) -> torch.Tensor:
     """C = A W^T (+ epilogue).  a [M,K] bf16, w [N,K] bf16, bias [N] fp32."""
     _cuda(a, w, bias, out, gate, row_cls)
     M, K = a.shape
@@ -35,6 +35,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if out is None:
         assert mode != EPI_F32_RESIDUAL
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if mode == EPI_F32 else torch.bfloat16)
+    if max_splits > 1:
+        assert mode == EPI_F32_RESIDUAL
+        check(lib().ltx2_gemm_bf16_splitk(ptr(a), C.c_int64(a.stride(0)), ptr(w), C.c_int64(w.stride(0)), M, N, K,
+                                          ptr(bias), ptr(out), C.c_int64(out.stride(0)), ptr(gate),
+                                          C.c_int64(gate.stride(0) if gate is not None else 0), ptr(row_cls),
+                                          C.c_float(alpha), max_splits, stream_ptr()), "ltx2_gemm_bf16_splitk")
+        return out
     check(lib().ltx2_gemm_bf16(ptr(a), C.c_int64(a.stride(0)), ptr(w), C.c_int64(w.stride(0)), M, N, K, mode,
                                ptr(bias), ptr(out), C.c_int64(out.stride(0)), ptr(gate),
                                C.c_int64(gate.stride(0) if gate is not None else 0), ptr(row_cls),

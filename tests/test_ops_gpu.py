@@ -239,3 +239,18 @@ def test_attention_v_in_row_form_from_fused_qkv(B, H, Tq, Tk, Dh):
     v = v_rows.reshape(B, Tk, H, Dh).permute(0, 2, 1, 3)
     ref, _ = _attn_ref(q, k, v)
     assert rel_err(out.float(), ref) < 1.2e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 4096), (432, 4096, 4096), (432, 4096, 16384), (100, 512, 640)])
+def test_gemm_residual_split_k_small_m(M, N, K):
+    """Small-M residual GEMMs (context-parallel ranks) split K across CTAs and accumulate with vector reductions."""
+    from ltx2_b200 import ops
+    a, w = rnd(M, K, seed=80, dtype=torch.bfloat16), rnd(N, K, seed=81, std=K ** -0.5, dtype=torch.bfloat16)
+    bias, x = rnd(N, seed=82), rnd(M, N, seed=83)
+    gate = rnd(2, N, seed=84)
+    cls = (torch.arange(M, device=dev()) % 2).to(torch.int32)
+    ref = x + gate[cls.long()] * (a.float() @ w.float().T + bias)
+    y = x.clone()
+    ops.gemm(a, w, bias, mode=ops.EPI_F32_RESIDUAL, out=y, gate=gate, row_cls=cls, max_splits=8)
+    assert rel_err(y, ref) < TOL_F32_OUT
+    assert float((y - ref).abs().max()) < 3e-4 * max(1.0, float(ref.abs().max()))

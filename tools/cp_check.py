@@ -26,12 +26,19 @@ def main():
     kw = dict(model_type=LTXModelType.VideoOnly, num_attention_heads=heads, attention_head_dim=128, in_channels=32,
               out_channels=32, num_layers=3, cross_attention_dim=heads * 128, caption_channels=64, device=dev)
     ok = True
-    for (B, F, H, W, S, per_token) in [(1, 4, 8, 8, 40, False), (2, 2, 4, 8, 24, True)]:
+    cases = [(1, 4, 8, 8, 64, False), (2, 2, 4, 8, 24, True), (2, 4, 4, 8, 128, False)]
+    # every case twice: split-K off (LTX2_CP_SPLIT_K=1) must be BIT-EXACT against the single-GPU engine -- this is the
+    # check of the sharding, head exchange and context broadcast -- then with the default split-K, a tolerance (below)
+    for (B, F, H, W, S, per_token), split_k in [(c, k) for c in cases for k in (1, 0)]:
         N = F * H * W
+        if split_k:
+            os.environ["LTX2_CP_SPLIT_K"] = str(split_k)
+        else:
+            os.environ.pop("LTX2_CP_SPLIT_K", None)
         single, sharded = LTXModel(**kw), LTXModel(**kw)
         load_transformer_state_dict(single, w)
         load_transformer_state_dict(sharded, w)
-        context_parallel.enable(sharded, batch=B, n_total=N)
+        context_parallel.enable(sharded, batch=B, n_total=N, context_tokens=S if S % (8 * world) == 0 else 0)
         lat = synthetic.latents((B, N, 32), seed=300)
         ctx = synthetic.latents((B, S, 64), seed=301, std=0.5)
         pos = synthetic.video_positions(B, F, H, W)
@@ -48,10 +55,18 @@ def main():
             d = float((out - ref).abs().max())
             d0 = float((x0 - x0r).abs().max())
             scale = float(ref.abs().max())
-            good = out.shape == ref.shape and d <= 1e-5 * max(scale, 1.0) and d0 <= 1e-5 * max(scale, 1.0)
+            rl2 = float((out - ref).norm() / ref.norm())
+            if split_k == 1:
+                good = torch.equal(out, ref) and torch.equal(x0, x0r)
+            else:
+                # split-K reductions change the fp32 summation order of the residual stream by ~1e-7; downstream that
+                # flips a few bf16 roundings of GEMM inputs (one bf16 ulp = 0.4 %), so the bound is a relative L2 of
+                # 2e-3: a tenth of the engine-vs-oracle tolerance (2e-2, tests/test_dit_gpu.py)
+                good = (out.shape == ref.shape and rl2 <= 2e-3 and d <= 1e-2 * max(scale, 1.0)
+                        and d0 <= 1e-2 * max(scale, 1.0))
             ok = ok and good
-            print(f"rank {rank} case B={B} N={N} per_token={per_token} step {step}: max|diff| {d:.3e} x0 {d0:.3e} "
-                  f"(max|ref| {scale:.3e}) {'OK' if good else 'MISMATCH'}", flush=True)
+            print(f"rank {rank} case B={B} N={N} per_token={per_token} split_k={split_k or 'default'} step {step}: max|diff| {d:.3e} x0 {d0:.3e} "
+                  f"(max|ref| {scale:.3e}, rel L2 {rl2:.2e}) {'OK' if good else 'MISMATCH'}", flush=True)
         del single, sharded
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
