@@ -187,6 +187,10 @@ struct CpState {
   bool opened[kMaxCpRanks] = {false, false, false, false, false, false, false, false};
   size_t off_q = 0, off_k = 0, off_v = 0, off_o = 0, off_flags = 0;
   size_t off_ckv[2] = {0, 0};      // text-context K/V of the current / next block, [B*S, 2*D] bf16 each
+  size_t off_gate = 0;              // gated self-attention: per-head gate logits of all tokens for MY heads, fp32
+  size_t off_akv = 0;               // AV: video-side K|V projection of the v2a attention for ALL tokens [B*Nt, 2*Da]
+  size_t off_crope[2][2] = {{0, 0}, {0, 0}};   // AV: cross-modal RoPE cos/sin of all video tokens, double-buffered per forward
+  int fwd_parity = 0;
   int split_k = 8;                  // split-K cap of the residual GEMMs on sharded ranks (LTX2_CP_SPLIT_K, 1 = off)
   int ctx_tokens = 0;               // > 0: every rank projects S/P context rows and broadcasts them to all peers
   uint32_t** peer_flags_dev = nullptr;
@@ -452,7 +456,8 @@ int ensure_workspace(LtxDit* e, const Shapes& s) {
                       ctx_ch_v, s.B, s.N, s.S, s.n_cls, e->n_ada, s.Na, e->Da, e->Da, v2, gated, av);
     if (av)
       layout_stream_buf(ab, ar, c, e->Da, c.audio_heads, c.audio_head_dim, c.audio_in_channels, c.audio_out_channels,
-                        ctx_ch_a, s.B, s.Na, s.Sa, s.n_cls_a, e->n_ada, s.N, e->D, e->Da, v2, gated, av);
+                        ctx_ch_a, s.B, s.Na, s.Sa, s.n_cls_a, e->n_ada, e->cp.world > 1 ? e->cp.n_total : s.N, e->D, e->Da,
+                        v2, gated, av);
     float* scratch = (float*)ar.take(size_t(64) * (256 + 12 * std::max(e->D, 1)) * 4);
     if (pass == 0) {
       const size_t need = ar.off + 1024;
@@ -933,6 +938,19 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     // q/k-norm + RoPE + the token->head all-to-all in one kernel: every head is stored into its owner's buffers
     LTX2_PROPAGATE(qkv_head_scatter(sb.qkv, 3 * inner, aw.qnorm, aw.knorm, sb.cos, sb.sin, hs, B, N, H, Dh,
                                     e->cfg.norm_eps, st));
+    const float* gl = nullptr;
+    if (aw.gate.w != nullptr) {
+      // per-head gate logits of my token rows (attention.py:243-250), sent to the ranks that own each head
+      if (H % 32 == 0) {
+        LTX2_PROPAGATE(linear_f32(sb.xn, dim, aw.gate, M, sb.gate_logits, H, st));
+      } else {
+        LTX2_PROPAGATE(rowdot_bf16(sb.xn, dim, aw.gate.w, aw.gate.b, sb.gate_logits, M, H, aw.gate.in, st));
+      }
+      float* peers[kMaxCpRanks];
+      for (int r = 0; r < cp.world; ++r) peers[r] = reinterpret_cast<float*>(cp.peer_base[r] + cp.off_gate);
+      LTX2_PROPAGATE(gate_scatter(sb.gate_logits, peers, B, N, H, Hl, Nt, cp.rank * cp.n_local, st));
+      gl = reinterpret_cast<const float*>(cp.region + cp.off_gate);
+    }
     if (cp.ctx_tokens == S && !v2) {
       // text-context K/V for this block: each rank projects S/P context rows and stores the result into EVERY rank's
       // buffer (GEMM epilogue with peer destinations) instead of all ranks repeating the full projection
@@ -962,11 +980,15 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
       ProfScope ps(PROF_ATTN, 4.0 * B * Hl * double(Nt) * Nt * Dh, st);
       // attention over all tokens for my heads; the epilogue stores each row into the token owner's buffer
       LTX2_PROPAGATE(attention_bf16_v(cp.region + cp.off_q, cp.region + cp.off_k, av, nullptr, B, Hl, Nt, Nt, Dh,
-                                      1.0f / sqrtf((float)Dh), nullptr, nullptr, st, nullptr, &sc));
+                                      1.0f / sqrtf((float)Dh), gl, nullptr, st, nullptr, &sc));
     }
     LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, my_flags, cp.rank, cp.world, ++cp.epoch, st));
     LTX2_PROPAGATE(linear_residual(reinterpret_cast<const bf16*>(cp.region + cp.off_o), inner, aw.o, M, sb.x, dim,
                                    mod + 2 * dim, ms, sb.row_cls, 1.0f, st));
+  } else if (skip_self && e->cp.world > 1 && &sb == &e->vb) {
+    // STG skip on sharded ranks: keep one barrier per block so the double-buffered exchange areas stay ordered
+    LTX2_PROPAGATE(cp_barrier(e->cp.peer_flags_dev, reinterpret_cast<uint32_t*>(e->cp.region + e->cp.off_flags),
+                              e->cp.rank, e->cp.world, ++e->cp.epoch, st));
   } else if (!skip_self) {
     LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
     AttnCall a{&w.attn1, sb.xn, dim, M, N, sb.xn, dim, N, sb.cos, sb.sin, sb.cos, sb.sin};
@@ -1053,12 +1075,9 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   }
   if (e->cp.world > 1) {
     LTX2_REQUIRE(e->cp.connected, "context parallel: ltx2_dit_cp_connect has not been called");
-    LTX2_REQUIRE(!has_audio && !c.apply_gated_attention,
-                 "context parallel supports the video-only, non-gated model in this round");
     LTX2_REQUIRE(video->tokens == e->cp.n_local && video->batch == e->cp.B,
                  "context parallel: expected the local slice of %d tokens (batch %d), got %d (batch %d)",
                  e->cp.n_local, e->cp.B, video->tokens, video->batch);
-    LTX2_REQUIRE(skip == nullptr || skip->video_self_attn == 0, "context parallel: STG self-attention skips unsupported");
   }
   LtxDitSkip sk = {0, 0, 0, 0};
   if (skip) sk = *skip;
@@ -1091,6 +1110,23 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     const float mp[1] = {c.audio_max_pos};
     LTX2_PROPAGATE(rope_tables_dev(video->positions, sh.B, 3, 1, sh.N, e->Da, mp, e->fg_audio, e->nf_audio, vb.ccos,
                                    vb.csin, st));
+    if (e->cp.world > 1) {
+      // the v2a keys are ALL video tokens: gather every rank's slice of the table into every rank's copy
+      CpState& cp = e->cp;
+      cp.fwd_parity ^= 1;
+      const size_t half = size_t(e->Da) / 2, slice = size_t(cp.n_local) * half * 4;
+      for (int t = 0; t < 2; ++t)
+        for (int b = 0; b < sh.B; ++b) {
+          const size_t byte0 = cp.off_crope[cp.fwd_parity][t] + (size_t(b) * cp.n_total + size_t(cp.rank) * cp.n_local) * half * 4;
+          const float* src = (t == 0 ? vb.ccos : vb.csin) + size_t(b) * cp.n_local * half;
+          LTX2_CUDA_CHECK(cudaMemcpyAsync(cp.region + byte0, src, slice, cudaMemcpyDeviceToDevice, st));
+          void* peers[kMaxCpRanks];
+          int np = 0;
+          for (int r = 0; r < cp.world; ++r)
+            if (r != cp.rank) peers[np++] = cp.peer_base[r] + byte0;
+          LTX2_PROPAGATE(peer_broadcast(cp.region + byte0, peers, np, int64_t(slice), st));
+        }
+    }
     // cross-attention timestep embeddings use the OTHER modality's sigma (model.py:394-399)
     LTX2_PROPAGATE(prepare_cross_mod(e, vb, e->av_v_ss, e->av_v_gate, e->catable_arena_v, *audio, st));
     LTX2_PROPAGATE(prepare_cross_mod(e, ab, e->av_a_ss, e->av_a_gate, e->catable_arena_a, *video, st));
@@ -1101,8 +1137,13 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     const BlockW& w = e->blocks[l];
     const uint64_t bit = uint64_t(1) << l;
     const float cas = isnan(e->cross_attn_scale[l]) ? 1.0f : e->cross_attn_scale[l];
+    // split-K reductions are unordered fp32 atomics: only the sharded video stream uses them; the audio stream is
+    // REPLICATED across ranks and must stay bit-identical on all of them
+    const int split_v = e->cp.world > 1 ? e->cp.split_k : 1;
+    g_split_k = split_v;
     LTX2_PROPAGATE(run_self_and_text(e, vb, w.v, l, (sk.video_self_attn & bit) != 0, cas, st));
     if (has_audio) {
+      g_split_k = 1;
       LTX2_PROPAGATE(run_self_and_text(e, ab, w.a, l, (sk.audio_self_attn & bit) != 0, 1.0f, st));
       const bool do_a2v = (sk.a2v_cross_attn & bit) == 0, do_v2a = (sk.v2a_cross_attn & bit) == 0;
       const float* cmv = vb.ca_mod + size_t(l) * B * 5 * D;     // rows: scale_a2v, shift_a2v, scale_v2a, shift_v2a, gate
@@ -1119,18 +1160,46 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
       }
       if (do_a2v) {
         AttnCall a{&w.a2v, vq, D, B * N, N, ak, Da, Na, vb.ccos, vb.csin, ab.cos, ab.sin};
+        g_split_k = split_v;
         LTX2_PROPAGATE(run_attention_core(e, vb, a, B, st));
         LTX2_PROPAGATE(linear_residual(vb.attn, w.a2v.inner, w.a2v.o, B * N, vb.x, D, cmv + 4 * D, int64_t(5) * D,
                                        vb.row_batch, 1.0f, st));
       }
-      if (do_v2a) {
+      g_split_k = 1;
+      if (do_v2a && e->cp.world > 1) {
+        // audio queries (replicated) attend over ALL video tokens: every rank projects K|V of its token slice into
+        // every rank's [B*Nt, 2*Da] buffer, then all ranks run the same (small) attention -- SURVEY.md 8(e) item 2
+        CpState& cp = e->cp;
+        const int inner = w.v2a.inner, Nt = cp.n_total;
+        for (int b = 0; b < B; ++b) {
+          const size_t byte0 = cp.off_akv + (size_t(b) * Nt + size_t(cp.rank) * N) * 2 * inner * sizeof(bf16);
+          bf16* mine = reinterpret_cast<bf16*>(cp.region + byte0);
+          LTX2_PROPAGATE(linear_bf16(vk + size_t(b) * N * D, D, w.v2a.kv, N, mine, 2 * inner, false, st));
+          void* peers[kMaxCpRanks];
+          int np = 0;
+          for (int r = 0; r < cp.world; ++r)
+            if (r != cp.rank) peers[np++] = cp.peer_base[r] + byte0;
+          LTX2_PROPAGATE(peer_broadcast(mine, peers, np, int64_t(N) * 2 * inner * sizeof(bf16), st));
+        }
+        LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank,
+                                  cp.world, ++cp.epoch, st));
+        AttnCall a{&w.v2a, aq, Da, B * Na, Na, nullptr, D, Nt, ab.cos, ab.sin,
+                   reinterpret_cast<const float*>(cp.region + cp.off_crope[cp.fwd_parity][0]),
+                   reinterpret_cast<const float*>(cp.region + cp.off_crope[cp.fwd_parity][1])};
+        a.kv_pre = reinterpret_cast<const bf16*>(cp.region + cp.off_akv);
+        LTX2_PROPAGATE(run_attention_core(e, ab, a, B, st));
+        LTX2_PROPAGATE(linear_residual(ab.attn, w.v2a.inner, w.v2a.o, B * Na, ab.x, Da, cma + 4 * Da, int64_t(5) * Da,
+                                       ab.row_batch, 1.0f, st));
+      } else if (do_v2a) {
         AttnCall a{&w.v2a, aq, Da, B * Na, Na, vk, D, N, ab.cos, ab.sin, vb.ccos, vb.csin};
         LTX2_PROPAGATE(run_attention_core(e, ab, a, B, st));
         LTX2_PROPAGATE(linear_residual(ab.attn, w.v2a.inner, w.v2a.o, B * Na, ab.x, Da, cma + 4 * Da, int64_t(5) * Da,
                                        ab.row_batch, 1.0f, st));
       }
     }
+    g_split_k = split_v;
     LTX2_PROPAGATE(run_ffn(e, vb, w.v, l, st));
+    g_split_k = 1;
     if (has_audio) LTX2_PROPAGATE(run_ffn(e, ab, w.a, l, st));
   }
   LTX2_PROPAGATE(run_head(e, vb, e->vw, *video, x0, out_video, st));
@@ -1198,6 +1267,13 @@ extern "C" int ltx2_dit_cp_init(LtxDit* e, int32_t rank, int32_t world, int32_t 
     cp.off_ckv[0] = end;
     cp.off_ckv[1] = end + ckv_bytes;
     end += 2 * ckv_bytes;
+  }
+  auto take = [&](size_t bytes) { const size_t o = end; end += (bytes + 255) & ~size_t(255); return o; };
+  if (c.apply_gated_attention) cp.off_gate = take(size_t(batch) * n_total * cp.heads_local * 4);
+  if (c.audio_enabled) {
+    cp.off_akv = take(size_t(batch) * n_total * 2 * e->Da * 2);
+    for (int p = 0; p < 2; ++p)
+      for (int t = 0; t < 2; ++t) cp.off_crope[p][t] = take(size_t(batch) * n_total * (e->Da / 2) * 4);
   }
   cp.off_flags = end;
   cp.region_bytes = cp.off_flags + 256;

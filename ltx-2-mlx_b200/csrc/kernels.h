@@ -81,6 +81,8 @@ int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* 
                      const HeadScatter& dst, int B, int T, int H, int Dh, float eps, cudaStream_t stream);
 
 // copy `bytes` from src to dst_peers[0..n_peers) (peer pointers), coalesced
+int gate_scatter(const float* logits, float* const* dst_peers, int B, int n_local, int H, int heads_per_rank,
+                 int n_total, int t_offset, cudaStream_t stream);
 int peer_broadcast(const void* src, void* const* dst_peers, int n_peers, int64_t bytes, cudaStream_t stream);
 
 // cross-GPU barrier on flag words in peer memory: signal epoch to every rank's flags[rank], wait for all of mine

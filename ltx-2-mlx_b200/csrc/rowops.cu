@@ -282,6 +282,18 @@ __global__ void peer_broadcast_kernel(const uint4* __restrict__ src, PeerList ds
   }
 }
 
+// per-head gate logits [B*n_local, H] (fp32) -> the rank owning each head: dst[r][(b*Nt + t0 + t)*Hl + h%Hl]
+struct GatePeers { float* p[kMaxCpRanks]; };
+__global__ void gate_scatter_kernel(const float* __restrict__ src, GatePeers dst, int n_local, int H, int Hl, int Nt,
+                                    int t0, int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int h = i % H;
+  const int64_t row = i / H;
+  const int t = row % n_local, b = row / n_local;
+  dst.p[h / Hl][(static_cast<int64_t>(b) * Nt + t0 + t) * Hl + h % Hl] = src[i];
+}
+
 // signal `epoch` into every rank's flag array (slot = my rank), then wait until all my slots reached it
 __global__ void cp_barrier_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t* my_flags, int rank, int world,
                                   uint32_t epoch) {
@@ -551,6 +563,20 @@ int peer_broadcast(const void* src, void* const* dst_peers, int n_peers, int64_t
   int grid = static_cast<int>((n16 + 255) / 256);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   peer_broadcast_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), pl, n_peers, n16);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int gate_scatter(const float* logits, float* const* dst_peers, int B, int n_local, int H, int heads_per_rank,
+                 int n_total, int t_offset, cudaStream_t stream) {
+  LTX2_REQUIRE(H % heads_per_rank == 0 && H / heads_per_rank <= kMaxCpRanks, "gate_scatter: bad head split");
+  const int64_t total = static_cast<int64_t>(B) * n_local * H;
+  if (total == 0) return LTX2_OK;
+  GatePeers gp;
+  for (int r = 0; r < H / heads_per_rank; ++r) gp.p[r] = dst_peers[r];
+  gate_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(logits, gp, n_local, H, heads_per_rank,
+                                                                                    n_total, t_offset, total);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

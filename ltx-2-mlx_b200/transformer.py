@@ -390,6 +390,10 @@ class LTXModel:
             rank, world, _, cp_b, cp_n = self._cp
             if (B, N) != (cp_b, cp_n):
                 raise ValueError(f"context parallel was enabled for batch {cp_b} x {cp_n} tokens, got {B} x {N}")
+            if sigma is None and ts.shape[1] != 1:
+                # the scalar sigma of a modality defaults to its FIRST token's timestep (model.py:250-260,394-399);
+                # take it before slicing so every rank uses token 0 of the whole sequence
+                sigma = ts[:, 0].contiguous()
             latent, ts, pos = slice_tokens(latent, ts, pos, rank, world)
             N = latent.shape[1]
         keep.extend([latent, context, ts, pos, sigma])

@@ -14,6 +14,73 @@ from ltx2_b200.loader import load_transformer_state_dict  # noqa: E402
 from ltx2_b200.transformer import LTXModel, LTXModelType, Modality, X0Model  # noqa: E402
 
 
+def av_cases(rank, world, dev):
+    """V2.3-style audio+video model (cross_attention_adaln, gated attention, a2v/v2a) sharded over the ranks, with and
+    without STG skips: the video stream is token-sharded, the audio stream replicated."""
+    from ltx2_b200.transformer import (BatchedPerturbationConfig, Perturbation, PerturbationConfig, PerturbationType)
+    heads = 8
+    cfg = synthetic.DitConfig(num_attention_heads=heads, attention_head_dim=128, in_channels=32, out_channels=32,
+                              num_layers=3, cross_attention_dim=heads * 128, caption_channels=None,
+                              cross_attention_adaln=True, apply_gated_attention=True, audio=True,
+                              audio_heads=heads, audio_head_dim=64)
+    w = synthetic.dit_weights(cfg, seed=33)
+
+    class Small(LTXModel):
+        AUDIO_ATTENTION_HEADS = heads
+        AUDIO_HEAD_DIM = 64
+
+    kw = dict(model_type=LTXModelType.AudioVideo, num_attention_heads=heads, attention_head_dim=128, in_channels=32,
+              out_channels=32, num_layers=3, cross_attention_dim=heads * 128, caption_channels=None,
+              cross_attention_adaln=True, apply_gated_attention=True, av_ca_timestep_scale_multiplier=1000, device=dev)
+    ok = True
+    for (B, F, H, W, S, Na, per_token), split_k in [(c, k) for c in [(2, 2, 4, 8, 40, 9, False), (1, 4, 8, 8, 24, 17, True)]
+                                                    for k in (1, 0)]:
+        N = F * H * W
+        if split_k:
+            os.environ["LTX2_CP_SPLIT_K"] = str(split_k)
+        else:
+            os.environ.pop("LTX2_CP_SPLIT_K", None)
+        single, sharded = Small(**kw), Small(**kw)
+        load_transformer_state_dict(single, w)
+        load_transformer_state_dict(sharded, w)
+        assert sharded.missing_weights() == []
+        context_parallel.enable(sharded, batch=B, n_total=N)
+        lat = synthetic.latents((B, N, 32), seed=310)
+        ctx = synthetic.latents((B, S, heads * 128), seed=311, std=0.5)
+        pos = synthetic.video_positions(B, F, H, W)
+        alat = synthetic.latents((B, Na, 128), seed=312)
+        actx = synthetic.latents((B, S, heads * 64), seed=313, std=0.5)
+        apos = synthetic.audio_positions(B, Na)
+        sv, sa = torch.tensor([0.9, 0.4])[:B], torch.tensor([0.8, 0.3])[:B]
+        if per_token:
+            tsv = sv[:, None].repeat(1, N).clone()
+            tsv[:, : N // 4] = 0.0
+            vm = Modality(latent=lat, context=ctx, context_mask=None, timesteps=tsv, positions=pos)
+        else:
+            vm = Modality(latent=lat, context=ctx, context_mask=None, timesteps=sv, positions=pos, sigma=sv)
+        am = Modality(latent=alat, context=actx, context_mask=None, timesteps=sa, positions=apos, sigma=sa)
+        pc = PerturbationConfig([Perturbation(PerturbationType.SKIP_VIDEO_SELF_ATTN, [1]),
+                                 Perturbation(PerturbationType.SKIP_V2A_CROSS_ATTN, [0])])
+        for name, pert in [("plain", None), ("stg", BatchedPerturbationConfig([pc] * B)), ("plain2", None)]:
+            rv, ra = single(vm, am, perturbations=pert)
+            ov, oa = sharded(vm, am, perturbations=pert)
+            torch.cuda.synchronize()
+            if split_k == 1:
+                good = torch.equal(ov, rv) and torch.equal(oa, ra)
+            else:
+                good = (float((ov - rv).norm() / rv.norm()) <= 2e-3 and float((oa - ra).norm() / ra.norm()) <= 2e-3)
+            # the replicated audio stream must come out identical on every rank (no split-K on it)
+            parts = [torch.empty_like(oa) for _ in range(world)]
+            dist.all_gather(parts, oa.contiguous())
+            same = all(torch.equal(p, parts[0]) for p in parts)
+            ok = ok and good and same
+            print(f"rank {rank} AV case B={B} N={N} Na={Na} per_token={per_token} split_k={split_k or 'default'} {name}: "
+                  f"video rel {float((ov - rv).norm() / rv.norm()):.2e} audio rel {float((oa - ra).norm() / ra.norm()):.2e} "
+                  f"audio identical across ranks {same} {'OK' if good and same else 'MISMATCH'}", flush=True)
+        del single, sharded
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -68,6 +135,7 @@ def main():
             print(f"rank {rank} case B={B} N={N} per_token={per_token} split_k={split_k or 'default'} step {step}: max|diff| {d:.3e} x0 {d0:.3e} "
                   f"(max|ref| {scale:.3e}, rel L2 {rl2:.2e}) {'OK' if good else 'MISMATCH'}", flush=True)
         del single, sharded
+    ok = av_cases(rank, world, dev) and ok
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
