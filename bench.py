@@ -232,9 +232,11 @@ def vae_conv_flops(T, H, W, blocks=None, base=128):
     return total + 2 * C * 48 * 27 * T * H * W
 
 
-def bench_vae(args, dev, rank):
+def bench_vae(args, dev, rank, world=1):
     """decode_latent of a 9x16x24 latent (65 frames @ 512x768) exactly as the reference schedules it
-    (7-frame chunks, overlap 2, cross-fade, uint8), device-timed; plus the conv kernel's roofline."""
+    (7-frame chunks, overlap 2, cross-fade, uint8), device-timed; plus the conv kernel's roofline.
+    world > 1: the chunks are decoded round-robin over the ranks and collected on rank 0 (strong scaling; this
+    latent has only two chunks, so at most two ranks have work)."""
     import ctypes as C
     import torch
     from ltx2_b200 import _lib, synthetic
@@ -243,32 +245,50 @@ def bench_vae(args, dev, rank):
     dec = SimpleVideoDecoder(device=dev)
     dec.load_weights(synthetic.iter_vae_weights(vcfg, seed=0, device=dev, dtype=torch.bfloat16))
     assert not dec.missing_weights()
-    lat = synthetic.latents((1, 128, 9, 16, 24), seed=43 + rank).to(dev)
+    import torch.distributed as dist
+    lat = synthetic.latents((1, 128, 9, 16, 24), seed=43).to(dev)
     frames = 65
-    for _ in range(2):
-        out = decode_latent(lat, dec)
-    torch.cuda.synchronize()
+    kw = dict(group=dist.group.WORLD, dst=0) if world > 1 else {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        out = decode_latent(lat, dec, **kw)
     n = max(3, min(args.steps, 8))
     l0 = _lib.lib().ltx2_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
     e0.record()
     for _ in range(n):
-        out = decode_latent(lat, dec)
+        out = decode_latent(lat, dec, **kw)
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     ms = e0.elapsed_time(e1) / n
     launches = (_lib.lib().ltx2_launch_count() - l0) // n
-    assert out.shape == (frames, 512, 768, 3)
+    assert rank != 0 or out.shape == (frames, 512, 768, 3)
     # e2e: host latent in, uint8 frames on the host out
     lat_h = lat.cpu().pin_memory()
     out_h = torch.empty(frames, 512, 768, 3, dtype=torch.uint8).pin_memory()
+    sync()
     e0.record()
     for _ in range(n):
-        out_h.copy_(decode_latent(lat_h, dec), non_blocking=True)
+        r = decode_latent(lat_h, dec, **kw)
+        if r is not None:
+            out_h.copy_(r, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     ms_e2e = e0.elapsed_time(e1) / n
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        t2 = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        launches = int(t2[0])
     # roofline of the conv kernel: one profiled pass over the first (7 latent frame) chunk
     L = _lib.lib()
     _lib.check(L.ltx2_vae_set_profile(dec._h, 1))
@@ -284,6 +304,8 @@ def bench_vae(args, dev, rank):
         "metric": "VAE decode frames/sec", "value": frames * 1000.0 / ms, "unit": "frames/s", "ms_per_decode": ms,
         "config": {"workload": "decode_latent, latent 1x128x9x16x24 -> 65 frames @ 512x768, V2.0 decoder stack "
                                "(base 128, 5 res blocks/group), reference chunking 7/2 -> chunks " + str(plan),
+                   "parallelism": "single GPU" if world == 1 else
+                                  f"chunks round-robin over {world} ranks, collected on rank 0 (strong scaling)",
                    "noise": "decode_noise_scale 0.025 (reference default), timestep 0.05"},
         "gpu_launches": int(launches),
         "e2e": {"value": frames * 1000.0 / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(lat_h.numel() * 4),
@@ -403,11 +425,11 @@ def run_ours(args, c):
 
     # ---- second half of the metric: VAE decode frames/s (65 frames @ 512x768, BASELINE.json configs[4]) ----
     vae = None
-    if args.config == "19b" and not args.no_vae and rank == 0:
+    if args.config == "19b" and not args.no_vae:
         if world == 1:
             del x0model, model
             torch.cuda.empty_cache()
-        vae = bench_vae(args, dev, rank)
+        vae = bench_vae(args, dev, rank, world)
     if world > 1:
         dist.barrier()
 

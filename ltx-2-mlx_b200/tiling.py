@@ -138,8 +138,16 @@ def generate_tile_specs(latent_shape, tiling_config: TilingConfig, scale_factors
 
 
 def decode_tiled(latent, decoder_fn, tiling_config: TilingConfig, timestep: Optional[float] = 0.05,
-                 show_progress: bool = True, key=None) -> Iterator[torch.Tensor]:
-    """Yields the blended video (B, 3, 8(T-1)+1, 32H, 32W) fp32 once, like the reference generator."""
+                 show_progress: bool = True, key=None, group=None) -> Iterator[torch.Tensor]:
+    """Yields the blended video (B, 3, 8(T-1)+1, 32H, 32W) fp32 once, like the reference generator.
+
+    With a torch.distributed `group` the tiles (independent units) are decoded round-robin across the ranks; each
+    rank accumulates its own tiles and the weighted sums are all-reduced before the normalisation, so every rank
+    yields the full video."""
+    world, rank = 1, 0
+    if group is not None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = getattr(decoder_fn, "device", None) or torch.device("cuda", torch.cuda.current_device())
     x = to_device(latent, dev)
     b, _, t, h, w = x.shape
@@ -147,7 +155,9 @@ def decode_tiled(latent, decoder_fn, tiling_config: TilingConfig, timestep: Opti
     out = torch.zeros(b, 3, To, Ho, Wo, device=dev, dtype=torch.float32)
     wsum = torch.zeros(To, Ho, Wo, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        for s in generate_tile_specs(x.shape, tiling_config):
+        for i, s in enumerate(generate_tile_specs(x.shape, tiling_config)):
+            if i % world != rank:
+                continue
             tile = decoder_fn(x[:, :, s.in_t_start:s.in_t_end, s.in_h_start:s.in_h_end,
                                 s.in_w_start:s.in_w_end].contiguous(), timestep=timestep)
             tile = to_device(tile, dev, torch.float32)
@@ -162,5 +172,8 @@ def decode_tiled(latent, decoder_fn, tiling_config: TilingConfig, timestep: Opti
             check(lib().ltx2_tile_accumulate(ptr(out), ptr(wsum), ptr(tile), b * 3, To, Ho, Wo, dt, dh, dw,
                                              s.out_t_start, s.out_h_start, s.out_w_start, tt, th, tw, ptr(mt), ptr(mh),
                                              ptr(mw), stream_ptr()), "ltx2_tile_accumulate")
+        if world > 1:
+            dist.all_reduce(out, group=group)
+            dist.all_reduce(wsum, group=group)
         check(lib().ltx2_tile_normalize(ptr(out), ptr(wsum), b * 3, To * Ho * Wo, stream_ptr()), "ltx2_tile_normalize")
     yield out

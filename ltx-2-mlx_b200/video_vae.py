@@ -172,14 +172,44 @@ def _pix_t(lt: int) -> int:
     return lt
 
 
+def unit_owner(index: int, world: int) -> int:
+    """Round-robin owner of the index-th independent decode unit (temporal chunk or tile), SURVEY.md 8(e)."""
+    return index % world
+
+
+def _exchange_unit(t: torch.Tensor, owner: int, group, dst: Optional[int]) -> None:
+    """Move one decoded unit from its owner to `dst` (point to point) or to every rank (broadcast)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    g = lambda r: dist.get_global_rank(group, r)  # noqa: E731
+    if dst is None:
+        dist.broadcast(t, src=g(owner), group=group)
+    elif owner != dst:
+        if rank == owner:
+            dist.send(t, dst=g(dst), group=group)
+        elif rank == dst:
+            dist.recv(t, src=g(owner), group=group)
+
+
 def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[float] = 0.05,
-                        temporal_chunk_size: int = 7, temporal_overlap: int = 2) -> torch.Tensor:
-    """The float video (B,3,T,H,W) decode_latent builds before its uint8 conversion (:704-790)."""
+                        temporal_chunk_size: int = 7, temporal_overlap: int = 2, group=None,
+                        dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """The float video (B,3,T,H,W) decode_latent builds before its uint8 conversion (:704-790).
+
+    With a torch.distributed `group` (one rank per GPU, every rank holding the same latent and decoder weights) the
+    reference's temporal chunks are decoded round-robin across the ranks and exchanged before the cross-fade: to all
+    ranks (dst=None, every rank returns the video) or only to rank `dst` (the others return None)."""
     x = to_device(latent, decoder.device)
     if x.ndim == 4:
         x = x[None]
     T = x.shape[2]
+    world, rank = 1, 0
+    if group is not None:              # e.g. torch.distributed.group.WORLD
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
     if T <= temporal_chunk_size:
+        if world > 1 and dst is not None and rank != dst:
+            return None
         return decoder(x, timestep=timestep, show_progress=False)
     total = _pix_t(T)
     plan = chunk_plan(T, temporal_chunk_size, temporal_overlap)
@@ -188,25 +218,43 @@ def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[
     # chunks land at frame (len_so_far - overlap); the reference concatenates, we blend into one buffer
     pieces = []
     length = 0
-    for (a, b) in plan:
-        v = decoder(x[:, :, a:b].contiguous(), timestep=timestep, show_progress=False)
-        ov = 0 if not pieces else min(ref_overlap, v.shape[2], length)
+    for i, (a, b) in enumerate(plan):
+        if unit_owner(i, world) == rank:
+            v = decoder(x[:, :, a:b].contiguous(), timestep=timestep, show_progress=False)
+        elif dst is None or rank == dst:
+            v = torch.empty(decoder.output_shape((x.shape[0], x.shape[1], b - a, x.shape[3], x.shape[4])),
+                            device=decoder.device, dtype=torch.float32)
+        else:
+            v = None
+        n_t = _pix_t(b - a)
+        ov = 0 if not pieces else min(ref_overlap, n_t, length)
         if ov <= 1:
             ov = 0
-        pieces.append((v, length - ov, ov))
-        length = length - ov + v.shape[2]
+        pieces.append((v, length - ov, ov, n_t))
+        length = length - ov + n_t
+    if world > 1:
+        for i, (v, _, _, _) in enumerate(pieces):
+            if v is not None:
+                _exchange_unit(v, unit_owner(i, world), group, dst)
+        if dst is not None and rank != dst:
+            return None
     video = torch.empty(B, 3, length, H, W, device=decoder.device, dtype=torch.float32)
     with torch.cuda.device(decoder.device):
-        for v, t0, ov in pieces:
-            check(lib().ltx2_blend_chunk(ptr(video), ptr(v), B * 3, length, v.shape[2], H * W, t0, ov, stream_ptr()),
+        for v, t0, ov, n_t in pieces:
+            check(lib().ltx2_blend_chunk(ptr(video), ptr(v), B * 3, length, n_t, H * W, t0, ov, stream_ptr()),
                   "ltx2_blend_chunk")
     return video[:, :, :total]
 
 
 def decode_latent(latent, decoder: SimpleVideoDecoder, timestep: Optional[float] = 0.05, key=None,
-                  temporal_chunk_size: int = 7, temporal_overlap: int = 2) -> torch.Tensor:
-    """Decode latent to uint8 frames (T,H,W,3) -- drop-in for simple_decoder.decode_latent (:676-800)."""
-    video = decode_latent_video(latent, decoder, timestep, temporal_chunk_size, temporal_overlap).contiguous()
+                  temporal_chunk_size: int = 7, temporal_overlap: int = 2, group=None,
+                  dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Decode latent to uint8 frames (T,H,W,3) -- drop-in for simple_decoder.decode_latent (:676-800).
+    `group` / `dst`: multi-GPU chunk sharding, see decode_latent_video."""
+    video = decode_latent_video(latent, decoder, timestep, temporal_chunk_size, temporal_overlap, group, dst)
+    if video is None:
+        return None
+    video = video.contiguous()
     B, _, T, H, W = video.shape
     out = torch.empty(T, H, W, 3, device=decoder.device, dtype=torch.uint8)
     with torch.cuda.device(decoder.device):

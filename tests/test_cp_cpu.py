@@ -1,5 +1,5 @@
 """Host logic of the context-parallel layer on CPU with the gloo backend (world_size 2): token slicing, the output
-all-gather and the IPC-handle exchange.  No GPU, no compute kernels."""
+all-gather, the IPC-handle exchange and the VAE unit (chunk / tile) ownership + exchange.  No GPU, no compute kernels."""
 import os
 import socket
 
@@ -41,6 +41,19 @@ def _worker(rank, world, port, q):
         assert handles == b"".join(bytes([r]) * 64 for r in range(world))
         with pytest.raises(ValueError):
             cp.token_range(13, rank, world)
+        # VAE decode units (chunks / tiles) are owned round-robin and exchanged to all ranks or to one rank
+        from ltx2_b200 import video_vae as vv
+        assert [vv.unit_owner(i, world) for i in range(5)] == [0, 1, 0, 1, 0]
+        G = dist.group.WORLD
+        for i in range(3):
+            owner = vv.unit_owner(i, world)
+            unit = torch.full((2, 3), float(10 + i)) if rank == owner else torch.zeros(2, 3)
+            vv._exchange_unit(unit, owner, G, None)
+            assert torch.equal(unit, torch.full((2, 3), float(10 + i)))
+            unit = torch.full((2, 3), float(20 + i)) if rank == owner else torch.zeros(2, 3)
+            vv._exchange_unit(unit, owner, G, 0)
+            if rank == 0 or rank == owner:
+                assert torch.equal(unit, torch.full((2, 3), float(20 + i)))
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))

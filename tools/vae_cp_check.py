@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Multi-GPU VAE decode check, run under torchrun with one rank per GPU: chunk-sharded decode_latent and tile-sharded
+decode_tiled must reproduce the single-GPU results (chunks: bit-exact; tiles: fp32 sum order may differ by an ulp)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from ltx2_b200 import synthetic  # noqa: E402
+from ltx2_b200.tiling import SpatialTilingConfig, TemporalTilingConfig, TilingConfig, decode_tiled  # noqa: E402
+from ltx2_b200.video_vae import SimpleVideoDecoder, decode_latent, decode_latent_video  # noqa: E402
+
+BLOCKS = [["res_x", {"num_layers": 2}], ["compress_all", {"multiplier": 2, "residual": True}],
+          ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 2, "residual": True}],
+          ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 2, "residual": True}],
+          ["res_x", {"num_layers": 1}]]
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    G = dist.group.WORLD
+    cfg = synthetic.VaeConfig(decoder_blocks=BLOCKS, base_channels=64, timestep_conditioning=True)
+    dec = SimpleVideoDecoder(decoder_blocks=BLOCKS, base_channels=64, timestep_conditioning=True, device=dev)
+    dec.load_weights(synthetic.vae_weights(cfg, seed=24))
+    dec.decode_noise_scale = 0.0
+    ok = True
+    for T in (9, 16, 23):
+        lat = synthetic.latents((1, 128, T, 2, 2), seed=400 + T)
+        ref = decode_latent_video(lat, dec)
+        out = decode_latent_video(lat, dec, group=G)
+        good = torch.equal(out, ref)
+        to0 = decode_latent(lat, dec, group=G, dst=0)
+        if rank == 0:
+            good = good and torch.equal(to0, decode_latent(lat, dec))
+        else:
+            good = good and to0 is None
+        ok = ok and good
+        print(f"rank {rank} chunks T_lat={T}: {'OK' if good else 'MISMATCH'}", flush=True)
+    lat = synthetic.latents((1, 128, 3, 6, 6), seed=410)
+    for name, tc in [("spatial", TilingConfig(SpatialTilingConfig(64, 32), None)),
+                     ("spatial+temporal", TilingConfig(SpatialTilingConfig(96, 32), TemporalTilingConfig(16, 8)))]:
+        ref = next(decode_tiled(lat, dec, tc, timestep=0.05))
+        out = next(decode_tiled(lat, dec, tc, timestep=0.05, group=G))
+        d = float((out - ref).abs().max())
+        good = out.shape == ref.shape and d <= 1e-5
+        ok = ok and good
+        print(f"rank {rank} tiles {name}: max|diff| {d:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    print("VAE_CP_CHECK_PASS" if int(t) == 1 else "VAE_CP_CHECK_FAIL", flush=True)
+    sys.exit(0 if int(t) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
