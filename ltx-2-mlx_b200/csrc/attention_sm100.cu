@@ -21,6 +21,9 @@
 //                          factor of P and l, which cancels in O / l).
 // K is consumed [keys, d] (K-major for S), V is consumed TRANSPOSED [d, keys] (K-major for P V), so
 // both MMAs use the same K-major/128B-swizzle descriptor form as the GEMM.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -425,14 +428,22 @@ int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, in
   LTX2_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
   LTX2_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "attention: B*H too large for grid.y");
   LTX2_REQUIRE(Dh == 64 || Dh == 128, "attention: head_dim %d unsupported (64 or 128)", Dh);
-  if (v.rows) {
+  if (v.rows)
     LTX2_REQUIRE(v.stride_t % 8 == 0 && v.stride_h % 8 == 0 && v.stride_b % 8 == 0,
                  "attention: V strides must be multiples of 8 elements (16 B)");
+  else
+    LTX2_REQUIRE(v.Tkp >= Tk && v.Tkp % 8 == 0, "attention: V^T pitch %lld must be >= Tk=%d and a multiple of 8",
+                 (long long)v.Tkp, Tk);
+  // head_dim 128 (every video-stream attention): two-stream ping-pong kernel (attention_pair_sm100.cu).
+  // LTX2_ATTN_KERNEL=single keeps the one-tile kernel below for A/B measurements.
+  const char* env_kernel = getenv("LTX2_ATTN_KERNEL");
+  const bool use_pair = !(env_kernel && strcmp(env_kernel, "single") == 0);
+  if (Dh == 128 && use_pair)
+    return attention_pair_bf16(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, stream, trace, sc);
+  if (v.rows) {
     return Dh == 128 ? launch_attention<128, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream)
                      : launch_attention<64, true>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream);
   }
-  LTX2_REQUIRE(v.Tkp >= Tk && v.Tkp % 8 == 0, "attention: V^T pitch %lld must be >= Tk=%d and a multiple of 8",
-               (long long)v.Tkp, Tk);
   return Dh == 128 ? launch_attention<128, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream)
                    : launch_attention<64, false>(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, trace, sc, stream);
 }

@@ -64,6 +64,12 @@ int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, in
                      float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
                      long long* trace = nullptr, const AttnOutScatter* scatter = nullptr);
 
+// head_dim 128 only: two softmax streams per CTA (attention_pair_sm100.cu); attention_bf16_v dispatches to it.
+// trace (diagnostics): CTA 0 writes clock64 stamps to trace[16 * key_blocks].
+int attention_pair_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
+                        float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
+                        const AttnOutScatter& sc);
+
 // Self-attention head preparation in ONE pass over a token row of the fused QKV projection (pitch ld):
 //   q,k: RMSNorm over the full row (learned weight) + split RoPE;  v: copy (skipped when dst.v[0] == null);
 // each head h is written to dst.{q,k,v}[h / heads_per_rank] at [(b*heads_per_rank + h % heads_per_rank) * n_total +

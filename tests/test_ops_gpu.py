@@ -113,6 +113,46 @@ def test_attention(B, H, Tq, Tk, Dh):
     assert float((lse - ref_lse).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize("pairs", ["-1", "0", "1"])
+@pytest.mark.parametrize("B,H,Tq,Tk", [(1, 2, 256, 384), (2, 3, 200, 333), (1, 2, 640, 128), (1, 3, 384, 1000),
+                                       (1, 2, 130, 65)])
+def test_attention_two_stream_modes(monkeypatch, pairs, B, H, Tq, Tk):
+    """head_dim 128: force the pair (two query tiles share K/V) and split-KV (one tile, merged halves) work items on
+    shapes small enough that the scheduler would not pick them: ragged tails, odd tile counts, a single key block."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_ATTN_PAIRS", pairs)
+    Dh = 128
+    q = rnd(B, H, Tq, Dh, seed=27, std=2.0, dtype=torch.bfloat16)
+    k = rnd(B, H, Tk, Dh, seed=28, std=2.0, dtype=torch.bfloat16)
+    qkv = rnd(B, Tk, 3 * H * Dh, seed=29, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * H * Dh:]
+    gate = rnd(B * Tq, H, seed=26)
+    out = ops.attention_vrows(q, k, v_rows, H, Dh, gate_logits=gate)
+    v = v_rows.reshape(B, Tk, H, Dh).permute(0, 2, 1, 3)
+    ref, ref_lse = _attn_ref(q, k, v, gate)
+    assert rel_err(out.float(), ref) < 1.5e-2
+    Tp = (Tk + 63) // 64 * 64
+    vt = torch.zeros(B, H, Dh, Tp, device=dev(), dtype=torch.bfloat16)
+    vt[..., :Tk] = v.transpose(-1, -2)
+    out2, lse = ops.attention(q, k, vt.contiguous(), Tk, want_lse=True)
+    ref2, _ = _attn_ref(q, k, v)
+    assert rel_err(out2.float(), ref2) < 1.5e-2
+    assert float((lse - ref_lse).abs().max()) < 2e-3
+
+
+def test_attention_single_tile_kernel_still_matches(monkeypatch):
+    """LTX2_ATTN_KERNEL=single keeps the one-tile kernel (the head_dim 64 path) reachable at head_dim 128 for A/B runs."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_ATTN_KERNEL", "single")
+    B, H, Tq, Tk, Dh = 1, 2, 300, 500, 128
+    q, k = rnd(B, H, Tq, Dh, seed=20, dtype=torch.bfloat16), rnd(B, H, Tk, Dh, seed=21, dtype=torch.bfloat16)
+    qkv = rnd(B, Tk, 3 * H * Dh, seed=22, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * H * Dh:]
+    out = ops.attention_vrows(q, k, v_rows, H, Dh)
+    ref, _ = _attn_ref(q, k, v_rows.reshape(B, Tk, H, Dh).permute(0, 2, 1, 3))
+    assert rel_err(out.float(), ref) < 1.2e-2
+
+
 def test_attention_sharp_softmax_and_gate():
     from ltx2_b200 import ops
     B, H, Tq, Tk, Dh = 1, 2, 256, 300, 128

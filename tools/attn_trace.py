@@ -8,6 +8,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
+os.environ["LTX2_ATTN_KERNEL"] = "single"   # this tool reads the single-tile kernel's trace layout; see attn_bench.py
+
 from ltx2_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
 
 B, H, T, Dh = 1, 32, 3456, 128
