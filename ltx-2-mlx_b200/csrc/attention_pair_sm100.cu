@@ -26,6 +26,8 @@
 // itself: S_j complete implies P_{j-1}*V retired (same commit group), so O is quiescent during softmax j.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,7 +39,8 @@ constexpr int kPairThreads = 384;
 constexpr int kPairStages = 5;
 constexpr int DHP = 128;                    // head dim
 constexpr int BQP = 128;                    // queries per stream
-constexpr int BKP = 128;                    // keys per block
+constexpr int BKP = 128;                    // keys per K/V tile
+constexpr int SUB = 64;                     // keys per softmax sub-block (half a tile)
 constexpr int kTileBytes = 128 * 128 * 2;   // one Q / K / V tile
 constexpr int kPairSmem = 1024 + 2 * kTileBytes + kPairStages * kTileBytes + 256;
 constexpr int kTraceStride = 16;
@@ -58,6 +61,215 @@ struct PairGrid {
   int BH;
 };
 
+// Everything the TMA producer and the MMA issuer need to walk the tile schedule.
+struct PipeCtx {
+  const CUtensorMap* tmap_q;
+  const CUtensorMap* tmap_k;
+  const CUtensorMap* tmap_v;
+  uint8_t* sQ;
+  uint8_t* sRing;
+  uint64_t* q_full;
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* s_full;
+  uint64_t* p_full;
+  uint64_t* o_done;
+  uint32_t tmem_base;
+  int nsub0, nsub1, kv1, qa, bh, H;
+  long long* trace;   // null unless this CTA is traced
+};
+
+// mbarrier wait without the printf watchdog of common.cuh (keeps the issuing warps' loops lean); still traps on a hang
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 22)) __trap();
+}
+
+// The tile schedule, walked with identical control flow by the TMA producer (ROLE 0) and by the two MMA issuers
+// (ROLE 1: stream 0, ROLE 2: stream 1 -- one issuing warp per stream, because the scalar work around a group of
+// tcgen05.mma (barrier waits, descriptors, commits) costs about as many cycles as the MMAs themselves).
+// Keys are processed in sub-blocks of 64 (half a K/V tile).  Per tile step t, in the fixed order
+// (stream 0, half a), (1, a), (0, b), (1, b):   O_i += P_i(2t+h) * V_t[half h];   S_i(2t+2+h) = Q_i K_{t+1}[half h]^T
+// into the S buffer the softmax just drained.  A tile is fetched at its first use and released after its last.
+// PAIR: both streams use the same K/V tiles (each MMA warp waits for a tile at its own first use and commits to the
+// tile's `empty` barrier, which then counts two arrivals); otherwise every stream has its own tiles and an MMA warp
+// only steps over the ring slots of the other stream.  Everything is compile-time per (stream, half) so that the
+// tcgen05.mma operands stay in uniform registers.
+template <bool VROWS, bool PAIR, int ROLE>
+__device__ __forceinline__ void walk_schedule(const PipeCtx& c) {
+  constexpr bool PRODUCER = ROLE == 0;
+  constexpr int ME = ROLE - 1;
+  const bool leader = elect_one();
+  if (PRODUCER && leader) {
+    mbar_expect_tx(c.q_full, PAIR ? 2 * kTileBytes : kTileBytes);
+#pragma unroll
+    for (int t = 0; t < (PAIR ? 2 : 1); ++t)
+#pragma unroll
+      for (int cc = 0; cc < DHP / 64; ++cc)
+        tma_load_3d(c.sQ + t * kTileBytes + cc * (BQP * 128), c.tmap_q, c.q_full, cc * 64, (c.qa + t) * BQP, c.bh);
+  }
+  constexpr uint32_t idesc_s = umma_idesc_bf16(BQP, SUB);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(BQP, DHP, VROWS);
+  const int nsub0 = c.nsub0, nsub1 = c.nsub1;
+  int slot = 0;
+  uint32_t ph = 0;
+  // tile bookkeeping per owner (owner 0 = stream 0, or the shared tiles in PAIR mode; owner 1 = stream 1)
+  int k_t0 = -1, k_t1 = -1, v_t0 = -1, v_t1 = -1;
+  int k_slot0 = 0, k_slot1 = 0, v_slot0 = 0, v_slot1 = 0;
+
+  // next ring slot: the producer fills it with K (is_v = false) or V tile `tile`; an MMA warp waits for it
+  auto acquire = [&](bool is_v, int tile) -> int {
+    const int s = slot;
+    if (PRODUCER) {
+      mbar_wait_lean(&c.empty[s], ph ^ 1);
+      if (leader) {
+        uint8_t* dst = c.sRing + s * kTileBytes;
+        mbar_expect_tx(&c.full[s], kTileBytes);
+        if (!is_v) {
+#pragma unroll
+          for (int cc = 0; cc < DHP / 64; ++cc)
+            tma_load_3d(dst + cc * (BKP * 128), c.tmap_k, &c.full[s], cc * 64, tile * BKP, c.bh);
+        } else if (VROWS) {   // V rows [keys, d]: one 128-key x 64-channel box per 64 channels (MN-major B operand)
+#pragma unroll
+          for (int cc = 0; cc < DHP / 64; ++cc)
+            tma_load_4d(dst + cc * (BKP * 128), c.tmap_v, &c.full[s], cc * 64, tile * BKP, c.bh % c.H, c.bh / c.H);
+        } else {              // V^T [d, keys]: one DH x 64-key box per 64 keys (K-major B operand)
+#pragma unroll
+          for (int cc = 0; cc < BKP / 64; ++cc)
+            tma_load_3d(dst + cc * (DHP * 128), c.tmap_v, &c.full[s], tile * BKP + cc * 64, 0, c.bh);
+        }
+      }
+    } else {
+      mbar_wait_lean(&c.full[s], ph);
+      tc_fence_after();
+    }
+    if (++slot == kPairStages) { slot = 0; ph ^= 1; }
+    return s;
+  };
+  auto skip = [&]() -> int {   // a ring slot that belongs to the other stream's MMA warp
+    const int s = slot;
+    if (++slot == kPairStages) { slot = 0; ph ^= 1; }
+    return s;
+  };
+  auto release = [&](int s) {
+    if (!PRODUCER && leader) umma_commit(&c.empty[s]);
+  };
+  // S_i[half h] = Q_i K[64h .. 64h+63]^T  (M 128, N 64, K 128) into S buffer h of stream i
+  auto issue_s = [&](auto I_, auto H_, int k_slot) {
+    constexpr int i = decltype(I_)::value, h = decltype(H_)::value;
+    const uint64_t qd = umma_desc_k_sw128(smem_u32(c.sQ + ((PAIR && i) ? kTileBytes : 0)));
+    const uint64_t kd = umma_desc_k_sw128(smem_u32(c.sRing + k_slot * kTileBytes) + h * (SUB * 128));
+    if (leader) {
+#pragma unroll
+      for (int ks = 0; ks < DHP / 16; ++ks) {
+        const uint64_t off = ((ks / 4) * (128 * 128) >> 4) + 2 * (ks % 4);
+        umma_bf16_ss(c.tmem_base + i * BKP + h * SUB, qd + off, kd + off, idesc_s, ks != 0);
+      }
+    }
+  };
+  // O_i += P_i[half h] V[64h .. 64h+63]  (M 128, N 128, K 64); P sits in the first 32 columns of S buffer h
+  auto issue_pv = [&](auto I_, auto H_, int v_slot, bool acc) {
+    constexpr int i = decltype(I_)::value, h = decltype(H_)::value;
+    const uint32_t v_addr = smem_u32(c.sRing + v_slot * kTileBytes);
+    const uint64_t vd = VROWS ? umma_desc_mn_sw128(v_addr, BKP * 128, 1024) : umma_desc_k_sw128(v_addr);
+    if (leader) {
+#pragma unroll
+      for (int ks = 0; ks < SUB / 16; ++ks) {
+        constexpr int kk0 = h * (SUB / 16);
+        const int kk = kk0 + ks;
+        umma_bf16_ts(c.tmem_base + 256 + i * DHP, c.tmem_base + i * BKP + h * SUB + ks * 8,
+                     vd + (VROWS ? kk * (2048 >> 4) : ((kk / 4) * (DHP * 128) >> 4) + 2 * (kk % 4)), idesc_o,
+                     acc || ks != 0);
+      }
+    }
+  };
+  auto has = [&](int i, int k) { return k < (i == 0 ? nsub0 : nsub1); };
+  using I0 = std::integral_constant<int, 0>;
+  using I1 = std::integral_constant<int, 1>;
+
+  if (!PRODUCER) {
+    mbar_wait_lean(c.q_full, 0);
+    tc_fence_after();
+  }
+  // ---- prologue: the S of tile 0 ----
+  auto pro = [&](auto I_, auto H_) {
+    constexpr int i = decltype(I_)::value, h = decltype(H_)::value;
+    constexpr bool mine = PRODUCER || i == ME;
+    if (PAIR && !mine) return;                             // shared tiles: I fetch them at my own first use
+    constexpr bool own1 = !PAIR && i == 1;                 // which owner's tile this stream reads
+    if (!has(i, h)) return;
+    int& k_t = own1 ? k_t1 : k_t0;
+    int& k_slot = own1 ? k_slot1 : k_slot0;
+    if (k_t != 0) {
+      k_slot = mine ? acquire(false, own1 ? c.kv1 : 0) : skip();
+      k_t = 0;
+    }
+    if (PRODUCER || !mine) return;
+    issue_s(I_, H_, k_slot);
+    if (leader) umma_commit(&c.s_full[i * 2 + h]);
+    if (h == 1 || !has(i, 1)) release(k_slot);
+  };
+  pro(I0{}, I0{});
+  pro(I1{}, I0{});
+  pro(I0{}, I1{});
+  pro(I1{}, I1{});
+  __syncwarp();
+  // ---- main loop over tile steps ----
+  const int nt = (nsub0 + 1) >> 1;                         // stream 0 never has fewer sub-blocks than stream 1
+  for (int t = 0; t < nt; ++t) {
+    auto step = [&](auto I_, auto H_) {
+      constexpr int i = decltype(I_)::value, h = decltype(H_)::value;
+      constexpr bool mine = PRODUCER || i == ME;
+      if (PAIR && !mine) return;
+      constexpr bool own1 = !PAIR && i == 1;
+      const int k = 2 * t + h;
+      if (!has(i, k)) return;
+      int& k_t = own1 ? k_t1 : k_t0;
+      int& k_slot = own1 ? k_slot1 : k_slot0;
+      int& v_t = own1 ? v_t1 : v_t0;
+      int& v_slot = own1 ? v_slot1 : v_slot0;
+      const int tile0 = own1 ? c.kv1 : 0;
+      if (!PRODUCER && mine) {
+        mbar_wait_lean(&c.p_full[i * 2 + h], t & 1);
+        tc_fence_after();
+        if (c.trace && leader && h == 0) c.trace[t * kTraceStride + 2 * i] = clock64();
+      }
+      if (v_t != t) {
+        v_slot = mine ? acquire(true, tile0 + t) : skip();
+        v_t = t;
+      }
+      if (!PRODUCER && mine) {
+        issue_pv(I_, H_, v_slot, k > 0);
+        if (h == 1 || !has(i, 2 * t + 1)) release(v_slot);
+      }
+      if (has(i, k + 2)) {
+        if (k_t != t + 1) {
+          k_slot = mine ? acquire(false, tile0 + t + 1) : skip();
+          k_t = t + 1;
+        }
+        if (!PRODUCER && mine) {
+          issue_s(I_, H_, k_slot);
+          if (h == 1 || !has(i, 2 * t + 3)) release(k_slot);
+        }
+      }
+      if (!PRODUCER && mine) {
+        if (leader) {
+          // also signalled when no further S goes into this buffer: "P_i(k)*V retired" is what a rescale waits for
+          umma_commit(&c.s_full[i * 2 + h]);
+          if (k == (i == 0 ? nsub0 : nsub1) - 1) umma_commit(&c.o_done[i]);
+          if (c.trace && h == 0) c.trace[t * kTraceStride + 2 * i + 1] = clock64();
+        }
+        __syncwarp();
+      }
+    };
+    step(I0{}, I0{});
+    step(I1{}, I0{});
+    step(I0{}, I1{});
+    step(I1{}, I1{});
+  }
+}
+
 template <bool VROWS, int POLY>
 __global__ void __launch_bounds__(kPairThreads, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -72,9 +284,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* q_full = bars;                              // 1
   uint64_t* full = bars + 1;                            // stages   TMA -> MMA
   uint64_t* empty = full + kPairStages;                 // stages   MMA -> TMA
-  uint64_t* s_full = empty + kPairStages;               // 2        MMA -> softmax i: S_j in TMEM
-  uint64_t* p_full = s_full + 2;                        // 2        softmax i -> MMA: P_j in TMEM (O rescaled if needed)
-  uint64_t* o_done = p_full + 2;                        // 2        MMA -> softmax i: last P*V retired
+  uint64_t* s_full = empty + kPairStages;               // [stream][half]  MMA -> softmax: S sub-block in TMEM buffer `half`
+  uint64_t* p_full = s_full + 4;                        // [stream][half]  softmax -> MMA: P sub-block in TMEM (O rescaled)
+  uint64_t* o_done = p_full + 4;                        // [stream]        MMA -> softmax: last P*V retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform role
@@ -102,6 +314,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int n0 = pair ? nkv : (nkv + 1) / 2;            // key blocks of stream 0
   const int n1 = pair ? nkv : nkv - n0;                 // key blocks of stream 1 (may be 0 in split mode)
   const int kv1 = pair ? 0 : n0;                        // first key block of stream 1
+  const int keys0 = pair ? Tk : min(n0 * BKP, Tk);      // keys of stream 0 / 1, processed in sub-blocks of 64
+  const int keys1 = pair ? Tk : Tk - n0 * BKP;
+  const int nsub0 = (keys0 + SUB - 1) / SUB;
+  const int nsub1 = keys1 > 0 ? (keys1 + SUB - 1) / SUB : 0;
   const bool tr = trace != nullptr && blockIdx.x == 0;
 
   if (warp == 8 && lane == 0) {
@@ -111,13 +327,14 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_init(q_full, 1);
     for (int i = 0; i < kPairStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], pair ? 2 : 1);               // pair items: both MMA warps release a shared tile
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
-      mbar_init(&o_done[i], 1);
     }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -130,225 +347,82 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-  // third warpgroup: one setmaxnreg for all four warps, then the roles
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-  if (warp == 8) {
-    // ===================== TMA producer =====================
-    const bool leader = elect_one();
-    if (leader) {
-      mbar_expect_tx(q_full, pair ? 2 * kTileBytes : kTileBytes);
-      for (int t = 0; t < (pair ? 2 : 1); ++t)
-#pragma unroll
-        for (int i = 0; i < DHP / 64; ++i)
-          tma_load_3d(sQ + t * kTileBytes + i * (BQP * 128), &tmap_q, q_full, i * 64, (qa + t) * BQP, bh);
-    }
-    int slot = 0;
-    uint32_t ph = 0;
-    auto load_k = [&](int blk) {
-      mbar_wait(&empty[slot], ph ^ 1);
-      if (leader) {
-        uint8_t* dst = sRing + slot * kTileBytes;
-        mbar_expect_tx(&full[slot], kTileBytes);
-#pragma unroll
-        for (int i = 0; i < DHP / 64; ++i) tma_load_3d(dst + i * (BKP * 128), &tmap_k, &full[slot], i * 64, blk * BKP, bh);
-      }
-      if (++slot == kPairStages) { slot = 0; ph ^= 1; }
-    };
-    auto load_v = [&](int blk) {
-      mbar_wait(&empty[slot], ph ^ 1);
-      if (leader) {
-        uint8_t* dst = sRing + slot * kTileBytes;
-        mbar_expect_tx(&full[slot], kTileBytes);
-        if (VROWS) {   // V rows [keys, d]: one 128-key x 64-channel box per 64 channels (MN-major B operand)
-#pragma unroll
-          for (int i = 0; i < DHP / 64; ++i)
-            tma_load_4d(dst + i * (BKP * 128), &tmap_v, &full[slot], i * 64, blk * BKP, bh % H, bh / H);
-        } else {       // V^T [d, keys]: one DH x 64-key box per 64 keys (K-major B operand)
-#pragma unroll
-          for (int i = 0; i < BKP / 64; ++i)
-            tma_load_3d(dst + i * (DHP * 128), &tmap_v, &full[slot], blk * BKP + i * 64, 0, bh);
-        }
-      }
-      if (++slot == kPairStages) { slot = 0; ph ^= 1; }
-    };
-    // tile order = the order the MMA warp consumes them (see below)
-    load_k(0);
-    if (!pair && n1 > 0) load_k(kv1);
-    for (int j = 0; j < n0; ++j) {
-      load_v(j);
-      if (j + 1 < n0) load_k(j + 1);
-      if (!pair) {
-        if (j < n1) load_v(kv1 + j);
-        if (j + 1 < n1) load_k(kv1 + j + 1);
+    if (warp < 11) {
+      // ============ TMA producer (warp 8), MMA issuers (warp 9: stream 0, warp 10: stream 1) ============
+      PipeCtx c;
+      c.tmap_q = &tmap_q; c.tmap_k = &tmap_k; c.tmap_v = &tmap_v;
+      c.sQ = sQ; c.sRing = sRing;
+      c.q_full = q_full; c.full = full; c.empty = empty; c.s_full = s_full; c.p_full = p_full; c.o_done = o_done;
+      c.tmem_base = tmem_base;
+      c.nsub0 = nsub0; c.nsub1 = nsub1; c.kv1 = kv1; c.qa = qa; c.bh = bh; c.H = H;
+      c.trace = tr ? trace : nullptr;
+      if (warp == 8) {
+        if (pair) walk_schedule<VROWS, true, 0>(c);
+        else walk_schedule<VROWS, false, 0>(c);
+      } else if (warp == 9) {
+        if (pair) walk_schedule<VROWS, true, 1>(c);
+        else walk_schedule<VROWS, false, 1>(c);
+      } else {
+        if (pair) walk_schedule<VROWS, true, 2>(c);
+        else walk_schedule<VROWS, false, 2>(c);
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(BQP, BKP);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(BQP, DHP, VROWS);
-    int slot = 0;
-    uint32_t ph = 0;
-    int cur_slot = 0;
-    uint32_t cur_addr = 0;
-    auto acquire = [&]() {
-      mbar_wait(&full[slot], ph);
-      tc_fence_after();
-      cur_slot = slot;
-      cur_addr = smem_u32(sRing + slot * kTileBytes);
-      if (++slot == kPairStages) { slot = 0; ph ^= 1; }
-    };
-    auto release = [&](int s) {
-      if (leader) umma_commit(&empty[s]);
-    };
-    auto issue_s = [&](int i, uint32_t k_addr) {
-      const uint64_t qd = umma_desc_k_sw128(smem_u32(sQ + ((pair && i) ? kTileBytes : 0)));
-      const uint64_t kd = umma_desc_k_sw128(k_addr);
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < DHP / 16; ++ks) {
-          const uint64_t off = ((ks / 4) * (128 * 128) >> 4) + 2 * (ks % 4);
-          umma_bf16_ss(tmem_base + i * BKP, qd + off, kd + off, idesc_s, ks != 0);
-        }
-        umma_commit(&s_full[i]);
-      }
-    };
-    auto issue_pv = [&](int i, uint32_t v_addr, bool acc) {
-      const uint64_t vd = VROWS ? umma_desc_mn_sw128(v_addr, BKP * 128, 1024) : umma_desc_k_sw128(v_addr);
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < BKP / 16; ++ks)
-          umma_bf16_ts(tmem_base + 256 + i * DHP, tmem_base + i * BKP + ks * 8,
-                       vd + (VROWS ? ks * (2048 >> 4) : ((ks / 4) * (DHP * 128) >> 4) + 2 * (ks % 4)), idesc_o,
-                       acc || ks != 0);
-      }
-    };
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    acquire();
-    issue_s(0, cur_addr);
-    if (pair) {
-      issue_s(1, cur_addr);
-      release(cur_slot);
-    } else {
-      release(cur_slot);
-      if (n1 > 0) {
-        acquire();
-        issue_s(1, cur_addr);
-        release(cur_slot);
-      }
-    }
-    __syncwarp();
-    for (int j = 0; j < n0; ++j) {
-      int v_slot, k_slot = 0;
-      uint32_t v_addr, k_addr = 0;
-      // ---- stream 0: O0 += P0_j V_j, then S0_{j+1} ----
-      mbar_wait(&p_full[0], j & 1);
-      tc_fence_after();
-      if (tr && leader) trace[j * kTraceStride + 0] = clock64();
-      acquire();
-      v_slot = cur_slot;
-      v_addr = cur_addr;
-      issue_pv(0, v_addr, j > 0);
-      if (!pair) release(v_slot);
-      if (j + 1 < n0) {
-        acquire();
-        k_slot = cur_slot;
-        k_addr = cur_addr;
-        issue_s(0, k_addr);
-        if (!pair) release(k_slot);
-      } else if (leader) {
-        umma_commit(&o_done[0]);
-      }
-      if (tr && leader) trace[j * kTraceStride + 1] = clock64();
-      __syncwarp();
-      // ---- stream 1 ----
-      if (j < n1) {
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        if (tr && leader) trace[j * kTraceStride + 2] = clock64();
-        if (!pair) {
-          acquire();
-          v_slot = cur_slot;
-          v_addr = cur_addr;
-        }
-        issue_pv(1, v_addr, j > 0);
-        release(v_slot);
-        if (j + 1 < n1) {
-          if (!pair) {
-            acquire();
-            k_slot = cur_slot;
-            k_addr = cur_addr;
-          }
-          issue_s(1, k_addr);
-          release(k_slot);
-        } else if (leader) {
-          umma_commit(&o_done[1]);
-        }
-        if (tr && leader) trace[j * kTraceStride + 3] = clock64();
-        __syncwarp();
-      }
-    }
-  }
   } else {
     // ===================== softmax + output (warps 0..7) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int i = warp >> 2;                            // stream
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;                  // query row inside the tile
     const int qtile = pair ? qa + i : qa;
     const int row = qtile * BQP + r;
-    const int nblk = i == 0 ? n0 : n1;
-    const int kvb = i == 0 ? 0 : kv1;
+    const int nsub = i == 0 ? nsub0 : nsub1;
+    const int keys = i == 0 ? keys0 : keys1;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = t_lane + i * BKP;
     const uint32_t t_o = t_lane + 256 + i * DHP;
     const bool trs = tr && lane == 0 && quarter == 0;   // warps 0 and 4
-    const int tro = 4 + 4 * i;
     float m_run = -INFINITY;                            // true running row maximum (raw scores)
     float m_used = -INFINITY;                           // maximum the current scale of P, l and O refers to
     float l = 0.f;
 
-    for (int j = 0; j < nblk; ++j) {
-      const int kv_valid = Tk - (kvb + j) * BKP;
-      mbar_wait(&s_full[i], j & 1);
-      if (trs) trace[j * kTraceStride + tro + 0] = clock64();
+    for (int k = 0; k < nsub; ++k) {
+      const int h = k & 1, t = k >> 1;
+      const int kv_valid = keys - k * SUB;
+      const int tro = i == 0 ? 4 + 4 * h : 12;
+      const bool trk = trs && (i == 0 || h == 0);
+      mbar_wait(&s_full[i * 2 + h], t & 1);
+      if (trk) trace[t * kTraceStride + tro + 0] = clock64();
       tc_fence_after();
-      uint32_t s[BKP];
+      uint32_t s[SUB];
       {
         uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
         uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-        uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
-        uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
-        tmem_ld_32x32(t_s + 0, s0);
-        tmem_ld_32x32(t_s + 32, s1);
-        tmem_ld_32x32(t_s + 64, s2);
-        tmem_ld_32x32(t_s + 96, s3);
+        tmem_ld_32x32(t_s + h * SUB + 0, s0);
+        tmem_ld_32x32(t_s + h * SUB + 32, s1);
         tmem_ld_wait();
       }
-      if (trs) trace[j * kTraceStride + tro + 1] = clock64();
+      if (trk) trace[t * kTraceStride + tro + 1] = clock64();
       if (POLY == 8) {   // diagnostics: no softmax arithmetic -> the tensor-pipe + hand-off floor of this structure
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = s[e] & 0x3f803f80u;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_st_32x16(t_s + c * 16, pk);
+        for (int c = 0; c < 2; ++c) tmem_st_32x16(t_s + h * SUB + c * 16, pk);
         l = 1.f;
         m_used = 0.f;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[i]);
+        mbar_arrive(&p_full[i * 2 + h]);
         continue;
       }
-      if (kv_valid < BKP) {
+      if (kv_valid < SUB) {
 #pragma unroll
-        for (int e = 0; e < BKP; ++e)
+        for (int e = 0; e < SUB; ++e)
           if (e >= kv_valid) s[e] = 0xff800000u;        // -inf
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
             mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int e = 4; e < BKP; e += 4) {
+      for (int e = 4; e < SUB; e += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(s[e]));
         mx1 = fmaxf(mx1, __uint_as_float(s[e + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(s[e + 2]));
@@ -357,7 +431,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       m_run = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
       float alpha = 1.f;
       bool need = false;
-      if (j == 0) {
+      if (k == 0) {
         m_used = m_run;
       } else if ((m_run - m_used) * scale_log2 > 8.0f) {
         alpha = ex2_approx((m_used - m_run) * scale_log2);
@@ -365,7 +439,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         need = true;
       }
       if (__any_sync(0xffffffffu, need)) {
-        // O_i is quiescent here (P_{j-1}*V retired before S_j was signalled)
+        // O_i must be quiescent: P(k-1)*V is retired once the OTHER S buffer's next completion (S(k+1), or the
+        // bare commit when no S(k+1) exists) is signalled; P(k)*V cannot start before this thread publishes P(k)
+        mbar_wait(&s_full[i * 2 + (h ^ 1)], ((k + 1) >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int c = 0; c < DHP; c += 32) {
           uint32_t v[32];
@@ -382,7 +459,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const float2 sl2 = make_float2(scale_log2, scale_log2), nmb = make_float2(-mb, -mb);
       float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int ii = 0; ii < 16; ii += 2) {
@@ -408,14 +485,14 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           pk[ii] = pack_bf16x2(a.x, a.y);
           pk[ii + 1] = pack_bf16x2(b2.x, b2.y);
         }
-        tmem_st_32x16(t_s + c * 16, pk);
+        tmem_st_32x16(t_s + h * SUB + c * 16, pk);
       }
       l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
-      if (trs) trace[j * kTraceStride + tro + 2] = clock64();
+      if (trk) trace[t * kTraceStride + tro + 2] = clock64();
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[i]);
-      if (trs) trace[j * kTraceStride + tro + 3] = clock64();
+      mbar_arrive(&p_full[i * 2 + h]);
+      if (trk) trace[t * kTraceStride + tro + 3] = clock64();
     }
 
     // ---- normalise, gate, store ----

@@ -75,19 +75,20 @@ def timeline(T=3456):
     torch.cuda.synchronize()
     t = trace.cpu().reshape(nkv, 16)
     t0 = int(t[0][t[0] > 0].min())
-    names = ["P0 seen", "PV0+S0 iss", "P1 seen", "PV1+S1 iss", "S0 seen", "S0 regs", "exp0 done", "P0 pub",
-             "S1 seen", "S1 regs", "exp1 done", "P1 pub"]
-    print("blk " + " ".join(f"{n:>10s}" for n in names))
+    names = ["P0a seen", "PV0a+S iss", "P1a seen", "PV1a+S iss", "S0a seen", "S0a regs", "exp0a done", "P0a pub",
+             "S0b seen", "S0b regs", "exp0b done", "P0b pub", "S1a seen", "S1a regs", "exp1a done", "P1a pub"]
+    print("tile " + " ".join(f"{n:>10s}" for n in names))
     for j in range(min(nkv, 10)):
-        print(f"{j:3d} " + " ".join(f"{int(x) - t0:10d}" for x in t[j][:12]))
-    d = (t[3:, 7] - t[2:-1, 7]).float()
-    print("period of stream 0 (P0 published -> next):", d.mean().item(), "cycles  (tensor floor 2048)")
-    print("softmax 0: S seen->regs", (t[2:, 5] - t[2:, 4]).float().mean().item(), " regs->exp done",
-          (t[2:, 6] - t[2:, 5]).float().mean().item(), " exp done->published", (t[2:, 7] - t[2:, 6]).float().mean().item(),
-          " published->next S seen", (t[3:, 4] - t[2:-1, 7]).float().mean().item())
-    print("MMA: P0 seen->issued", (t[2:, 1] - t[2:, 0]).float().mean().item(), " issued->P1 seen",
-          (t[2:, 2] - t[2:, 1]).float().mean().item(), " P1 seen->issued", (t[2:, 3] - t[2:, 2]).float().mean().item(),
-          " issued->next P0 seen", (t[3:, 0] - t[2:-1, 3]).float().mean().item())
+        print(f"{j:4d} " + " ".join(f"{int(x) - t0:10d}" for x in t[j][:16]))
+    d = (t[3:-1, 7] - t[2:-2, 7]).float()
+    print("period of stream 0 per 128-key tile (P0a published -> next):", d.mean().item(), "cycles  (tensor floor 2048)")
+    print("softmax 0, half a: S seen->regs", (t[2:-1, 5] - t[2:-1, 4]).float().mean().item(), " regs->exp done",
+          (t[2:-1, 6] - t[2:-1, 5]).float().mean().item(), " exp done->published",
+          (t[2:-1, 7] - t[2:-1, 6]).float().mean().item(), " published->S0b seen",
+          (t[2:-1, 8] - t[2:-1, 7]).float().mean().item(), " P0b published->next S0a seen",
+          (t[3:-1, 4] - t[2:-2, 11]).float().mean().item())
+    print("MMA: P0a seen->issued", (t[2:-1, 1] - t[2:-1, 0]).float().mean().item(), " issued->P1a seen",
+          (t[2:-1, 2] - t[2:-1, 1]).float().mean().item(), " P1a seen->issued", (t[2:-1, 3] - t[2:-1, 2]).float().mean().item())
     setenv()
 
 

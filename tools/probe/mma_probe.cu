@@ -39,10 +39,21 @@ __global__ void __launch_bounds__(128, 1) mma_probe(long long* cyc, int n_groups
             if (MODE == 1) umma_bf16_ts(tm + (g & 1) * 128, tm + 256 + ks * 8, bd + off, id128, ks != 0);
             if (MODE == 2) umma_bf16_ts(tm + (g & 1) * 128, tm + 256 + ks * 8, bmn + ks * (2048 >> 4), id128mn, ks != 0);
             if (MODE == 3) umma_bf16_ss(tm + (g & 1) * 256, ad + off, bd + off, id256, ks != 0);
+            if (MODE == 5) umma_bf16_ss(tm + (g & 3) * 64, ad + off, bd + off, umma_idesc_bf16(128, 64), ks != 0);
+            if (MODE == 6) {   // sub-block step: P*V with K = 64 (4 TS MMAs, N = 128), then S with N = 64 (8 SS MMAs)
+              if (ks < 4) umma_bf16_ts(tm + 256 + (g & 1) * 128, tm + (g & 3) * 64 + ks * 8, bmn + ks * (2048 >> 4), id128mn, 1);
+            }
             if (MODE == 4) {
               if (g & 1) umma_bf16_ts(tm + 256 + (g & 2) * 64, tm + (g & 2) * 64 + ks * 8, bmn + ks * (2048 >> 4), id128mn, 1);
               else umma_bf16_ss(tm + (g & 2) * 64, ad + off, bd + off, id128, ks != 0);
             }
+          }
+        }
+        if (MODE == 6 && leader) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t off = ((ks / 4) * (128 * 128) >> 4) + 2 * (ks % 4);
+            umma_bf16_ss(tm + (g & 3) * 64, ad + off, bd + off + (8192 >> 4), umma_idesc_bf16(128, 64), ks != 0);
           }
         }
         __syncwarp();
@@ -81,6 +92,8 @@ int main() {
     run<2>("TS  A tmem, B MN-major smem, N=128", sms);
     run<3>("SS  N=256", sms);
     run<4>("alternating SS (QK^T) / TS MN-major (PV)", sms);
+    run<5>("SS  N=64", sms);
+    run<6>("sub-block step: 4x TS N=128 + 8x SS N=64", sms);
   }
   return 0;
 }
