@@ -1,29 +1,32 @@
-// Flash-style attention on tcgen05 tensor cores, head_dim 128, TWO softmax streams per CTA (ping-pong):
+// Flash-style attention on tcgen05 tensor cores, head_dim 128, TWO softmax streams per CTA:
 //   O = softmax(Q K^T / sqrt(d)) V, non-causal, no mask.
 //
 // Reference op replaced: mx.fast.scaled_dot_product_attention as called from
 // _compiled_attention_core_no_mask (attention.py:12-34), plus the head merge
 // (B,H,T,D)->(B,T,H*D) (:34) and the V2 per-head gate 2*sigmoid(logits) (:243-250).
 //
-// Why two streams: with one 128-query tile per CTA every 128x128 key block needs its own 64 KB of K/V from L2
-// (64 B/clk/SM at tensor-pipe speed -- beyond what the L2 delivers to 148 SMs) and the softmax of block j sits on
-// the critical path between S_j and P_j*V_j.  Here a CTA owns two streams that share the tensor pipe:
+// Why two streams: with one 128-query tile per CTA every 128x128 key block needs its own 64 KB of K/V from L2 and
+// the softmax of block j sits alone on its SM sub-partition (one warp per scheduler: measured IPC 0.4).  Here a CTA
+// owns two streams that share the tensor pipe and put two independent softmax warps on every scheduler:
 //   pair mode   streams = two adjacent 128-query tiles of one head over ALL keys; every K/V tile fetched from L2 is
 //               used by both (half the L2->SM traffic per FLOP);
 //   split mode  streams = ONE query tile over the first / second half of the keys, merged in the CTA at the end
 //               (used for the odd tile of a head and for small grids such as the context-parallel head shards).
-// While the softmax warpgroup of stream 0 turns S0_j into P0_j, the tensor pipe runs P1_{j-1}*V and S1_j for
-// stream 1, and vice versa, so neither side waits for the other in steady state.
+// Keys are processed in SUB-BLOCKS of 64 (half a K/V tile) and each stream's S region is two 64-column buffers, so
+// S(k+2) is computed while the softmax still works on S(k+1): in steady state a softmax warp never waits for the
+// tensor pipe and the tensor pipe never waits for one particular softmax (tools/attn_bench.py prints the timeline).
 //
-// Warps (384 threads = 3 warpgroups): 0-3 = softmax of stream 0, 4-7 = softmax of stream 1 (one thread per query
-// row: no cross-thread reductions), 8 = TMA producer, 9 = MMA issuer, 10-11 idle.  The third warpgroup hands its
-// registers to the softmax warpgroups (setmaxnreg 72 / 216) so a whole 128-column score row stays in registers.  Tensor memory (512 columns):
-//   [0,128) S0 / P0   [128,256) S1 / P1   [256,384) O0   [384,512) O1
-// P_j (bf16, 64 columns) overwrites the first half of S_j once the row has been pulled into registers; S_{j+1} is
-// issued behind P_j*V_j on the in-order tensor pipe, so the overwrite is safe.  Q lives in shared memory (SS-mode
-// MMA for S), P in tensor memory (TS-mode MMA for P*V).  K/V tiles (32 KB each) flow through one 5-stage ring.
+// Warps (384 threads): 0-3 = softmax of stream 0, 4-7 = softmax of stream 1 (one thread per query row: no
+// cross-thread reductions), 8 = TMA producer, 9 / 10 = MMA issuers of stream 0 / 1 (the scalar work around a group
+// of tcgen05.mma costs about as much as the MMAs, so one issuing warp for both streams was the bottleneck), 11 idle.
+// Tensor memory (512 columns):
+//   [0,64) [64,128) S buffers a, b of stream 0   [128,192) [192,256) the same for stream 1   [256,384) O0   [384,512) O1
+// P(k) (bf16, 32 columns) overwrites the first half of its S buffer once the row has been pulled into registers;
+// S(k+2) is issued behind P(k)*V on the in-order tensor pipe, so the overwrite is safe.  Q lives in shared memory
+// (SS-mode MMA for S: M 128, N 64 -- shared-memory bound at 48 instead of 32 clk per instruction, tools/probe), P in
+// tensor memory (TS-mode MMA for P*V).  K/V tiles (32 KB each) flow through one 5-stage ring.
 // The running output is rescaled lazily (only when the row maximum grew by more than 2^8), by the softmax thread
-// itself: S_j complete implies P_{j-1}*V retired (same commit group), so O is quiescent during softmax j.
+// itself, after waiting for the completion that proves P(k-1)*V has retired.
 #include <stdlib.h>
 
 #include <type_traits>
