@@ -60,9 +60,12 @@ def peaks():
 
 def profiled_traffic(rep_suffix, kernel_substr, skip=0):
     """Mean DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the committed
-    `ncu --set full` summary (profiles/r1b_kernels.json, produced by tools/summarize_profiles.py); None if absent."""
+    `ncu --set full` summary (profiles/r1c_kernels.json, else r1b; produced by tools/summarize_profiles.py); None if
+    absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1b_kernels.json")) as f:
+        path = next(p for p in (os.path.join(ROOT, "profiles", t + "_kernels.json") for t in ("r1c", "r1b"))
+                    if os.path.exists(p))
+        with open(path) as f:
             caps = json.load(f)
         rows = [k for name, ks in caps.items() if rep_suffix in name for k in ks if kernel_substr in k["kernel"]][skip:]
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -314,7 +317,7 @@ def bench_vae(args, dev, rank, world=1):
                      "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
                      "traffic": profiled_traffic("prof_conv", "conv3d_kernel<128>"),
                      "traffic_note": "DRAM bytes of one last-stage conv launch (128->128 ch, 49x128x192) from "
-                                     "profiles/r1b_kernels.json; algorithmic bytes 330 MB in + 308 MB out + 0.9 MB weights",
+                                     "profiles/r1c_kernels.json; algorithmic bytes 330 MB in + 308 MB out + 0.9 MB weights",
                      "launches": int(pl.value), "ms_in_decode": pm.value, "flops_in_decode": pf.value,
                      "decode": {"algorithmic_flops": alg, "achieved": alg / (ms * 1e-3) / 1e12,
                                 "frac": alg / (ms * 1e-3) / 1e12 / pk["tf"]}},
@@ -468,7 +471,7 @@ def run_ours(args, c):
                      "achieved": gemm_tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": gemm_tf / pk["tf"],
                      "traffic": profiled_traffic("prof_gemm", "gemm_bf16_kernel", skip=3),
                      "traffic_note": "mean DRAM bytes per launch over the 5 per-block GEMMs of one block (QKV, attn out, "
-                                     "text q, text kv, text out) from profiles/r1b_kernels.json; algorithmic bytes of "
+                                     "text q, text kv, text out) from profiles/r1c_kernels.json; algorithmic bytes of "
                                      "those launches average 128 MB", "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches": int(pl[0]), "ms_in_step": pm[0], "flops_in_step": pf[0],
                      "attention": {"achieved": attn_tf, "frac": attn_tf / pk["tf"], "launches": int(pl[1]),

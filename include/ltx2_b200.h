@@ -234,9 +234,11 @@ int ltx2_attention_vrows(const void* q, const void* k, const void* v, int64_t v_
                          int64_t v_stride_b, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t Dh,
                          float scale, const float* gate_logits, float* lse_out, void* stream);
 
-/* Diagnostics: ltx2_attention plus a clock64 timeline of CTA (0,0): trace[j*8 + e], e = 0 QK_j issued, 1 P_j seen by
- * the MMA thread, 2 PV_j issued, 3 S_j seen by softmax, 4 S_j in registers, 5 exps done, 6 PV_{j-1} retired,
- * 7 P_j published (tools/attn_trace.py). */
+/* Diagnostics: ltx2_attention plus a clock64 timeline of CTA 0.  head_dim 128 (two-stream kernel): trace must hold
+ * 16*(key tiles + 1) words; trace[t*16 + e] are the events of key tile t (tools/attn_bench.py names them) and the last
+ * 16 words hold the CTA phases (entry, set-up done, key loop done, epilogue done).  With LTX2_ATTN_KERNEL=single or
+ * head_dim 64: trace[j*8 + e], e = 0 QK_j issued, 1 P_j seen by the MMA thread, 2 PV_j issued, 3 S_j seen by softmax,
+ * 4 S_j in registers, 5 exps done, 6 PV_{j-1} retired, 7 P_j published (tools/attn_trace.py). */
 int ltx2_attention_trace(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
                          int32_t Tk, int32_t Tkp, int32_t Dh, float scale, long long* trace, void* stream);
 

@@ -322,6 +322,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int nsub0 = (keys0 + SUB - 1) / SUB;
   const int nsub1 = keys1 > 0 ? (keys1 + SUB - 1) / SUB : 0;
   const bool tr = trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) trace[nkv * kTraceStride + 0] = clock64();           // kernel entry
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -387,6 +388,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     float m_used = -INFINITY;                           // maximum the current scale of P, l and O refers to
     float l = 0.f;
 
+    if (trs && i == 0) trace[nkv * kTraceStride + 1] = clock64();   // set-up done (TMEM, barriers)
     for (int k = 0; k < nsub; ++k) {
       const int h = k & 1, t = k >> 1;
       const int kv_valid = keys - k * SUB;
@@ -498,6 +500,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       if (trk) trace[t * kTraceStride + tro + 3] = clock64();
     }
 
+    if (trs && i == 0) trace[nkv * kTraceStride + 2] = clock64();   // key loop done
     // ---- normalise, gate, store ----
     const int b_idx = bh / H, h_idx = bh % H;
     float g = 1.f;
@@ -588,6 +591,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         lse_out[static_cast<int64_t>(bh) * Tq + row] = m * scale + logf(lt);
     }
     tc_fence_before();
+    if (trs && i == 0) trace[nkv * kTraceStride + 3] = clock64();   // epilogue done
   }
 
   __syncthreads();

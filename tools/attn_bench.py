@@ -68,12 +68,14 @@ def timeline(T=3456):
     vt = torch.randn(1, H, Dh, T, device=dev).to(torch.bfloat16)
     out = torch.empty(1, T, H * Dh, device=dev, dtype=torch.bfloat16)
     nkv = (T + 127) // 128
-    trace = torch.zeros(nkv * 16, device=dev, dtype=torch.int64)
+    trace = torch.zeros(nkv * 16 + 16, device=dev, dtype=torch.int64)
     for _ in range(2):
         check(lib().ltx2_attention_trace(ptr(q), ptr(k), ptr(vt), ptr(out), 1, H, T, T, T, Dh,
                                          C.c_float(1 / math.sqrt(Dh)), ptr(trace), stream_ptr()))
     torch.cuda.synchronize()
-    t = trace.cpu().reshape(nkv, 16)
+    ph = trace.cpu()[nkv * 16:nkv * 16 + 4]
+    t = trace.cpu()[:nkv * 16].reshape(nkv, 16)
+    print('CTA 0 phases (cycles): set-up', int(ph[1] - ph[0]), ' key loop', int(ph[2] - ph[1]), ' epilogue', int(ph[3] - ph[2]))
     t0 = int(t[0][t[0] > 0].min())
     names = ["P0a seen", "PV0a+S iss", "P1a seen", "PV1a+S iss", "S0a seen", "S0a regs", "exp0a done", "P0a pub",
              "S0b seen", "S0b regs", "exp0b done", "P0b pub", "S1a seen", "S1a regs", "exp1a done", "P1a pub"]
