@@ -10,6 +10,8 @@
 //                          two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2-5 epilogue     tcgen05.ld (32 lanes x 32 columns per warp) -> bias/GELU/gate/residual -> global
 // Both operands are K-major (row-major activations, nn.Linear [out,in] weights), so no transposes exist anywhere.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,6 +32,79 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+// Epilogue of one accumulator tile for the calling thread's row: TMEM (lane = row, BN fp32 columns at t_row) ->
+// bias / GELU / gate / residual -> global.  Shared by the 1-CTA and the 2-CTA kernels.
+template <int BN>
+__device__ __forceinline__ void epilogue_row(const GemmEpilogue& ep, uint32_t t_row, int row, bool row_ok, int n0, int N,
+                                             bool first_slice) {
+  int cls = 0;
+  if (ep.row_cls != nullptr && row_ok) cls = ep.row_cls[row];
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c, r);
+    tmem_ld_wait();
+    const int col0 = n0 + c;
+    if (row_ok && col0 < N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.bias != nullptr && first_slice) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+      }
+      if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
+        if (ep.mode == GEMM_EPI_BF16_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+        }
+        uint4 q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+          q[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+          q[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+          q[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        }
+        const int64_t off = static_cast<int64_t>(row) * ep.ldo + col0;
+        if (ep.n_out_peers == 0) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
+        } else {
+          // context parallel: the same tile is stored into every rank's buffer (stores to peer memory over NVLink)
+          for (int pr = 0; pr < ep.n_out_peers; ++pr) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out_peers[pr]) + off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
+          }
+        }
+      } else if (ep.mode == GEMM_EPI_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {  // GEMM_EPI_F32_RESIDUAL: out += alpha * gate[cls, col] * (acc + bias)
+        // the add is performed by the L2 (red.global.add.v4.f32): no read of the residual on the SM, and K slices
+        // of a split-K launch can accumulate into the same rows
+        float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+        const float* g = ep.gate ? ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 gg = g ? __ldg(reinterpret_cast<const float4*>(g + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * gg.x * v[j]),
+                       "f"(ep.alpha * gg.y * v[j + 1]), "f"(ep.alpha * gg.z * v[j + 2]),
+                       "f"(ep.alpha * gg.w * v[j + 3])
+                       : "memory");
+        }
+      }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -150,72 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      int cls = 0;
-      if (ep.row_cls != nullptr && row_ok) cls = ep.row_cls[row];
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row_ok && col0 < N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias != nullptr && first_slice) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
-            if (ep.mode == GEMM_EPI_BF16_GELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-            }
-            uint4 q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              q[j].x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-              q[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              q[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              q[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            }
-            const int64_t off = static_cast<int64_t>(row) * ep.ldo + col0;
-            if (ep.n_out_peers == 0) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + off;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
-            } else {
-              // context parallel: the same tile is stored into every rank's buffer (stores to peer memory over NVLink)
-              for (int pr = 0; pr < ep.n_out_peers; ++pr) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out_peers[pr]) + off;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + 8 * j) = q[j];
-              }
-            }
-          } else if (ep.mode == GEMM_EPI_F32) {
-            float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {  // GEMM_EPI_F32_RESIDUAL: out += alpha * gate[cls, col] * (acc + bias)
-            // the add is performed by the L2 (red.global.add.v4.f32): no read of the residual on the SM, and K slices
-            // of a split-K launch can accumulate into the same rows
-            float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
-            const float* g = ep.gate ? ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 gg = g ? __ldg(reinterpret_cast<const float4*>(g + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * gg.x * v[j]),
-                           "f"(ep.alpha * gg.y * v[j + 1]), "f"(ep.alpha * gg.z * v[j + 2]),
-                           "f"(ep.alpha * gg.w * v[j + 3])
-                           : "memory");
-            }
-          }
-        }
-      }
+      epilogue_row<BN>(ep, t_row, row, row_ok, n0, N, first_slice);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -229,6 +239,336 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile of C^T.  CTA r loads weight
+// rows [128 r, 128 r + 128) of the tile and half of the tile's tokens into ITS shared memory; one thread of CTA 0
+// issues tcgen05.mma.cta_group::2 (M 256 = weight rows, N 256 = tokens), which reads the "A" half and half of "B" from
+// each CTA and accumulates output columns [128 r, ...) of the tile into CTA r's tensor memory.  Per MMA an SM now reads 8 KB of operands instead of 12 KB and
+// receives 32 KB instead of 48 KB per K block from TMA -- shared-memory bandwidth is what held the 1-CTA kernel at
+// ~82 % tensor-pipe activity (profiles/r1c_kernels.json).
+//   warp 0 (both CTAs)  TMA producer for the CTA's halves -> own `full` barriers
+//   warp 1, CTA 1       relay: own `full` complete -> remote arrive on CTA 0's `peer_full`
+//   warp 1, CTA 0       MMA issuer: waits full + peer_full, commits multicast to `empty` / `acc_full` of both CTAs
+//   warps 2-5           epilogue of the CTA's 128 rows; `acc_empty` lives in CTA 0 and counts all 8 epilogue warps
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStages2 = 6;
+constexpr int kHalfBytes = 128 * BK * 2;                       // 16 KB: 128 rows x 64 k
+constexpr int kStageBytes2 = 2 * kHalfBytes;                   // A half + W half
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// relaxed variant for the relay: it only forwards "TMA bytes have landed" (async-proxy writes, made visible by the
+// complete_tx the relay waited for); a release here costs a cluster-scope memory barrier per K block
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.b32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs when all MMAs issued so far have retired
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// Transposed epilogue of the 2-CTA kernel: the accumulator tile is C^T, i.e. TMEM lane = output column (weight row),
+// TMEM column = token.  Thread `lane` of a warp owns one output column; the 32 lanes of a warp store 32 consecutive
+// output columns of one token per instruction (64 B bf16 / 128 B fp32 runs).
+__device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t t_row, int col, int tok0, int ntok, int M) {
+  const float b = ep.bias != nullptr ? __ldg(ep.bias + col) : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < ntok; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c, r);
+    tmem_ld_wait();
+    const int t0 = tok0 + c;
+    if (t0 >= M) break;
+    const int nv = min(32, M - t0);                       // warp-uniform
+    if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = __uint_as_float(r[j]) + b;
+        if (ep.mode == GEMM_EPI_BF16_GELU) v = gelu_tanh_f(v);
+        if (j < nv) o[static_cast<int64_t>(j) * ep.ldo] = __float2bfloat16_rn(v);
+      }
+    } else if (ep.mode == GEMM_EPI_F32) {
+      float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nv) o[static_cast<int64_t>(j) * ep.ldo] = __uint_as_float(r[j]) + b;
+    } else {  // GEMM_EPI_F32_RESIDUAL: out += alpha * gate[cls(token), col] * (acc + bias), added by the L2
+      float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nv) {
+          const int cls = ep.row_cls != nullptr ? __ldg(ep.row_cls + t0 + j) : 0;
+          const float g = ep.gate != nullptr ? __ldg(ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col) : 1.f;
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + static_cast<int64_t>(j) * ep.ldo),
+                       "f"(ep.alpha * g * (__uint_as_float(r[j]) + b))
+                       : "memory");
+        }
+      }
+    }
+  }
+}
+
+// Static tile schedule of the 2-CTA kernel.  Work items are full tiles (256 tokens) and, when the token count leaves at
+// most 128 tokens for the last tile, half tiles (128 tokens, half the time).  Full tiles go round-robin over the clusters
+// (token tile fastest, so a weight slab is reused from L2); the half tiles then go two at a time to the clusters that
+// got one full tile fewer, so that e.g. 16 x 13.5 tiles finish in 3 tile times on 74 SM pairs instead of 4.
+struct PairSched {
+  int nc, c;          // clusters, this cluster
+  int n_full_t;       // full-width token tiles
+  int num_t;          // token tiles incl. a half one
+  int nfull, nhalf;   // work items
+  int my_full;        // full tiles of this cluster
+  int lh0;            // half tiles this cluster takes as a "light" cluster
+  int li;             // its index among the light clusters
+  int n_light_halves;
+};
+__device__ __forceinline__ PairSched make_sched(int M, int N, int nc, int c) {
+  PairSched s;
+  s.nc = nc;
+  s.c = c;
+  s.num_t = (M + 255) / 256;
+  const bool half = (M - (s.num_t - 1) * 256) <= 128;
+  s.n_full_t = half ? s.num_t - 1 : s.num_t;
+  const int num_w = N / 256;
+  s.nfull = s.n_full_t * num_w;
+  s.nhalf = half ? num_w : 0;
+  s.my_full = c < s.nfull ? (s.nfull - c + nc - 1) / nc : 0;
+  const int rem = s.nfull % nc;
+  const int light = rem == 0 ? 0 : nc - rem;
+  s.n_light_halves = min(s.nhalf, 2 * light);
+  s.li = c - rem;
+  s.lh0 = (light > 0 && s.li >= 0) ? max(0, min(2, s.n_light_halves - 2 * s.li)) : 0;
+  return s;
+}
+// i-th work item of this cluster: weight tile wi, token tile ti, nt tokens wide; false when the cluster is done
+__device__ __forceinline__ bool sched_tile(const PairSched& s, int i, int& wi, int& ti, int& nt) {
+  if (i < s.my_full) {
+    const int f = s.c + i * s.nc;
+    wi = f / s.n_full_t;
+    ti = f % s.n_full_t;
+    nt = 256;
+    return true;
+  }
+  const int j = i - s.my_full;
+  const int h = j < s.lh0 ? 2 * s.li + j : s.n_light_halves + s.c + (j - s.lh0) * s.nc;
+  if (h >= s.nhalf) return false;
+  wi = h;
+  ti = s.num_t - 1;
+  nt = 128;
+  return true;
+}
+
+// The pair computes C^T tiles: MMA M = 256 WEIGHT rows (every DiT width is a multiple of 256), MMA N = 256 tokens, or
+// 128 for the last token tile when at most 128 tokens remain -- so a token count that is an odd multiple of 128
+// (3456 = 27 x 128) costs nothing, where 256-token-row tiles would waste half a tile per weight slab.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x128,
+                  const __grid_constant__ CUtensorMap tmap_x64, int M, int N, int K, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                       // [stages][128 weight rows x 64]
+  uint8_t* smem_b = smem + kStages2 * kHalfBytes;               // [stages][128 (or 64) tokens x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
+  uint64_t* full_bar = bars;                         // [stages]  own TMA -> MMA (CTA 0) / relay (CTA 1)
+  uint64_t* peer_full = full_bar + kStages2;         // [stages]  CTA 1 relay -> CTA 0 MMA (used in CTA 0 only)
+  uint64_t* empty_bar = peer_full + kStages2;        // [stages]  MMA (multicast) -> own TMA
+  uint64_t* acc_full = empty_bar + kStages2;         // [2]       MMA (multicast) -> own epilogue
+  uint64_t* acc_empty = acc_full + 2;                // [2]       all 8 epilogue warps -> MMA (used in CTA 0 only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const PairSched sched = make_sched(M, N, num_clusters, cluster_id);
+  const int num_kb = (K + BK - 1) / BK;
+  int wi, ti, nt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x128);
+    tma_prefetch_desc(&tmap_x64);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&peer_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();                                 // both CTAs are running and their barriers exist
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============ TMA producer (both CTAs: this CTA's 128 weight rows and its half of the token tile) ============
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
+      const int w0 = wi * 256 + static_cast<int>(rank) * 128;
+      const int t0 = ti * 256 + static_cast<int>(rank) * (nt / 2);
+      const uint32_t bytes = kHalfBytes + (nt / 2) * BK * 2;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], bytes);
+          tma_load_2d(smem_a + stage * kHalfBytes, &tmap_w, &full_bar[stage], kb * BK, w0);
+          tma_load_2d(smem_b + stage * kHalfBytes, nt == 256 ? &tmap_x128 : &tmap_x64, &full_bar[stage], kb * BK, t0);
+        }
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ===================== relay (CTA 1): my halves have landed -> tell the MMA issuer in CTA 0 =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        if (leader) mbar_arrive_cluster_relaxed(mapa_u32(&peer_full[stage], 0));
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc256 = umma_idesc_bf16(256, 256), idesc128 = umma_idesc_bf16(256, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
+      const uint32_t idesc = nt == 128 ? idesc128 : idesc256;
+      mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_cluster(&peer_full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kHalfBytes));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * kHalfBytes));
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma2_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma2_commit_both(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma2_commit_both(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ============ epilogue (warps 2..5, both CTAs: this CTA's 128 output columns x all tokens of the tile) ============
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
+      const int col = wi * 256 + static_cast<int>(rank) * 128 + quarter * 32 + lane;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+      epilogue_col_t(ep, t_row, col, ti * 256, nt, M);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // nobody leaves while the peer may still touch my barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+int gemm2_tiles(int M, int N) { return ((M + 255) / 256) * (N / 256); }
+
+int launch_gemm2(const CUtensorMap* tw, const CUtensorMap* tx128, const CUtensorMap* tx64, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    configured = true;
+  }
+  const int tiles = gemm2_tiles(M, N);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm2_bf16_kernel<<<grid, kGemmThreads, kSmemBytes2, stream>>>(*tw, *tx128, *tx64, M, N, K, ep);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
 }
 
 template <int BN>
@@ -277,6 +617,23 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
   }
   const CUtensorMap *ta, *tb;
   LTX2_PROPAGATE(get_tensor_map_2d(&ta, A, M, K, lda, BM));
+  // 2-CTA kernel (256 weight rows x 256 tokens per SM pair, C^T tiles): OPT-IN.  Stand-alone it beats the 1-CTA kernel
+  // by 2-5 % on the long launches (QKV, FFN up-projection; tools/gemm_vs_cublas.py) and loses ~3 % at ~3 tiles per pair
+  // (longer prologue, scalar-store epilogue); inside the power-capped denoising step the two measure the same
+  // (90.7 vs 91.2 ms, same box), so the simpler kernel stays the default.
+  //   LTX2_GEMM_2CTA=1  2-CTA kernel for launches with >= 6 tiles per SM pair
+  //   LTX2_GEMM_2CTA=2  2-CTA kernel whenever it fills the machine (tests)
+  const char* env2 = getenv("LTX2_GEMM_2CTA");
+  const bool on2 = env2 && (env2[0] == '1' || env2[0] == '2');
+  const int min_rounds = (env2 && env2[0] == '2') ? 1 : 6;
+  if (bn == 256 && splits == 1 && ep.n_out_peers == 0 && M >= 256 &&
+      gemm2_tiles(M, N) >= min_rounds * (num_sms() / 2) && on2) {
+    const CUtensorMap *tw, *tx128, *tx64;
+    LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
+    LTX2_PROPAGATE(get_tensor_map_2d(&tx128, A, M, K, lda, 128));
+    LTX2_PROPAGATE(get_tensor_map_2d(&tx64, A, M, K, lda, 64));
+    return launch_gemm2(tw, tx128, tx64, M, N, K, ep, stream);
+  }
   LTX2_PROPAGATE(get_tensor_map_2d(&tb, W, N, K, ldw, bn));
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, M, N, K, splits, ep, stream);

@@ -281,6 +281,40 @@ def test_attention_v_in_row_form_from_fused_qkv(B, H, Tq, Tk, Dh):
     assert rel_err(out.float(), ref) < 1.2e-2
 
 
+@pytest.mark.parametrize("M", [3456, 3500, 3328, 2049])
+@pytest.mark.parametrize("mode", ["bf16", "gelu", "f32", "residual"])
+def test_gemm_two_cta_transposed_tiles(monkeypatch, M, mode):
+    """Opt-in kernel (LTX2_GEMM_2CTA): SM pairs (tcgen05 cta_group::2) compute C^T tiles, 256 weight rows x 256 tokens,
+    the last token tile 128 wide when <= 128 tokens remain (3456), zero-filled otherwise (3500); every epilogue mode.
+    The 1-CTA kernel on the same inputs must agree to rounding."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_GEMM_2CTA", "2")          # take the pair kernel as soon as it fills the machine
+    N, K = 2560, 320
+    a, w = rnd(M, K, seed=85, dtype=torch.bfloat16), rnd(N, K, seed=86, std=K ** -0.5, dtype=torch.bfloat16)
+    bias, x = rnd(N, seed=87), rnd(M, N, seed=88)
+    gate = rnd(2, N, seed=89)
+    cls = (torch.arange(M, device=dev()) % 2).to(torch.int32)
+    acc = a.float() @ w.float().T + bias
+
+    def run():
+        if mode == "bf16":
+            return ops.gemm(a, w, bias).float(), acc, TOL_BF16_OUT
+        if mode == "gelu":
+            return (ops.gemm(a, w, bias, mode=ops.EPI_BF16_GELU).float(),
+                    torch.nn.functional.gelu(acc, approximate="tanh"), TOL_BF16_OUT)
+        if mode == "f32":
+            return ops.gemm(a, w, bias, mode=ops.EPI_F32), acc, TOL_F32_OUT
+        y = x.clone()
+        ops.gemm(a, w, bias, mode=ops.EPI_F32_RESIDUAL, out=y, gate=gate, row_cls=cls, alpha=0.5)
+        return y, x + 0.5 * gate[cls.long()] * acc, TOL_F32_OUT
+
+    out2, ref, tol = run()
+    assert rel_err(out2, ref) < tol
+    monkeypatch.delenv("LTX2_GEMM_2CTA")
+    out1, _, _ = run()
+    assert rel_err(out2, out1) < 1e-5 if mode in ("f32", "residual") else rel_err(out2, out1) < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 1024, 4096), (432, 4096, 4096), (432, 4096, 16384), (100, 512, 640)])
 def test_gemm_residual_split_k_small_m(M, N, K):
     """Small-M residual GEMMs (context-parallel ranks) split K across CTAs and accumulate with vector reductions."""

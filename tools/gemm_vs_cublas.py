@@ -39,7 +39,12 @@ for M, N, K in [(3456, 12288, 4096), (3456, 4096, 4096), (3456, 16384, 4096), (3
     w = torch.randn(N, K, device=dev).to(torch.bfloat16) * K ** -0.5
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     fl = 2.0 * M * N * K
+    os.environ.pop("LTX2_GEMM_2CTA", None)
     ms_ours = timed(lambda: ops.gemm(a, w, None, out=out))
+    os.environ["LTX2_GEMM_2CTA"] = "2"
+    ms_pair = timed(lambda: ops.gemm(a, w, None, out=out))
+    os.environ.pop("LTX2_GEMM_2CTA", None)
     ms_cublas = timed(lambda: torch.matmul(a, w.t(), out=out))
-    print(f"M={M:5d} N={N:5d} K={K:5d}  ours {fl / ms_ours / 1e9:7.1f} TF/s ({ms_ours * 1e3:7.1f} us)   "
+    print(f"M={M:5d} N={N:5d} K={K:5d}  1-CTA {fl / ms_ours / 1e9:7.1f} TF/s ({ms_ours * 1e3:7.1f} us)   "
+          f"2-CTA {fl / ms_pair / 1e9:7.1f} TF/s ({ms_pair * 1e3:7.1f} us)   "
           f"cuBLAS {fl / ms_cublas / 1e9:7.1f} TF/s ({ms_cublas * 1e3:7.1f} us)", flush=True)
