@@ -12,6 +12,8 @@
 // Both operands are K-major (row-major activations, nn.Linear [out,in] weights), so no transposes exist anywhere.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -324,16 +326,18 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 // Transposed epilogue of the 2-CTA kernel: the accumulator tile is C^T, i.e. TMEM lane = output column (weight row),
 // TMEM column = token.  Thread `lane` of a warp owns one output column; the 32 lanes of a warp store 32 consecutive
 // output columns of one token per instruction (64 B bf16 / 128 B fp32 runs).
-__device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t t_row, int col, int tok0, int ntok, int M) {
-  const float b = ep.bias != nullptr ? __ldg(ep.bias + col) : 0.f;
+__device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t t_row, int col, int tok0, int ntok, int M,
+                                               bool first_slice = true) {
+  const float b = (ep.bias != nullptr && first_slice) ? __ldg(ep.bias + col) : 0.f;
 #pragma unroll 1
   for (int c = 0; c < ntok; c += 32) {
     uint32_t r[32];
     tmem_ld_32x32(t_row + c, r);
     tmem_ld_wait();
     const int t0 = tok0 + c;
-    if (t0 >= M) break;
-    const int nv = min(32, M - t0);                       // warp-uniform
+    const int tend = min(M, tok0 + ntok);                 // tokens of THIS tile only (ntok need not be a multiple of 32)
+    if (t0 >= tend) break;
+    const int nv = min(32, tend - t0);                    // warp-uniform
     if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
 #pragma unroll
@@ -363,26 +367,179 @@ __device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t 
   }
 }
 
-// Static tile schedule of the 2-CTA kernel.  Work items are full tiles (256 tokens) and, when the token count leaves at
-// most 128 tokens for the last tile, half tiles (128 tokens, half the time).  Full tiles go round-robin over the clusters
-// (token tile fastest, so a weight slab is reused from L2); the half tiles then go two at a time to the clusters that
-// got one full tile fewer, so that e.g. 16 x 13.5 tiles finish in 3 tile times on 74 SM pairs instead of 4.
+// ---------------------------------------------------------------------------------------------------------------
+// Transposed 1-CTA variant for token counts that do not fill 128-row tiles (context-parallel shards: 432 rows per rank
+// waste 16 % of every 128-row tile, and 4 row tiles x N/256 columns quantise badly over 148 SMs).  The CTA computes a
+// C^T tile: MMA M = 128 WEIGHT rows, MMA N = nt tokens, nt any multiple of 16 up to 256 chosen by the host so that
+// (a) no token column is wasted (432 = 3 x 144) and (b) the tile count fills whole waves.  Same warp roles and pipeline
+// as gemm_bf16_kernel; the accumulator is read with the transposed epilogue (lane = output column).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStagesT = 4;
+constexpr int kStageBytesT = BM * BK * 2 + 256 * BK * 2;       // 16 KB weights + up to 32 KB tokens
+constexpr int kSmemBytesT = kStagesT * kStageBytesT + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_t_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, int M, int N,
+                   int K, int nt, int num_t, int splits, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                       // [stages][128 weight rows x 64]
+  uint8_t* smem_b = smem + kStagesT * (BM * BK * 2);            // [stages][<= 256 tokens x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesT * kStageBytesT);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStagesT;
+  uint64_t* acc_full = bars + 2 * kStagesT;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int num_w = N / BM;
+  const int num_wt = num_w * num_t;
+  const int num_tiles = num_wt * splits;             // work item = (token tile [fastest], weight tile, K slice)
+  const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + splits - 1) / splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kStagesT; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stage_tx = BM * BK * 2 + nt * BK * 2;          // the token box is nt rows (out-of-range rows count too)
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int t0 = (tile % num_t) * nt;
+      const int w0 = ((tile / num_t) % num_w) * BM;
+      const int kb0 = (tile / num_wt) * kb_per;
+      const int kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_2d(smem_a + stage * (BM * BK * 2), &tmap_w, &full_bar[stage], kb * BK, w0);
+          tma_load_2d(smem_b + stage * (256 * BK * 2), &tmap_x, &full_bar[stage], kb * BK, t0);
+        }
+        if (++stage == kStagesT) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int t0 = (tile % num_t) * nt;
+      const int n_mma = min(nt, (M - t0 + 15) & ~15);           // tokens of this tile, rounded up to the MMA N step
+      const uint32_t idesc = umma_idesc_bf16(BM, static_cast<uint32_t>(n_mma));
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      const int kb0 = (tile / num_wt) * kb_per;
+      const int kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * (BM * BK * 2)));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * (256 * BK * 2)));
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStagesT) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int t0 = (tile % num_t) * nt;
+      const int col = ((tile / num_t) % num_w) * BM + quarter * 32 + lane;
+      const bool first_slice = tile < num_wt;                   // the bias is added by K slice 0 only
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
+      epilogue_col_t(ep, t_row, col, t0, min(nt, M - t0), M, first_slice);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_gemm_t(const CUtensorMap* tw, const CUtensorMap* tx, int M, int N, int K, int nt, int num_t, int splits,
+                  const GemmEpilogue& ep, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm_t_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT));
+    configured = true;
+  }
+  const int tiles = (N / BM) * num_t * splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_t_bf16_kernel<<<grid, kGemmThreads, kSmemBytesT, stream>>>(*tw, *tx, M, N, K, nt, num_t, splits, ep);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+// Static tile schedule of the 2-CTA kernel.  Token tiles are tw wide (a multiple of 32, <= 256); the last one is lw wide
+// (the remaining tokens rounded up to 32).  When lw <= tw / 2 the last tile of every weight slab is a "half" item
+// (about half the time): full tiles go round-robin over the clusters (token tile fastest, so a weight slab is reused
+// from L2) and the half tiles then go two at a time to the clusters that got one full tile fewer, so that e.g.
+// 16 x 13.5 tiles finish in 3 tile times on 74 SM pairs instead of 4.
 struct PairSched {
   int nc, c;          // clusters, this cluster
-  int n_full_t;       // full-width token tiles
+  int tw, lw;         // tile widths
+  int n_full_t;       // token tiles scheduled as full items
   int num_t;          // token tiles incl. a half one
   int nfull, nhalf;   // work items
-  int my_full;        // full tiles of this cluster
-  int lh0;            // half tiles this cluster takes as a "light" cluster
+  int my_full;        // full items of this cluster
+  int lh0;            // half items this cluster takes as a "light" cluster
   int li;             // its index among the light clusters
   int n_light_halves;
 };
-__device__ __forceinline__ PairSched make_sched(int M, int N, int nc, int c) {
+__device__ __forceinline__ PairSched make_sched(int M, int N, int tw, int nc, int c) {
   PairSched s;
   s.nc = nc;
   s.c = c;
-  s.num_t = (M + 255) / 256;
-  const bool half = (M - (s.num_t - 1) * 256) <= 128;
+  s.tw = tw;
+  s.num_t = (M + tw - 1) / tw;
+  s.lw = min(tw, (M - (s.num_t - 1) * tw + 31) & ~31);
+  const bool half = 2 * s.lw <= tw;
   s.n_full_t = half ? s.num_t - 1 : s.num_t;
   const int num_w = N / 256;
   s.nfull = s.n_full_t * num_w;
@@ -401,7 +558,7 @@ __device__ __forceinline__ bool sched_tile(const PairSched& s, int i, int& wi, i
     const int f = s.c + i * s.nc;
     wi = f / s.n_full_t;
     ti = f % s.n_full_t;
-    nt = 256;
+    nt = ti == s.num_t - 1 ? s.lw : s.tw;
     return true;
   }
   const int j = i - s.my_full;
@@ -409,7 +566,7 @@ __device__ __forceinline__ bool sched_tile(const PairSched& s, int i, int& wi, i
   if (h >= s.nhalf) return false;
   wi = h;
   ti = s.num_t - 1;
-  nt = 128;
+  nt = s.lw;
   return true;
 }
 
@@ -418,7 +575,8 @@ __device__ __forceinline__ bool sched_tile(const PairSched& s, int i, int& wi, i
 // (3456 = 27 x 128) costs nothing, where 256-token-row tiles would waste half a tile per weight slab.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x128,
-                  const __grid_constant__ CUtensorMap tmap_x64, int M, int N, int K, GemmEpilogue ep) {
+                  const __grid_constant__ CUtensorMap tmap_x64, int M, int N, int K, int tw, GemmEpilogue ep) {
+  // tmap_x128 / tmap_x64: the token operand with a box of tw/2 rows (full tiles) and lw/2 rows (last tile)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                       // [stages][128 weight rows x 64]
@@ -435,7 +593,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const PairSched sched = make_sched(M, N, num_clusters, cluster_id);
+  const PairSched sched = make_sched(M, N, tw, num_clusters, cluster_id);
   const int num_kb = (K + BK - 1) / BK;
   int wi, ti, nt;
 
@@ -470,14 +628,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     uint32_t phase = 0;
     for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
       const int w0 = wi * 256 + static_cast<int>(rank) * 128;
-      const int t0 = ti * 256 + static_cast<int>(rank) * (nt / 2);
+      const bool last = ti == sched.num_t - 1;
+      const int t0 = ti * tw + static_cast<int>(rank) * (nt / 2);
       const uint32_t bytes = kHalfBytes + (nt / 2) * BK * 2;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           mbar_expect_tx(&full_bar[stage], bytes);
           tma_load_2d(smem_a + stage * kHalfBytes, &tmap_w, &full_bar[stage], kb * BK, w0);
-          tma_load_2d(smem_b + stage * kHalfBytes, nt == 256 ? &tmap_x128 : &tmap_x64, &full_bar[stage], kb * BK, t0);
+          tma_load_2d(smem_b + stage * kHalfBytes, last ? &tmap_x64 : &tmap_x128, &full_bar[stage], kb * BK, t0);
         }
         if (++stage == kStages2) { stage = 0; phase ^= 1; }
       }
@@ -498,13 +657,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (CTA 0) =====================
     const bool leader = elect_one();
-    constexpr uint32_t idesc256 = umma_idesc_bf16(256, 256), idesc128 = umma_idesc_bf16(256, 128);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
-      const uint32_t idesc = nt == 128 ? idesc128 : idesc256;
+      const uint32_t idesc = umma_idesc_bf16(256, static_cast<uint32_t>(nt));
       mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
@@ -536,7 +694,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * 256;
-      epilogue_col_t(ep, t_row, col, ti * 256, nt, M);
+      epilogue_col_t(ep, t_row, col, ti * tw, nt, M);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
@@ -553,19 +711,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   }
 }
 
-int gemm2_tiles(int M, int N) { return ((M + 255) / 256) * (N / 256); }
+int gemm2_tiles(int M, int N, int tile_w = 256) { return ((M + tile_w - 1) / tile_w) * (N / 256); }
 
 int launch_gemm2(const CUtensorMap* tw, const CUtensorMap* tx128, const CUtensorMap* tx64, int M, int N, int K,
-                 const GemmEpilogue& ep, cudaStream_t stream) {
+                 int tile_w, const GemmEpilogue& ep, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
     configured = true;
   }
-  const int tiles = gemm2_tiles(M, N);
+  const int tiles = gemm2_tiles(M, N, tile_w);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_bf16_kernel<<<grid, kGemmThreads, kSmemBytes2, stream>>>(*tw, *tx128, *tx64, M, N, K, ep);
+  gemm2_bf16_kernel<<<grid, kGemmThreads, kSmemBytes2, stream>>>(*tw, *tx128, *tx64, M, N, K, tile_w, ep);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;
@@ -615,25 +773,98 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
     if (N % 128 != 0 || (bn == 128 && ((M + BM - 1) / BM) * ((N + 127) / 128) < num_sms() / 2)) bn = 64;
     if (N % 64 != 0) bn = 32;
   }
+  // Kernel choice by a small cycle model.  One work item costs max(MMA cycles, operand bytes / ~77 B per clock -- what
+  // the L2 feeds one SM; the standard 128 x 256 tile is bound by it: 48 KB against 512 MMA clocks per K block, the 82 %
+  // tensor-pipe activity of profiles/r1c_kernels.json) plus a fixed cost, and a launch costs that times the number
+  // of waves.  Candidates:
+  //   standard     128 token rows x bn columns (above)
+  //   transposed   128 weight rows x nt tokens, nt a multiple of 16 (no wasted token rows, flexible tile count)
+  //   pair         SM pairs (cta_group::2): 256 weight rows x tw tokens, tw a multiple of 32; each SM loads only half
+  //                of the token operand, so the small tiles a 432-row shard needs stay fed
+  // Measured (tools/gemm_cp_shapes.py, tools/gemm_vs_cublas.py): the alternatives win on the wide bf16-output
+  // projections (QKV N = 12288, FFN up N = 16384: 4-22 % at 432 / 864 / 1728 / 3456 token rows) and lose on the
+  // N = 4096 launches (few weight slabs) and on the residual epilogue (scalar reductions, no split-K in the pair
+  // kernel), so unless forced they are only considered for bf16 outputs with N >= 8192, and the standard kernel keeps
+  // a 10 % bonus.  At the full 3456 rows they gain 3-4 % stand-alone but nothing inside the power-capped step (11.20 vs
+  // 11.23 steps/s, same box), so up to 2048 rows only: the single-GPU path stays on the standard kernel.
+  //   LTX2_GEMM_T=0 / LTX2_GEMM_2CTA=0 remove a candidate, =2 force it when it applies (tests)
+  {
+    const char* envt = getenv("LTX2_GEMM_T");
+    const char* env2 = getenv("LTX2_GEMM_2CTA");
+    const int nsm = num_sms();
+    auto item_cost = [](long kb, long mma_per_kb, long bytes_per_kb, long fixed) {
+      const long feed = bytes_per_kb / 77;
+      return kb * (mma_per_kb > feed ? mma_per_kb : feed) + fixed;
+    };
+    const long kb_std = (num_kb + splits - 1) / splits;
+    const long items_std = static_cast<long>((M + BM - 1) / BM) * ((N + bn - 1) / bn) * splits;
+    const long cost_std = ((items_std + nsm - 1) / nsm) * item_cost(kb_std, 4 * (bn / 2), (BM + bn) * BK * 2, 1500);
+    const bool may_split = ep.mode == GEMM_EPI_F32_RESIDUAL && ep.max_splits > 1;
+    // transposed 1-CTA
+    long best_t = -1;
+    int t_nt = 0, t_num = 0, t_splits = 1;
+    if (N % BM == 0 && ep.n_out_peers == 0 && !(envt && envt[0] == '0')) {
+      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 16; ++num_t) {
+        const int nt = (((M + num_t - 1) / num_t) + 15) & ~15;
+        if (nt > 256 || static_cast<long>(nt) * (num_t - 1) >= M) continue;
+        const long base = static_cast<long>(N / BM) * num_t;
+        for (int sp = 1; sp <= (may_split ? 8 : 1); ++sp) {
+          if (sp > 1 && (sp > ep.max_splits || num_kb / sp < 8)) break;
+          const long cost = ((base * sp + nsm - 1) / nsm) *
+                            item_cost((num_kb + sp - 1) / sp, 4 * (nt / 2), (BM + nt) * BK * 2, 2500);
+          if (best_t < 0 || cost < best_t) {
+            best_t = cost;
+            t_nt = nt;
+            t_num = num_t;
+            t_splits = sp;
+          }
+        }
+      }
+    }
+    // pair (2-CTA) kernel: no split-K
+    long best_p = -1;
+    int p_tw = 0;
+    if (N % 256 == 0 && ep.n_out_peers == 0 && splits == 1 && M >= 64 && !(env2 && env2[0] == '0')) {
+      const int pairs = nsm / 2;
+      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 16; ++num_t) {
+        const int tw = (((M + num_t - 1) / num_t) + 31) & ~31;
+        if (tw > 256 || static_cast<long>(tw) * (num_t - 1) >= M) continue;
+        const int lw = std::min(tw, (M - (num_t - 1) * tw + 31) & ~31);
+        const long num_w = N / 256;
+        // items in units of full tiles (a last tile of at most half width counts as half)
+        const long units2 = 2 * num_w * (num_t - 1) + (2 * lw <= tw ? num_w : 2 * num_w);
+        const long waves2 = (units2 + 2 * pairs - 1) / (2 * pairs);   // in half-tile steps
+        const long cost = waves2 * item_cost(num_kb, 4 * (tw / 2), (BM + tw / 2) * BK * 2, 3000) / 2 +
+                          item_cost(0, 0, 0, 1500);
+        if (best_p < 0 || cost < best_p) {
+          best_p = cost;
+          p_tw = tw;
+        }
+      }
+    }
+    const bool force_t = envt && envt[0] == '2', force_p = env2 && env2[0] == '2';
+    const bool wide_bf16 = (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) && N >= 8192 && M <= 2048;
+    const bool take_p = best_p > 0 && (force_p || (!force_t && wide_bf16 && best_p * 10 < cost_std * 9 &&
+                                                   (best_t < 0 || best_p <= best_t)));
+    const bool take_t = !take_p && best_t > 0 && (force_t || (wide_bf16 && best_t * 10 < cost_std * 9));
+    if (take_p) {
+      const int num_t = (M + p_tw - 1) / p_tw;
+      const int lw = std::min(p_tw, (M - (num_t - 1) * p_tw + 31) & ~31);
+      const CUtensorMap *tw, *txf, *txl;
+      LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
+      LTX2_PROPAGATE(get_tensor_map_2d(&txf, A, M, K, lda, p_tw / 2));
+      LTX2_PROPAGATE(get_tensor_map_2d(&txl, A, M, K, lda, lw / 2));
+      return launch_gemm2(tw, txf, txl, M, N, K, p_tw, ep, stream);
+    }
+    if (take_t) {
+      const CUtensorMap *tw, *tx;
+      LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, BM));
+      LTX2_PROPAGATE(get_tensor_map_2d(&tx, A, M, K, lda, t_nt));
+      return launch_gemm_t(tw, tx, M, N, K, t_nt, t_num, t_splits, ep, stream);
+    }
+  }
   const CUtensorMap *ta, *tb;
   LTX2_PROPAGATE(get_tensor_map_2d(&ta, A, M, K, lda, BM));
-  // 2-CTA kernel (256 weight rows x 256 tokens per SM pair, C^T tiles): OPT-IN.  Stand-alone it beats the 1-CTA kernel
-  // by 2-5 % on the long launches (QKV, FFN up-projection; tools/gemm_vs_cublas.py) and loses ~3 % at ~3 tiles per pair
-  // (longer prologue, scalar-store epilogue); inside the power-capped denoising step the two measure the same
-  // (90.7 vs 91.2 ms, same box), so the simpler kernel stays the default.
-  //   LTX2_GEMM_2CTA=1  2-CTA kernel for launches with >= 6 tiles per SM pair
-  //   LTX2_GEMM_2CTA=2  2-CTA kernel whenever it fills the machine (tests)
-  const char* env2 = getenv("LTX2_GEMM_2CTA");
-  const bool on2 = env2 && (env2[0] == '1' || env2[0] == '2');
-  const int min_rounds = (env2 && env2[0] == '2') ? 1 : 6;
-  if (bn == 256 && splits == 1 && ep.n_out_peers == 0 && M >= 256 &&
-      gemm2_tiles(M, N) >= min_rounds * (num_sms() / 2) && on2) {
-    const CUtensorMap *tw, *tx128, *tx64;
-    LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
-    LTX2_PROPAGATE(get_tensor_map_2d(&tx128, A, M, K, lda, 128));
-    LTX2_PROPAGATE(get_tensor_map_2d(&tx64, A, M, K, lda, 64));
-    return launch_gemm2(tw, tx128, tx64, M, N, K, ep, stream);
-  }
   LTX2_PROPAGATE(get_tensor_map_2d(&tb, W, N, K, ldw, bn));
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, M, N, K, splits, ep, stream);

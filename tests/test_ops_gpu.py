@@ -281,12 +281,12 @@ def test_attention_v_in_row_form_from_fused_qkv(B, H, Tq, Tk, Dh):
     assert rel_err(out.float(), ref) < 1.2e-2
 
 
-@pytest.mark.parametrize("M", [3456, 3500, 3328, 2049])
+@pytest.mark.parametrize("M", [3456, 3500, 3328, 2049, 432, 864, 65, 1000])
 @pytest.mark.parametrize("mode", ["bf16", "gelu", "f32", "residual"])
 def test_gemm_two_cta_transposed_tiles(monkeypatch, M, mode):
-    """Opt-in kernel (LTX2_GEMM_2CTA): SM pairs (tcgen05 cta_group::2) compute C^T tiles, 256 weight rows x 256 tokens,
-    the last token tile 128 wide when <= 128 tokens remain (3456), zero-filled otherwise (3500); every epilogue mode.
-    The 1-CTA kernel on the same inputs must agree to rounding."""
+    """Pair kernel (tcgen05 cta_group::2): two SMs compute a C^T tile of 256 weight rows x tw tokens, tw a multiple of
+    32 picked by the host (432 -> 3 x 160 ...), a narrow last tile scheduled as a half item (3456 = 13.5 x 256), rows
+    past M zero-filled (3500); every epilogue mode.  Forced on here; the standard kernel must agree to rounding."""
     from ltx2_b200 import ops
     monkeypatch.setenv("LTX2_GEMM_2CTA", "2")          # take the pair kernel as soon as it fills the machine
     N, K = 2560, 320
@@ -310,9 +310,45 @@ def test_gemm_two_cta_transposed_tiles(monkeypatch, M, mode):
 
     out2, ref, tol = run()
     assert rel_err(out2, ref) < tol
-    monkeypatch.delenv("LTX2_GEMM_2CTA")
+    monkeypatch.setenv("LTX2_GEMM_2CTA", "0")
+    monkeypatch.setenv("LTX2_GEMM_T", "0")
     out1, _, _ = run()
     assert rel_err(out2, out1) < 1e-5 if mode in ("f32", "residual") else rel_err(out2, out1) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(432, 1536, 512), (432, 4096, 2048), (65, 2048, 256), (864, 12288, 256), (200, 384, 640),
+                                   (1000, 1024, 4096)])
+@pytest.mark.parametrize("mode", ["bf16", "gelu", "f32", "residual", "residual_splitk"])
+def test_gemm_transposed_tiles_for_ragged_token_counts(monkeypatch, M, N, K, mode):
+    """Token counts that do not fill 128-row tiles (context-parallel shards, audio tokens) run as C^T tiles: 128 weight
+    rows x nt tokens, nt a multiple of 16 chosen by the host (432 -> 3 x 144).  Forced on here for every shape and
+    epilogue mode; the standard kernel on the same inputs must agree."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_GEMM_T", "2")
+    a, w = rnd(M, K, seed=90, dtype=torch.bfloat16), rnd(N, K, seed=91, std=K ** -0.5, dtype=torch.bfloat16)
+    bias, x = rnd(N, seed=92), rnd(M, N, seed=93)
+    gate = rnd(3, N, seed=94)
+    cls = (torch.arange(M, device=dev()) % 3).to(torch.int32)
+    acc = a.float() @ w.float().T + bias
+
+    def run():
+        if mode == "bf16":
+            return ops.gemm(a, w, bias).float(), acc, TOL_BF16_OUT
+        if mode == "gelu":
+            return (ops.gemm(a, w, bias, mode=ops.EPI_BF16_GELU).float(),
+                    torch.nn.functional.gelu(acc, approximate="tanh"), TOL_BF16_OUT)
+        if mode == "f32":
+            return ops.gemm(a, w, bias, mode=ops.EPI_F32), acc, TOL_F32_OUT
+        y = x.clone()
+        ops.gemm(a, w, bias, mode=ops.EPI_F32_RESIDUAL, out=y, gate=gate, row_cls=cls, alpha=0.5,
+                 max_splits=8 if mode == "residual_splitk" else 1)
+        return y, x + 0.5 * gate[cls.long()] * acc, TOL_F32_OUT
+
+    out_t, ref, tol = run()
+    assert rel_err(out_t, ref) < tol
+    monkeypatch.setenv("LTX2_GEMM_T", "0")
+    out_s, _, _ = run()
+    assert rel_err(out_t, out_s) < (2e-3 if mode in ("bf16", "gelu") else 2e-5)
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 1024, 4096), (432, 4096, 4096), (432, 4096, 16384), (100, 512, 640)])

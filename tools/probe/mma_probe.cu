@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe(long long* cyc, int n_groups
             if (MODE == 1) umma_bf16_ts(tm + (g & 1) * 128, tm + 256 + ks * 8, bd + off, id128, ks != 0);
             if (MODE == 2) umma_bf16_ts(tm + (g & 1) * 128, tm + 256 + ks * 8, bmn + ks * (2048 >> 4), id128mn, ks != 0);
             if (MODE == 3) umma_bf16_ss(tm + (g & 1) * 256, ad + off, bd + off, id256, ks != 0);
+            if (MODE >= 16) umma_bf16_ss(tm + (g & 1) * 256, ad + off, bd + off, umma_idesc_bf16(128, MODE), ks != 0);
             if (MODE == 5) umma_bf16_ss(tm + (g & 3) * 64, ad + off, bd + off, umma_idesc_bf16(128, 64), ks != 0);
             if (MODE == 6) {   // sub-block step: P*V with K = 64 (4 TS MMAs, N = 128), then S with N = 64 (8 SS MMAs)
               if (ks < 4) umma_bf16_ts(tm + 256 + (g & 1) * 128, tm + (g & 3) * 64 + ks * 8, bmn + ks * (2048 >> 4), id128mn, 1);
@@ -94,6 +95,14 @@ int main() {
     run<4>("alternating SS (QK^T) / TS MN-major (PV)", sms);
     run<5>("SS  N=64", sms);
     run<6>("sub-block step: 4x TS N=128 + 8x SS N=64", sms);
+    run<80>("SS  N=80", sms);
+    run<112>("SS  N=112", sms);
+    run<144>("SS  N=144", sms);
+    run<176>("SS  N=176", sms);
+    run<192>("SS  N=192", sms);
+    run<208>("SS  N=208", sms);
+    run<224>("SS  N=224", sms);
+    run<240>("SS  N=240", sms);
   }
   return 0;
 }
