@@ -268,6 +268,17 @@ int ltx2_small_linear(const float* x, int32_t R, int32_t K, const void* W_bf16, 
 int ltx2_x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int32_t M,
                           int32_t C, void* stream);
 
+/* The elementwise tail of one denoising step of the reference's host loops (pipelines/distilled.py:243-251,
+ * pipelines/one_stage.py:284-320), fused into one pass over fp32 [M, C] tensors:
+ *   CFGGuider.guide (components/guiders.py:40-44)            d = cond + (cfg_scale - 1)(cond - uncond)   [uncond_x0 != NULL]
+ *   post_process_latent (pipelines/common.py:169-190)        d = d * mask[row] + clean * (1 - mask[row]) [mask, clean != NULL]
+ *   EulerDiffusionStep.step (components/diffusion_steps.py:55-67, to_velocity core_utils.py:34-62)
+ *                                                            out = sample + (sample - d) / sigma * (sigma_next - sigma)
+ * denoised_out (optional) receives d.  sigma == 0 is LTX2_ERR_INVALID ("Sigma can't be 0.0", core_utils.py:54-55). */
+int ltx2_denoise_update(const float* sample, const float* cond_x0, const float* uncond_x0, float cfg_scale,
+                        const float* denoise_mask, const float* clean_latent, float sigma, float sigma_next, float* out,
+                        float* denoised_out, int32_t M, int32_t C, void* stream);
+
 /* The reference's own three kernels (kernels/fused_ops.py:50, 95, 183). */
 int ltx2_silu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream);
 int ltx2_gelu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream);

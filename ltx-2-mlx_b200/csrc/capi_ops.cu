@@ -135,6 +135,13 @@ int ltx2_x0_from_velocity(const float* latent, const float* velocity, const floa
   return x0_from_velocity(latent, velocity, t_row, x0, M, C, S(stream));
 }
 
+int ltx2_denoise_update(const float* sample, const float* cond_x0, const float* uncond_x0, float cfg_scale,
+                        const float* denoise_mask, const float* clean_latent, float sigma, float sigma_next, float* out,
+                        float* denoised_out, int32_t M, int32_t C, void* stream) {
+  return denoise_update(sample, cond_x0, uncond_x0, cfg_scale, denoise_mask, clean_latent, sigma, sigma_next, out,
+                        denoised_out, M, C, S(stream));
+}
+
 int ltx2_silu_mul(const void* a, const void* b, void* out, int64_t n, int32_t dtype, void* stream) {
   return silu_mul(a, b, out, n, dtype, S(stream));
 }

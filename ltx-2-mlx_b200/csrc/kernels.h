@@ -150,6 +150,13 @@ int rope_tables_dev(const float* positions, int B, int pos_dims, int n_dims, int
 int x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int M, int C,
                      cudaStream_t stream);
 
+// One fused pass for the elementwise tail of a denoising step (the reference's host loop, pipelines/distilled.py:243-251,
+// one_stage.py:284-320): CFG guide (uncond != null) -> masked blend with the clean latent (mask [M] per row, clean
+// [M,C]; both null = off) -> Euler step.  All fp32 [M,C]; denoised_out (optional) receives the guided+blended x0.
+int denoise_update(const float* sample, const float* cond, const float* uncond, float cfg_scale, const float* mask,
+                   const float* clean, float sigma, float sigma_next, float* out, float* denoised_out, int M, int C,
+                   cudaStream_t stream);
+
 int cast_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStream_t stream);
 int cast_to_f32(const void* src, int src_dtype, float* dst, int64_t n, cudaStream_t stream);
 

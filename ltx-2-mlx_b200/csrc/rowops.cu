@@ -663,6 +663,63 @@ int rope_tables_dev(const float* positions, int B, int pos_dims, int n_dims, int
   return LTX2_OK;
 }
 
+namespace {
+
+// The elementwise tail of a denoising step in one pass (all fp32):
+//   d = cond + (cfg_scale - 1) * (cond - uncond)           CFGGuider.guide        (components/guiders.py:40-44)
+//   d = d * mask[row] + clean * (1 - mask[row])             post_process_latent    (pipelines/common.py:169-190)
+//   out = sample + (sample - d) / sigma * (sigma_next - sigma)   EulerDiffusionStep.step (diffusion_steps.py:55-67,
+//                                                                 to_velocity core_utils.py:34-62)
+// uncond / mask / clean may be null (that stage is skipped); denoised_out (optional) receives d.
+__global__ void denoise_update_kernel(const float* __restrict__ sample, const float* __restrict__ cond,
+                                      const float* __restrict__ uncond, float cfg_m1, const float* __restrict__ mask,
+                                      const float* __restrict__ clean, float inv_sigma, float dt,
+                                      float* __restrict__ out, float* __restrict__ denoised_out, int64_t n4, int C4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4*>(sample)[i];
+  float4 d = reinterpret_cast<const float4*>(cond)[i];
+  if (uncond != nullptr) {
+    const float4 u = reinterpret_cast<const float4*>(uncond)[i];
+    d.x = d.x + cfg_m1 * (d.x - u.x);
+    d.y = d.y + cfg_m1 * (d.y - u.y);
+    d.z = d.z + cfg_m1 * (d.z - u.z);
+    d.w = d.w + cfg_m1 * (d.w - u.w);
+  }
+  if (mask != nullptr) {
+    const float m = mask[i / C4];
+    const float4 c = reinterpret_cast<const float4*>(clean)[i];
+    d.x = d.x * m + c.x * (1.f - m);
+    d.y = d.y * m + c.y * (1.f - m);
+    d.z = d.z * m + c.z * (1.f - m);
+    d.w = d.w * m + c.w * (1.f - m);
+  }
+  if (denoised_out != nullptr) reinterpret_cast<float4*>(denoised_out)[i] = d;
+  float4 o;
+  o.x = x.x + ((x.x - d.x) * inv_sigma) * dt;
+  o.y = x.y + ((x.y - d.y) * inv_sigma) * dt;
+  o.z = x.z + ((x.z - d.z) * inv_sigma) * dt;
+  o.w = x.w + ((x.w - d.w) * inv_sigma) * dt;
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+
+}  // namespace
+
+int denoise_update(const float* sample, const float* cond, const float* uncond, float cfg_scale, const float* mask,
+                   const float* clean, float sigma, float sigma_next, float* out, float* denoised_out, int M, int C,
+                   cudaStream_t stream) {
+  LTX2_REQUIRE(sigma != 0.f, "denoise_update: sigma can't be 0.0");          // core_utils.py:54-55
+  LTX2_REQUIRE(C % 4 == 0, "denoise_update: channel count %d must be a multiple of 4", C);
+  LTX2_REQUIRE((mask == nullptr) == (clean == nullptr), "denoise_update: mask and clean latent go together");
+  const int64_t n4 = static_cast<int64_t>(M) * C / 4;
+  if (n4 == 0) return LTX2_OK;
+  denoise_update_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(
+      sample, cond, uncond, cfg_scale - 1.f, mask, clean, 1.f / sigma, sigma_next - sigma, out, denoised_out, n4, C / 4);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
 int x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int M, int C,
                      cudaStream_t stream) {
   const int64_t n = static_cast<int64_t>(M) * C;

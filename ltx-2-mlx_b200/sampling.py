@@ -1,0 +1,109 @@
+"""The elementwise tail of the reference's denoising loops on the device, in one fused pass.
+
+Mirrors, with the same names and argument meaning:
+  * ``EulerDiffusionStep.step``   components/diffusion_steps.py:36-67  (``to_velocity``: core_utils.py:34-62)
+  * ``CFGGuider``                 components/guiders.py:26-47
+  * ``post_process_latent``       pipelines/common.py:169-190
+and adds ``denoise_update`` (guide -> masked blend -> Euler step in ONE kernel, ``ltx2_denoise_update``) plus
+``euler_denoising_loop``, the distilled pipeline's loop (pipelines/distilled.py:214-253) with every tensor resident on
+the GPU: per step one X0Model call and one update kernel, no host round trip.  Pipelines that keep their own loop can
+swap in the three mirrors one by one; all arithmetic is fp32 like the reference's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+from .transformer import Modality, to_device
+
+
+def _f32(x, dev) -> torch.Tensor:
+    return to_device(x, dev).to(torch.float32).contiguous()
+
+
+def denoise_update(sample, cond_x0, sigma: float, sigma_next: float, *, uncond_x0=None, cfg_scale: float = 1.0,
+                   denoise_mask=None, clean_latent=None, return_denoised: bool = False):
+    """sample, cond_x0[, uncond_x0, clean_latent] (B,T,C); denoise_mask (B,T) or (B,T,1) -> next sample (B,T,C) fp32.
+
+    ``sigma == 0`` raises ValueError("Sigma can't be 0.0") like ``to_velocity`` (core_utils.py:54-55)."""
+    if float(sigma) == 0.0:
+        raise ValueError("Sigma can't be 0.0")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x, c = _f32(sample, dev), _f32(cond_x0, dev)
+    assert x.shape == c.shape and x.ndim == 3, f"Shape mismatch: {tuple(x.shape)} vs {tuple(c.shape)}"
+    u = _f32(uncond_x0, dev) if uncond_x0 is not None else None
+    m = cl = None
+    if denoise_mask is not None:
+        if clean_latent is None:
+            raise ValueError("denoise_mask needs clean_latent")
+        m = _f32(denoise_mask, dev).reshape(x.shape[0], x.shape[1])
+        cl = _f32(clean_latent, dev)
+        assert cl.shape == x.shape
+    out = torch.empty_like(x)
+    den = torch.empty_like(x) if return_denoised else None
+    B, T, Cc = x.shape
+    check(lib().ltx2_denoise_update(ptr(x), ptr(c), ptr(u), C.c_float(cfg_scale), ptr(m), ptr(cl), C.c_float(sigma),
+                                    C.c_float(sigma_next), ptr(out), ptr(den), B * T, Cc, stream_ptr()),
+          "ltx2_denoise_update")
+    return (out, den) if return_denoised else out
+
+
+class EulerDiffusionStep:
+    """components/diffusion_steps.py:22-67: sample + (sample - denoised) / sigma * (sigma_next - sigma), in fp32."""
+
+    def step(self, sample, denoised_sample, sigmas: Sequence[float], step_index: int) -> torch.Tensor:
+        sigma, sigma_next = float(sigmas[step_index]), float(sigmas[step_index + 1])
+        return denoise_update(sample, denoised_sample, sigma, sigma_next)
+
+
+@dataclass(frozen=True)
+class CFGGuider:
+    """components/guiders.py:26-47."""
+    scale: float
+
+    def delta(self, cond, uncond):
+        return (self.scale - 1) * (cond - uncond)
+
+    def guide(self, cond, uncond):
+        return cond + self.delta(cond, uncond)
+
+    def enabled(self) -> bool:
+        return self.scale != 1.0
+
+
+def post_process_latent(denoised, denoise_mask, clean_latent):
+    """pipelines/common.py:169-190 (torch tensors on any device)."""
+    if denoise_mask.ndim == 2 and denoised.ndim == 3:
+        denoise_mask = denoise_mask.unsqueeze(-1)
+    return (denoised * denoise_mask + clean_latent * (1 - denoise_mask)).to(denoised.dtype)
+
+
+def euler_denoising_loop(x0_model, latent, context, positions, sigmas: Sequence[float], *, denoise_mask=None,
+                         clean_latent=None, negative_context=None, cfg_scale: float = 1.0) -> torch.Tensor:
+    """pipelines/distilled.py:214-253 (video only) with optional CFG (pipelines/one_stage.py:267-326): for every sigma,
+    x0 = model(Modality(latent, timesteps = mask * sigma, ...)), then the fused update.  Returns the final latent."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = _f32(latent, dev)
+    B, T, _ = x.shape
+    mask = _f32(denoise_mask, dev).reshape(B, T) if denoise_mask is not None else torch.ones(B, T, device=dev)
+    clean = _f32(clean_latent, dev) if clean_latent is not None else None
+    use_mask = denoise_mask is not None
+    if use_mask and clean is None:
+        raise ValueError("denoise_mask needs clean_latent")
+    ctx, pos = to_device(context, dev), to_device(positions, dev)
+    nctx = to_device(negative_context, dev) if negative_context is not None else None
+    for i in range(len(sigmas) - 1):
+        sigma = float(sigmas[i])
+        ts = mask * sigma                                                   # timesteps_from_mask, common.py:193-203
+        sig = torch.full((B,), sigma, device=dev)
+        cond = x0_model(Modality(latent=x, context=ctx, context_mask=None, timesteps=ts, positions=pos, sigma=sig))
+        uncond = None
+        if nctx is not None and cfg_scale != 1.0:
+            uncond = x0_model(Modality(latent=x, context=nctx, context_mask=None, timesteps=ts, positions=pos, sigma=sig))
+        x = denoise_update(x, cond, sigma, float(sigmas[i + 1]), uncond_x0=uncond, cfg_scale=cfg_scale,
+                           denoise_mask=mask if use_mask else None, clean_latent=clean)
+    return x

@@ -282,7 +282,47 @@ def golden_ops():
     print("ops", y_nc.shape, un.shape, d2s.shape)
 
 
+def _ref_function(path, name):
+    """Compile ONE function of a reference file that cannot be imported as a module here (pipelines/common.py pulls
+    in PIL, the encoder, ...): its source text is taken from the reference file at run time and executed as is."""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"mx": mx}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def golden_sampling():
+    """The elementwise tail of the reference's denoise loops (pipelines/distilled.py:243-251, one_stage.py:284-320):
+    CFGGuider.guide -> post_process_latent -> EulerDiffusionStep.step, run by the reference's own code."""
+    from LTX_2_MLX.components import diffusion_steps as ref_steps
+    from LTX_2_MLX.components import guiders as ref_guiders
+    from LTX_2_MLX.components import schedulers as ref_sched
+    post = _ref_function(f"{REF}/LTX_2_MLX/pipelines/common.py", "post_process_latent")
+    B, T, C = 2, 24, 16
+    sample, cond, uncond, clean = rnd((B, T, C), 60), rnd((B, T, C), 61), rnd((B, T, C), 62), rnd((B, T, C), 63)
+    mask = (np.random.default_rng(64).random((B, T)) > 0.3).astype(np.float32)
+    mask[0, :3] = 0.25                                    # fractional masks occur with strength < 1 conditioning
+    sigmas = np.asarray(ref_sched.DISTILLED_SIGMA_VALUES, np.float32)
+    out = {}
+    stepper = ref_steps.EulerDiffusionStep()
+    for idx in (0, 5, 7):
+        plain = stepper.step(mx.array(sample), mx.array(cond), mx.array(sigmas), idx)
+        guided = ref_guiders.CFGGuider(3.0).guide(mx.array(cond), mx.array(uncond))
+        blended = post(guided, mx.array(mask), mx.array(clean))
+        full = stepper.step(mx.array(sample), blended, mx.array(sigmas), idx)
+        out[f"plain_{idx}"], out[f"full_{idx}"] = A(plain), A(full)
+    out["guided"], out["blended"] = A(guided), A(blended)
+    np.savez_compressed(os.path.join(HERE, "sampling.npz"), sample=sample, cond=cond, uncond=uncond, clean=clean,
+                        mask=mask, sigmas=sigmas, cfg_scale=np.float32(3.0), **out)
+    print("sampling", out["full_0"].shape)
+
+
 if __name__ == "__main__":
+    golden_sampling()
+    if "--sampling-only" in sys.argv:
+        sys.exit(0)
     golden_ops()
     golden_rope()
     golden_dit_v1()
