@@ -279,6 +279,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                       const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
                       float scale_log2, float scale, const float* __restrict__ gate_logits,
                       float* __restrict__ lse_out, long long* __restrict__ trace, AttnOutScatter sc, PairGrid pg) {
+  pdl_trigger();                                        // the next kernel may become resident under my tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2 tiles][2 x (128 rows x 128 B)]
@@ -349,6 +350,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // set-up above overlapped the previous kernel's tail
 
   if (warp >= 8) {
     if (warp < 11) {
@@ -682,8 +684,8 @@ int launch_pair(const void* q, const void* k, const AttnV& v, void* out, int B, 
   const float kLog2e = 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #define LTX2_LAUNCH_PAIR(P)                                                                                        \
-  attention_pair_kernel<VROWS, P><<<grid, kPairThreads, kPairSmem, stream>>>(mq, mk, mv, o, H, Tq, Tk, scale * kLog2e, \
-                                                                             scale, gate_logits, lse_out, trace, sc, pg)
+  launch_pdl(attention_pair_kernel<VROWS, P>, dim3(grid), dim3(kPairThreads), kPairSmem, stream, mq, mk, mv, o, H, Tq, Tk, \
+             scale * kLog2e, scale, gate_logits, lse_out, trace, sc, pg)
   switch (variant) {
     case 0: LTX2_LAUNCH_PAIR(0); break;
     case 2: LTX2_LAUNCH_PAIR(2); break;

@@ -1,6 +1,8 @@
 // Host-side helpers: last-error string, tensor-map creation through the driver entry
 // point (no libcuda link dependency, so the library loads on a GPU-less host), a small
 // tensor-map cache and device queries.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <stdarg.h>
@@ -101,6 +103,15 @@ int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, 
 static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LTX2_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 int num_sms() {
   static int n = 0;

@@ -57,6 +57,13 @@ int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, 
 
 int num_sms();
 
+// Programmatic dependent launch (PDL): the big per-block kernels are launched with the programmatic-stream-serialization
+// attribute, call pdl_trigger() when they start and pdl_wait() before they first touch global memory.  The next kernel's
+// CTAs then become resident as soon as every CTA of the running kernel has started, run their set-up (barrier init, TMEM
+// allocation, tensor-map prefetch) under its tail and start the moment it has completed and flushed -- the ~3 us
+// drain + launch + set-up gap per kernel boundary (737 boundaries per denoising step) shrinks.  LTX2_PDL=0 turns it off.
+bool pdl_enabled();
+
 // number of kernels launched by this library since load (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 int64_t launch_count();
@@ -65,6 +72,9 @@ int64_t launch_count();
 // device-side PTX wrappers
 // ---------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -308,5 +318,25 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// launch `kernel` so that it may overlap the tail of the previous kernel in the stream (see pdl_enabled above); the
+// kernel MUST call pdl_wait() before its first global-memory access
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace ltx2

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  int M, int N, int K, int splits, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
+  pdl_trigger();                                     // the next kernel may become resident under my tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -158,6 +159,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                        // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -381,6 +383,7 @@ constexpr int kSmemBytesT = kStagesT * kStageBytesT + 1024 + 256;
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_t_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, int M, int N,
                    int K, int nt, int num_t, int splits, GemmEpilogue ep) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                       // [stages][128 weight rows x 64]
@@ -422,6 +425,7 @@ gemm_t_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t stage_tx = BM * BK * 2 + nt * BK * 2;          // the token box is nt rows (out-of-range rows count too)
+  pdl_wait();
 
   if (warp == 0) {
     const bool leader = elect_one();
@@ -510,8 +514,8 @@ int launch_gemm_t(const CUtensorMap* tw, const CUtensorMap* tx, int M, int N, in
   }
   const int tiles = (N / BM) * num_t * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_t_bf16_kernel<<<grid, kGemmThreads, kSmemBytesT, stream>>>(*tw, *tx, M, N, K, nt, num_t, splits, ep);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+  LTX2_CUDA_CHECK(launch_pdl(gemm_t_bf16_kernel, dim3(grid), dim3(kGemmThreads), kSmemBytesT, stream, *tw, *tx, M, N, K, nt,
+                             num_t, splits, ep));
   count_launch();
   return LTX2_OK;
 }
@@ -741,8 +745,8 @@ int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(*ta, *tb, M, N, K, splits, ep);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+  LTX2_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, *ta, *tb, M, N, K,
+                             splits, ep));
   count_launch();
   return LTX2_OK;
 }

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kRowThreads)
 norm_modulate_kernel(const void* __restrict__ x_, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ldo, int D,
                      int norm_kind, float eps, const float* __restrict__ mod, int64_t mod_stride, int64_t shift_off,
                      int64_t scale_off, const int* __restrict__ row_cls) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const int units = D / 8;
   float v[kMaxUnits][8];
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(kRowThreads)
 headnorm_rope_kernel(const __nv_bfloat16* __restrict__ in, int64_t ld, const float* __restrict__ weight,
                      const float* __restrict__ cosb, const float* __restrict__ sinb, __nv_bfloat16* __restrict__ out,
                      int T, int H, int Dh, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;             // b*T + t
   const int b = row / T, t = row % T;
   const int inner = H * Dh, half = Dh / 2;
@@ -204,6 +208,8 @@ __global__ void __launch_bounds__(kRowThreads)
 qkv_head_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ wq,
                         const float* __restrict__ wk, const float* __restrict__ cosb, const float* __restrict__ sinb,
                         HeadScatter dst, int T, int H, int Dh, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;             // b*T + t (local tokens)
   const int b = row / T, t = row % T;
   const int inner = H * Dh, half = Dh / 2;
@@ -514,14 +520,13 @@ int norm_modulate(const void* x, int x_is_bf16, int64_t ldx, void* out, int64_t 
   LTX2_REQUIRE(ldx % 8 == 0 && ldo % 8 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0 && mod_stride % 4 == 0,
                "norm_modulate: pitches/offsets must keep 16-byte alignment");
   if (x_is_bf16)
-    norm_modulate_kernel<true><<<M, kRowThreads, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, D,
-                                                              norm_kind, eps, mod, mod_stride, shift_off, scale_off,
-                                                              row_cls);
+    LTX2_CUDA_CHECK(launch_pdl(norm_modulate_kernel<true>, dim3(M), dim3(kRowThreads), 0, stream, x, ldx,
+                               reinterpret_cast<__nv_bfloat16*>(out), ldo, D, norm_kind, eps, mod, mod_stride, shift_off,
+                               scale_off, row_cls));
   else
-    norm_modulate_kernel<false><<<M, kRowThreads, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, D,
-                                                               norm_kind, eps, mod, mod_stride, shift_off, scale_off,
-                                                               row_cls);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+    LTX2_CUDA_CHECK(launch_pdl(norm_modulate_kernel<false>, dim3(M), dim3(kRowThreads), 0, stream, x, ldx,
+                               reinterpret_cast<__nv_bfloat16*>(out), ldo, D, norm_kind, eps, mod, mod_stride, shift_off,
+                               scale_off, row_cls));
   count_launch();
   return LTX2_OK;
 }
@@ -532,9 +537,9 @@ int headnorm_rope(const void* in, int64_t ld, const float* weight, const float* 
   const int inner = H * Dh;
   LTX2_REQUIRE(Dh % 16 == 0 && inner <= kRowThreads * 16 * kHeadUnits, "headnorm_rope: H=%d Dh=%d unsupported", H, Dh);
   LTX2_REQUIRE(ld % 8 == 0, "headnorm_rope: pitch must be a multiple of 8");
-  headnorm_rope_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, weight, cos,
-                                                          sin, reinterpret_cast<__nv_bfloat16*>(out), T, H, Dh, eps);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+  LTX2_CUDA_CHECK(launch_pdl(headnorm_rope_kernel, dim3(B * T), dim3(kRowThreads), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(in), ld, weight, cos, sin,
+                             reinterpret_cast<__nv_bfloat16*>(out), T, H, Dh, eps));
   count_launch();
   return LTX2_OK;
 }
@@ -547,9 +552,8 @@ int qkv_head_scatter(const void* qkv, int64_t ld, const float* wq, const float* 
   LTX2_REQUIRE(ld % 8 == 0 && cos != nullptr && sin != nullptr, "qkv_head_scatter: bad pitch or missing RoPE tables");
   LTX2_REQUIRE(dst.heads_per_rank > 0 && H % dst.heads_per_rank == 0 && H / dst.heads_per_rank <= kMaxCpRanks,
                "qkv_head_scatter: %d heads cannot be split %d per rank", H, dst.heads_per_rank);
-  qkv_head_scatter_kernel<<<B * T, kRowThreads, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ld, wq, wk,
-                                                             cos, sin, dst, T, H, Dh, eps);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+  LTX2_CUDA_CHECK(launch_pdl(qkv_head_scatter_kernel, dim3(B * T), dim3(kRowThreads), 0, stream,
+                             reinterpret_cast<const __nv_bfloat16*>(qkv), ld, wq, wk, cos, sin, dst, T, H, Dh, eps));
   count_launch();
   return LTX2_OK;
 }

@@ -25,10 +25,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="19b")
     ap.add_argument("--layers", type=int, default=None, help="override block count (ncu --set full replays are slow)")
+    ap.add_argument("--grid", type=int, nargs=3, default=None, metavar=("F", "H", "W"),
+                    help="override the latent grid, e.g. 1 18 24 = the 432 tokens of an 8-way context-parallel shard")
     args = ap.parse_args()
     c = dict(bench.CONFIGS[args.config])
     if args.layers:
         c["layers"] = args.layers
+    if args.grid:
+        c["F"], c["H"], c["W"] = args.grid
     dev = torch.device("cuda:0")
     D = c["heads"] * c["head_dim"]
     cfg = synthetic.DitConfig(num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], num_layers=c["layers"],
