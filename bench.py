@@ -474,8 +474,13 @@ def run_ours(args, c):
                                      "text q, text kv, text out) from profiles/r1c_kernels.json; algorithmic bytes of "
                                      "those launches average 128 MB", "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches": int(pl[0]), "ms_in_step": pm[0], "flops_in_step": pf[0],
-                     "attention": {"achieved": attn_tf, "frac": attn_tf / pk["tf"], "launches": int(pl[1]),
-                                   "ms_in_step": pm[1], "flops_in_step": pf[1]},
+                     "attention": {"kernel": "attention_pair_kernel (tcgen05, two softmax streams per CTA; head_dim 128)",
+                                   "achieved": attn_tf, "frac": attn_tf / pk["tf"], "launches": int(pl[1]),
+                                   "ms_in_step": pm[1], "flops_in_step": pf[1],
+                                   "traffic": profiled_traffic("prof_attn", "attention_pair_kernel"),
+                                   "traffic_note": "mean DRAM bytes per launch over one self- and one text "
+                                                   "cross-attention launch (profiles/r1c_kernels.json); algorithmic "
+                                                   "bytes: Q, K, V, O of the launch = 113 MB / 50 MB"},
                      "step": {"algorithmic_flops": fl, "achieved": fl / (ms_step * 1e-3) / 1e12,
                               "frac": fl / (ms_step * 1e-3) / 1e12 / (pk["tf"] * world),
                               "note": "whole-step FLOPs over all ranks / step time, against world x the per-GPU peak"}},

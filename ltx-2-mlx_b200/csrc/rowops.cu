@@ -235,6 +235,18 @@ qkv_head_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const
       }
     }
   }
+  // the RoPE rows (HBM) are fetched BEFORE the block reduction so their latency overlaps it (ncu: 42.7 -> 38.5 us;
+  // the same change in norm_modulate / headnorm_rope cost occupancy and was slower, so it lives only here)
+  float cs[kHeadUnits][8], sns[kHeadUnits][8];
+#pragma unroll
+  for (int u = 0; u < kHeadUnits; ++u) {
+    const int idx = threadIdx.x + u * kRowThreads;
+    if (idx < units) {
+      const int64_t off = static_cast<int64_t>(row) * (inner / 2) + (idx / upr) * half + (idx % upr) * 8;
+      load8_f32(cosb + off, cs[u]);
+      load8_f32(sinb + off, sns[u]);
+    }
+  }
   const float2 s = block_sum2<kRowThreads>(sq, sk);
   const float rq = rsqrtf(s.x / inner + eps), rk = rsqrtf(s.y / inner + eps);
 #pragma unroll
@@ -242,10 +254,9 @@ qkv_head_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const
     const int idx = threadIdx.x + u * kRowThreads;
     if (idx < units) {
       const int h = idx / upr, j0 = (idx % upr) * 8;
-      float a1[8], a2[8], c[8], sn[8], o1[8], o2[8];
-      const int64_t off = static_cast<int64_t>(row) * (inner / 2) + h * half + j0;
-      load8_f32(cosb + off, c);
-      load8_f32(sinb + off, sn);
+      float a1[8], a2[8], o1[8], o2[8];
+      const float (&c)[8] = cs[u];
+      const float (&sn)[8] = sns[u];
       const int dr = h / dst.heads_per_rank, hl = h % dst.heads_per_rank;
       const int64_t o = ((static_cast<int64_t>(b) * dst.heads_per_rank + hl) * dst.n_total + dst.t_offset + t) * Dh + j0;
       load8_f32(wq + h * Dh + j0, a1);
