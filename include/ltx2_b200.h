@@ -268,6 +268,15 @@ int ltx2_small_linear(const float* x, int32_t R, int32_t K, const void* W_bf16, 
 int ltx2_x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int32_t M,
                           int32_t C, void* stream);
 
+/* Host-side planners (no GPU needed; 148 SMs are assumed when no device is visible).  They expose which kernel and
+ * tiling a launch will take, so the scheduling logic is testable on a CPU-only machine.
+ *   ltx2_gemm_plan: out6 = {kernel (0 standard 128-token-row tiles, 1 transposed 128-weight-row tiles, 2 SM-pair tiles),
+ *                           bn, K splits, token tile width, last token tile width, token tiles}
+ *   ltx2_attention_plan: pair work items per (batch, head) slice of the two-stream attention kernel (the remaining
+ *                           128-query tiles run as split-KV items) and the resulting CTA count. */
+int ltx2_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t max_splits, int32_t* out6);
+int ltx2_attention_plan(int32_t Tq, int32_t BH, int32_t* pairs_per_slice, int32_t* n_ctas);
+
 /* The elementwise tail of one denoising step of the reference's host loops (pipelines/distilled.py:243-251,
  * pipelines/one_stage.py:284-320), fused into one pass over fp32 [M, C] tensors:
  *   CFGGuider.guide (components/guiders.py:40-44)            d = cond + (cfg_scale - 1)(cond - uncond)   [uncond_x0 != NULL]

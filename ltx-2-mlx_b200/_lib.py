@@ -64,7 +64,7 @@ EXPORTS = [
     "ltx2_vae_create", "ltx2_vae_destroy", "ltx2_vae_set_weight", "ltx2_vae_missing_weights", "ltx2_vae_output_shape",
     "ltx2_vae_decode", "ltx2_vae_set_profile", "ltx2_vae_profile_read", "ltx2_blend_chunk", "ltx2_video_to_uint8", "ltx2_tile_accumulate", "ltx2_tile_normalize",
     "ltx2_gemm_bf16", "ltx2_gemm_bf16_splitk", "ltx2_attention", "ltx2_attention_trace", "ltx2_attention_vrows", "ltx2_norm_modulate", "ltx2_headnorm_rope", "ltx2_v_transpose",
-    "ltx2_rope_tables", "ltx2_timestep_sinusoid", "ltx2_small_linear", "ltx2_x0_from_velocity", "ltx2_denoise_update", "ltx2_silu_mul",
+    "ltx2_rope_tables", "ltx2_timestep_sinusoid", "ltx2_small_linear", "ltx2_x0_from_velocity", "ltx2_denoise_update", "ltx2_gemm_plan", "ltx2_attention_plan", "ltx2_silu_mul",
     "ltx2_gelu_mul", "ltx2_interleaved_rope", "ltx2_cast",
 ]
 

@@ -664,19 +664,10 @@ int launch_pair(const void* q, const void* k, const AttnV& v, void* out, int B, 
     uint32_t box[3] = {64, static_cast<uint32_t>(DHP), 1};
     LTX2_PROPAGATE(make_tensor_map_bf16(&mv, v.ptr, 3, dims, str, box));
   }
-  // choose how many tiles of each head run as pairs: minimal makespan over the SMs, ties -> more pairs (less L2 traffic)
   PairGrid pg;
   pg.n_q = (Tq + BQP - 1) / BQP;
   pg.BH = static_cast<int>(BH);
-  const int nsm = num_sms();
-  int best_np = 0, best_span = 1 << 30;
-  for (int np = pg.n_q / 2; np >= 0; --np) {
-    const int span = makespan(pg.BH * np, pg.BH * (pg.n_q - 2 * np), nsm);
-    if (span < best_span) {
-      best_span = span;
-      best_np = np;
-    }
-  }
+  int best_np = attention_pair_items(Tq, pg.BH, nullptr);
   if (force_pairs == -1) best_np = pg.n_q / 2;
   if (force_pairs >= 0 && force_pairs <= pg.n_q / 2) best_np = force_pairs;
   pg.n_pairs = best_np;
@@ -700,6 +691,23 @@ int launch_pair(const void* q, const void* k, const AttnV& v, void* out, int B, 
 }
 
 }  // namespace
+
+int attention_pair_items(int Tq, int BH, int* n_ctas) {
+  // how many tiles of each (batch, head) slice run as pairs: minimal makespan over the SMs, ties -> more pairs (less
+  // L2 traffic)
+  const int n_q = (Tq + BQP - 1) / BQP;
+  const int nsm = num_sms();
+  int best_np = 0, best_span = 1 << 30;
+  for (int np = n_q / 2; np >= 0; --np) {
+    const int span = makespan(BH * np, BH * (n_q - 2 * np), nsm);
+    if (span < best_span) {
+      best_span = span;
+      best_np = np;
+    }
+  }
+  if (n_ctas != nullptr) *n_ctas = BH * (n_q - best_np);
+  return best_np;
+}
 
 int attention_pair_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
                         float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,

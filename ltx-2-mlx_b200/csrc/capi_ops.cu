@@ -135,6 +135,27 @@ int ltx2_x0_from_velocity(const float* latent, const float* velocity, const floa
   return x0_from_velocity(latent, velocity, t_row, x0, M, C, S(stream));
 }
 
+int ltx2_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t max_splits, int32_t* out6) {
+  if (out6 == nullptr || M <= 0 || N <= 0 || K <= 0) {
+    set_error("gemm_plan: bad argument");
+    return LTX2_ERR_INVALID;
+  }
+  const GemmPlan p = plan_gemm(M, N, K, mode, max_splits, 0);
+  out6[0] = p.kernel; out6[1] = p.bn; out6[2] = p.splits; out6[3] = p.tile_w; out6[4] = p.last_w; out6[5] = p.num_t;
+  return LTX2_OK;
+}
+
+int ltx2_attention_plan(int32_t Tq, int32_t BH, int32_t* pairs_per_slice, int32_t* n_ctas) {
+  if (Tq <= 0 || BH <= 0 || pairs_per_slice == nullptr) {
+    set_error("attention_plan: bad argument");
+    return LTX2_ERR_INVALID;
+  }
+  int n = 0;
+  *pairs_per_slice = attention_pair_items(Tq, BH, &n);
+  if (n_ctas != nullptr) *n_ctas = n;
+  return LTX2_OK;
+}
+
 int ltx2_denoise_update(const float* sample, const float* cond_x0, const float* uncond_x0, float cfg_scale,
                         const float* denoise_mask, const float* clean_latent, float sigma, float sigma_next, float* out,
                         float* denoised_out, int32_t M, int32_t C, void* stream) {

@@ -753,22 +753,16 @@ int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int 
 
 }  // namespace
 
-int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
-              cudaStream_t stream) {
-  LTX2_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  LTX2_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
-  LTX2_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16 B rows)");
-  LTX2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
-               "gemm: operands must be 16-byte aligned");
-  LTX2_REQUIRE(ep.out != nullptr || ep.n_out_peers > 0, "gemm: null output");
+GemmPlan plan_gemm(int M, int N, int K, int mode, int max_splits, int n_out_peers) {
+  GemmPlan p;
   // BN=256 fills the tensor pipe best; fall back to narrower tiles when N is small or when 128x256 tiles would
   // leave most SMs idle.  The residual epilogue accumulates with reductions, so there the K loop is split instead.
   int bn = 256, splits = 1;
   const int num_kb = (K + BK - 1) / BK;
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
-  if (N % 256 == 0 && ep.mode == GEMM_EPI_F32_RESIDUAL && ep.max_splits > 1 && tiles256 < num_sms()) {
+  if (N % 256 == 0 && mode == GEMM_EPI_F32_RESIDUAL && max_splits > 1 && tiles256 < num_sms()) {
     splits = num_sms() / tiles256;
-    if (splits > ep.max_splits) splits = ep.max_splits;
+    if (splits > max_splits) splits = max_splits;
     if (splits > 8) splits = 8;
     while (splits > 1 && num_kb / splits < 8) --splits;     // keep >= 8 K blocks (512 of K) per slice
     if (splits < 1) splits = 1;
@@ -803,17 +797,17 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
     const long kb_std = (num_kb + splits - 1) / splits;
     const long items_std = static_cast<long>((M + BM - 1) / BM) * ((N + bn - 1) / bn) * splits;
     const long cost_std = ((items_std + nsm - 1) / nsm) * item_cost(kb_std, 4 * (bn / 2), (BM + bn) * BK * 2, 1500);
-    const bool may_split = ep.mode == GEMM_EPI_F32_RESIDUAL && ep.max_splits > 1;
+    const bool may_split = mode == GEMM_EPI_F32_RESIDUAL && max_splits > 1;
     // transposed 1-CTA
     long best_t = -1;
     int t_nt = 0, t_num = 0, t_splits = 1;
-    if (N % BM == 0 && ep.n_out_peers == 0 && !(envt && envt[0] == '0')) {
-      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 16; ++num_t) {
+    if (N % BM == 0 && n_out_peers == 0 && !(envt && envt[0] == '0')) {
+      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 64; ++num_t) {
         const int nt = (((M + num_t - 1) / num_t) + 15) & ~15;
         if (nt > 256 || static_cast<long>(nt) * (num_t - 1) >= M) continue;
         const long base = static_cast<long>(N / BM) * num_t;
         for (int sp = 1; sp <= (may_split ? 8 : 1); ++sp) {
-          if (sp > 1 && (sp > ep.max_splits || num_kb / sp < 8)) break;
+          if (sp > 1 && (sp > max_splits || num_kb / sp < 8)) break;
           const long cost = ((base * sp + nsm - 1) / nsm) *
                             item_cost((num_kb + sp - 1) / sp, 4 * (nt / 2), (BM + nt) * BK * 2, 2500);
           if (best_t < 0 || cost < best_t) {
@@ -828,9 +822,9 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
     // pair (2-CTA) kernel: no split-K
     long best_p = -1;
     int p_tw = 0;
-    if (N % 256 == 0 && ep.n_out_peers == 0 && splits == 1 && M >= 64 && !(env2 && env2[0] == '0')) {
+    if (N % 256 == 0 && n_out_peers == 0 && splits == 1 && M >= 64 && !(env2 && env2[0] == '0')) {
       const int pairs = nsm / 2;
-      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 16; ++num_t) {
+      for (int num_t = (M + 255) / 256; num_t <= (M + 63) / 64 && num_t <= 64; ++num_t) {
         const int tw = (((M + num_t - 1) / num_t) + 31) & ~31;
         if (tw > 256 || static_cast<long>(tw) * (num_t - 1) >= M) continue;
         const int lw = std::min(tw, (M - (num_t - 1) * tw + 31) & ~31);
@@ -847,26 +841,57 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
       }
     }
     const bool force_t = envt && envt[0] == '2', force_p = env2 && env2[0] == '2';
-    const bool wide_bf16 = (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) && N >= 8192 && M <= 2048;
+    const bool wide_bf16 = (mode == GEMM_EPI_BF16 || mode == GEMM_EPI_BF16_GELU) && N >= 8192 && M <= 2048;
     const bool take_p = best_p > 0 && (force_p || (!force_t && wide_bf16 && best_p * 10 < cost_std * 9 &&
                                                    (best_t < 0 || best_p <= best_t)));
     const bool take_t = !take_p && best_t > 0 && (force_t || (wide_bf16 && best_t * 10 < cost_std * 9));
     if (take_p) {
       const int num_t = (M + p_tw - 1) / p_tw;
-      const int lw = std::min(p_tw, (M - (num_t - 1) * p_tw + 31) & ~31);
-      const CUtensorMap *tw, *txf, *txl;
-      LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
-      LTX2_PROPAGATE(get_tensor_map_2d(&txf, A, M, K, lda, p_tw / 2));
-      LTX2_PROPAGATE(get_tensor_map_2d(&txl, A, M, K, lda, lw / 2));
-      return launch_gemm2(tw, txf, txl, M, N, K, p_tw, ep, stream);
+      p.kernel = GEMM_KERNEL_PAIR;
+      p.tile_w = p_tw;
+      p.last_w = std::min(p_tw, (M - (num_t - 1) * p_tw + 31) & ~31);
+      p.num_t = num_t;
+      p.splits = 1;
+      return p;
     }
     if (take_t) {
-      const CUtensorMap *tw, *tx;
-      LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, BM));
-      LTX2_PROPAGATE(get_tensor_map_2d(&tx, A, M, K, lda, t_nt));
-      return launch_gemm_t(tw, tx, M, N, K, t_nt, t_num, t_splits, ep, stream);
+      p.kernel = GEMM_KERNEL_TRANSPOSED;
+      p.tile_w = t_nt;
+      p.last_w = std::min(t_nt, M - (t_num - 1) * t_nt);
+      p.num_t = t_num;
+      p.splits = t_splits;
+      return p;
     }
   }
+  p.kernel = GEMM_KERNEL_STANDARD;
+  p.bn = bn;
+  p.splits = splits;
+  return p;
+}
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t stream) {
+  LTX2_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  LTX2_REQUIRE(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  LTX2_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16 B rows)");
+  LTX2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  LTX2_REQUIRE(ep.out != nullptr || ep.n_out_peers > 0, "gemm: null output");
+  const GemmPlan plan = plan_gemm(M, N, K, ep.mode, ep.max_splits, ep.n_out_peers);
+  if (plan.kernel == GEMM_KERNEL_PAIR) {
+    const CUtensorMap *tw, *txf, *txl;
+    LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
+    LTX2_PROPAGATE(get_tensor_map_2d(&txf, A, M, K, lda, plan.tile_w / 2));
+    LTX2_PROPAGATE(get_tensor_map_2d(&txl, A, M, K, lda, plan.last_w / 2));
+    return launch_gemm2(tw, txf, txl, M, N, K, plan.tile_w, ep, stream);
+  }
+  if (plan.kernel == GEMM_KERNEL_TRANSPOSED) {
+    const CUtensorMap *tw, *tx;
+    LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, BM));
+    LTX2_PROPAGATE(get_tensor_map_2d(&tx, A, M, K, lda, plan.tile_w));
+    return launch_gemm_t(tw, tx, M, N, K, plan.tile_w, plan.num_t, plan.splits, ep, stream);
+  }
+  const int bn = plan.bn, splits = plan.splits;
   const CUtensorMap *ta, *tb;
   LTX2_PROPAGATE(get_tensor_map_2d(&ta, A, M, K, lda, BM));
   LTX2_PROPAGATE(get_tensor_map_2d(&tb, W, N, K, ldw, bn));

@@ -35,6 +35,17 @@ struct GemmEpilogue {
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
               cudaStream_t stream);
 
+// Which kernel and tiling gemm_bf16 takes for a problem (pure host logic: needs no GPU, uses 148 SMs when no device
+// is visible).  standard: 128 token rows x bn columns, K split `splits` ways;  transposed: 128 weight rows x tile_w
+// tokens (last tile last_w), num_t token tiles, K split `splits` ways;  pair: SM pairs, 256 weight rows x tile_w tokens.
+enum GemmKernel { GEMM_KERNEL_STANDARD = 0, GEMM_KERNEL_TRANSPOSED = 1, GEMM_KERNEL_PAIR = 2 };
+struct GemmPlan {
+  int kernel = GEMM_KERNEL_STANDARD;
+  int bn = 256, splits = 1;
+  int tile_w = 0, last_w = 0, num_t = 0;
+};
+GemmPlan plan_gemm(int M, int N, int K, int mode, int max_splits, int n_out_peers);
+
 // ---------------------------------------------------------------------------------
 // attention (attention_sm100.cu):  O = softmax(Q K^T * scale) V, no mask
 //   q  [B,H,Tq,Dh] bf16, k [B,H,Tk,Dh] bf16, vt [B,H,Dh,Tkp] bf16 (V transposed, pitch Tkp >= Tk, Tkp % 8 == 0)
@@ -66,6 +77,11 @@ int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, in
 
 // head_dim 128 only: two softmax streams per CTA (attention_pair_sm100.cu); attention_bf16_v dispatches to it.
 // trace (diagnostics): CTA 0 writes clock64 stamps to trace[16 * key_blocks].
+// Work items of the two-stream attention kernel for Tq queries and BH (batch x head) slices: pair items per slice
+// (two 128-query tiles sharing K/V) -- the remaining tiles run as split-KV items -- chosen for the smallest makespan
+// over the SMs (pure host logic).
+int attention_pair_items(int Tq, int BH, int* n_ctas);
+
 int attention_pair_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
                         float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
                         const AttnOutScatter& sc);
