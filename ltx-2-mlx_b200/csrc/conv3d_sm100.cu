@@ -36,6 +36,7 @@ template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, ConvParams p) {
   using Cfg = ConvCfg<BN>;
+  pdl_trigger();                                     // programmatic dependent launch, see common.cuh
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -78,6 +79,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                        // the set-up above overlapped the previous kernel's tail
 
   if (warp == 0) {
     const bool leader = elect_one();
@@ -257,8 +259,7 @@ int launch_conv(const CUtensorMap& tx, const CUtensorMap* tw, const ConvParams& 
   }
   const int tiles = p.B * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW) * ((p.Cout_pad + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv3d_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tx, *tw, p);
-  LTX2_CUDA_CHECK(cudaGetLastError());
+  LTX2_CUDA_CHECK(launch_pdl(conv3d_kernel<BN>, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, stream, tx, *tw, p));
   count_launch();
   return LTX2_OK;
 }

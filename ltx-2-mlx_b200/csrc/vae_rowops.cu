@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256)
 norm_act_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, int H, int W, int C,
                     int P, int act, const float* __restrict__ mod, int mod_stride, int shift_off, int scale_off,
                     float eps, int causal) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;                       // (b*(T+2) + tp)*(H+2) + hp
   const int hp = row % (H + 2);
   const int tp = (row / (H + 2)) % (T + 2);
@@ -278,10 +280,10 @@ int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, in
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const int ms = static_cast<int>(mod_stride), so = static_cast<int>(shift_off), sc = static_cast<int>(scale_off);
   switch (U) {
-    case 1: norm_act_pad_kernel<1><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
-    case 2: norm_act_pad_kernel<2><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
-    case 3: norm_act_pad_kernel<3><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
-    case 4: norm_act_pad_kernel<4><<<rows, 256, 0, stream>>>(xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal); break;
+    case 1: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<1>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
+    case 2: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<2>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
+    case 3: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<3>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
+    case 4: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<4>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
     default: set_error("norm_act_pad: C=%d unsupported", C); return LTX2_ERR_INVALID;
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
