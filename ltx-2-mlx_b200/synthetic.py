@@ -258,6 +258,31 @@ def iter_vae_weights(cfg: VaeConfig, seed: int = 0, device="cpu", dtype=torch.fl
         yield from _linear(T + ".linear_2", 2 * cf, 256, seed, device, dtype)
 
 
+def iter_vae_encoder_weights(seed: int = 0, device="cpu", dtype=torch.float32, channel_div: int = 1
+                             ) -> Iterator[Tuple[str, torch.Tensor]]:
+    """Yield (checkpoint_key, tensor) for the video-VAE ENCODER under the key names `load_vae_encoder_weights` reads
+    (simple_encoder.py:408-528).  The reference encoder's widths are fixed (128 .. 1024); `channel_div` > 1 only serves
+    block-level tests."""
+    L = 128
+    yield "vae.per_channel_statistics.mean-of-means", _normal("vae.mom", (L,), 0.1, 0.0, seed, device, torch.float32)
+    yield "vae.per_channel_statistics.std-of-means", _normal("vae.som", (L,), 0.05, 1.0, seed, device, torch.float32)
+    d = channel_div
+    yield from _conv3d("vae.encoder.conv_in.conv", 128 // d, 48, seed, device, dtype)
+    blocks = [("res", 128, 4, None), ("down", 128, 256, (1, 2, 2)), ("res", 256, 6, None), ("down", 256, 512, (2, 1, 1)),
+              ("res", 512, 6, None), ("down", 512, 1024, (2, 2, 2)), ("res", 1024, 2, None),
+              ("down", 1024, 1024, (2, 2, 2)), ("res", 1024, 2, None)]
+    for idx, (kind, c_in, n_or_cout, stride) in enumerate(blocks):
+        P = f"vae.encoder.down_blocks.{idx}"
+        if kind == "res":
+            for j in range(n_or_cout):
+                yield from _conv3d(f"{P}.res_blocks.{j}.conv1.conv", c_in // d, c_in // d, seed, device, dtype)
+                yield from _conv3d(f"{P}.res_blocks.{j}.conv2.conv", c_in // d, c_in // d, seed, device, dtype)
+        else:
+            sp = stride[0] * stride[1] * stride[2]
+            yield from _conv3d(f"{P}.conv.conv", n_or_cout // d // sp, c_in // d, seed, device, dtype)
+    yield from _conv3d("vae.encoder.conv_out.conv", 129, 1024 // d, seed, device, dtype)
+
+
 def dit_weights(cfg: DitConfig, seed: int = 0, device="cpu", dtype=torch.float32) -> Dict[str, torch.Tensor]:
     return dict(iter_dit_weights(cfg, seed, device, dtype))
 

@@ -282,6 +282,35 @@ def golden_ops():
     print("ops", y_nc.shape, un.shape, d2s.shape)
 
 
+def golden_vae_encoder():
+    """The reference's SimpleVideoEncoder at its fixed widths (128..1024 channels), weights through its own loader,
+    on a 9-frame 32x32 clip and a single 64x32 image: (1,3,9,32,32) -> (1,128,2,1,1), (1,3,1,64,32) -> (1,128,1,2,1)."""
+    ref_enc = importlib.import_module("LTX_2_MLX.model.video_vae.simple_encoder")
+    w = dict(synthetic.iter_vae_encoder_weights(seed=11))
+    enc = ref_enc.SimpleVideoEncoder()
+    from safetensors.torch import save_file
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "enc.safetensors")
+        save_file({k: v.contiguous() for k, v in w.items()}, path)
+        ref_enc.load_vae_encoder_weights(enc, path)       # the reference's own loader
+    clip = np.clip(rnd((1, 3, 9, 32, 32), 70, 0.5), -1, 1).astype(np.float32)
+    image = np.clip(rnd((1, 3, 1, 64, 32), 71, 0.5), -1, 1).astype(np.float32)
+    lat_clip = A(enc(mx.array(clip), show_progress=False))
+    lat_image = A(enc(mx.array(image), show_progress=False))
+    # building blocks on small tensors (channel order of patchify / space-to-depth, group-mean residual)
+    x = rnd((1, 3, 2, 8, 12), 72)
+    pat = A(ref_ops.patchify(mx.array(x), patch_size_hw=4, patch_size_t=1))
+    down = ref_enc.SpaceToDepthDownsample3d(8, 16, stride=(2, 2, 2))
+    dw, db = rnd((2, 8, 3, 3, 3), 73, 0.1), rnd((2,), 74, 0.1)
+    down.conv.weight, down.conv.bias = mx.array(dw), mx.array(db)
+    dx = rnd((1, 8, 3, 4, 6), 75)
+    dy = A(down(mx.array(dx), causal=True))
+    np.savez_compressed(os.path.join(HERE, "vae_encoder.npz"), clip=clip, image=image, latent_clip=lat_clip,
+                        latent_image=lat_image, weight_checksum=checksum(w), patchify_x=x, patchify_y=pat,
+                        down_w=dw, down_b=db, down_x=dx, down_y=dy)
+    print("vae_encoder", lat_clip.shape, lat_image.shape, pat.shape, dy.shape)
+
+
 def _ref_function(path, name):
     """Compile ONE function of a reference file that cannot be imported as a module here (pipelines/common.py pulls
     in PIL, the encoder, ...): its source text is taken from the reference file at run time and executed as is."""
@@ -320,9 +349,13 @@ def golden_sampling():
 
 
 if __name__ == "__main__":
+    if "--encoder-only" in sys.argv:
+        golden_vae_encoder()
+        sys.exit(0)
     golden_sampling()
     if "--sampling-only" in sys.argv:
         sys.exit(0)
+    golden_vae_encoder()
     golden_ops()
     golden_rope()
     golden_dit_v1()
