@@ -283,6 +283,32 @@ def iter_vae_encoder_weights(seed: int = 0, device="cpu", dtype=torch.float32, c
     yield from _conv3d("vae.encoder.conv_out.conv", 129, 1024 // d, seed, device, dtype)
 
 
+def iter_upscaler_weights(seed: int = 0, device="cpu", dtype=torch.float32, in_channels: int = 128,
+                          mid_channels: int = 1024, blocks: int = 4) -> Iterator[Tuple[str, torch.Tensor]]:
+    """Yield (checkpoint_key, tensor) for the 2x latent spatial upscaler under the key names
+    `load_spatial_upscaler_weights` reads (model/upscaler/spatial.py:414-538)."""
+    def conv(prefix, c_out, c_in):
+        w = _normal(prefix + ".weight", (c_out, c_in, 3, 3, 3), 1.0 / math.sqrt(27 * c_in), 0.0, seed, device, dtype)
+        return [(prefix + ".weight", w), (prefix + ".bias", _normal(prefix + ".bias", (c_out,), 0.02, 0.0, seed, device, dtype))]
+
+    def norm(prefix, c):
+        return [(prefix + ".weight", _normal(prefix + ".weight", (c,), 0.1, 1.0, seed, device, torch.float32)),
+                (prefix + ".bias", _normal(prefix + ".bias", (c,), 0.05, 0.0, seed, device, torch.float32))]
+
+    yield from conv("initial_conv", mid_channels, in_channels)
+    yield from norm("initial_norm", mid_channels)
+    for stage in ("res_blocks", "post_upsample_res_blocks"):
+        for i in range(blocks):
+            yield from conv(f"{stage}.{i}.conv1", mid_channels, mid_channels)
+            yield from norm(f"{stage}.{i}.norm1", mid_channels)
+            yield from conv(f"{stage}.{i}.conv2", mid_channels, mid_channels)
+            yield from norm(f"{stage}.{i}.norm2", mid_channels)
+    yield "upsampler.conv.weight", _normal("upsampler.conv.weight", (4 * mid_channels, mid_channels, 3, 3),
+                                           1.0 / math.sqrt(9 * mid_channels), 0.0, seed, device, dtype)
+    yield "upsampler.conv.bias", _normal("upsampler.conv.bias", (4 * mid_channels,), 0.02, 0.0, seed, device, dtype)
+    yield from conv("final_conv", in_channels, mid_channels)
+
+
 def dit_weights(cfg: DitConfig, seed: int = 0, device="cpu", dtype=torch.float32) -> Dict[str, torch.Tensor]:
     return dict(iter_dit_weights(cfg, seed, device, dtype))
 

@@ -165,6 +165,10 @@ def pad(a, pad_width, constant_values=0):
     return _wrap(np.pad(_np(a), pad_width, constant_values=constant_values))
 
 
+def all(a, axis=None, keepdims=False):  # noqa: A001
+    return _wrap(np.all(_np(a), axis=axis, keepdims=keepdims))
+
+
 def mean(a, axis=None, keepdims=False):
     return _wrap(np.mean(_np(a), axis=axis, keepdims=keepdims, dtype=np.float32))
 

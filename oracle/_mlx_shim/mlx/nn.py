@@ -81,6 +81,23 @@ class LayerNorm(Module):
         return mx._wrap(y)
 
 
+class GroupNorm(Module):
+    """Parameter container only: the reference's upscaler stores weight/bias here and applies the normalisation itself
+    (model/upscaler/spatial.py:91-128 group_norm_5d); calling it is not part of any restated path."""
+
+    def __init__(self, num_groups, dims, eps=1e-5, affine=True, pytorch_compatible=False):
+        super().__init__()
+        self.num_groups = num_groups
+        self.dims = dims
+        self.eps = eps
+        if affine:
+            self.weight = mx.ones((dims,))
+            self.bias = mx.zeros((dims,))
+
+    def __call__(self, x):
+        raise NotImplementedError("mlx shim: nn.GroupNorm.__call__ is not restated (unused by the reference paths)")
+
+
 def silu(x):
     x = np.asarray(x)
     return mx._wrap(x / (1.0 + np.exp(-x)))

@@ -311,6 +311,25 @@ def golden_vae_encoder():
     print("vae_encoder", lat_clip.shape, lat_image.shape, pat.shape, dy.shape)
 
 
+def golden_upscaler():
+    """The reference's SpatialUpscaler (64 mid channels, 8 groups, 2 blocks per stage to keep the fixture small; the
+    class takes these as constructor arguments), weights through its own loader: (1,16,3,4,5) -> (1,16,3,8,10)."""
+    ref_up = importlib.import_module("LTX_2_MLX.model.upscaler.spatial")
+    cin, mid, groups, blocks = 16, 64, 8, 2
+    w = dict(synthetic.iter_upscaler_weights(seed=13, in_channels=cin, mid_channels=mid, blocks=blocks))
+    up = ref_up.SpatialUpscaler(in_channels=cin, mid_channels=mid, num_blocks_per_stage=blocks, num_groups=groups)
+    from safetensors.torch import save_file
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "up.safetensors")
+        save_file({k: v.contiguous() for k, v in w.items()}, path)
+        ref_up.load_spatial_upscaler_weights(up, path)
+    lat = rnd((1, cin, 3, 4, 5), 80)
+    out = A(up(mx.array(lat)))
+    np.savez_compressed(os.path.join(HERE, "upscaler.npz"), latent=lat, upscaled=out, weight_checksum=checksum(w),
+                        cfg=np.asarray([cin, mid, groups, blocks]))
+    print("upscaler", out.shape)
+
+
 def _ref_function(path, name):
     """Compile ONE function of a reference file that cannot be imported as a module here (pipelines/common.py pulls
     in PIL, the encoder, ...): its source text is taken from the reference file at run time and executed as is."""
@@ -349,6 +368,9 @@ def golden_sampling():
 
 
 if __name__ == "__main__":
+    if "--upscaler-only" in sys.argv:
+        golden_upscaler()
+        sys.exit(0)
     if "--encoder-only" in sys.argv:
         golden_vae_encoder()
         sys.exit(0)
@@ -356,6 +378,7 @@ if __name__ == "__main__":
     if "--sampling-only" in sys.argv:
         sys.exit(0)
     golden_vae_encoder()
+    golden_upscaler()
     golden_ops()
     golden_rope()
     golden_dit_v1()
