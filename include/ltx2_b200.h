@@ -85,6 +85,13 @@ typedef struct LtxModalityView {
   int32_t context_tokens;    /* S */
   int32_t n_t;               /* 1 or N */
   int32_t n_dims;            /* 3 video, 1 audio */
+  /* Optional pre-computed timestep classes (n_cls > 0): `timesteps` then holds the n_cls DISTINCT (batch, sigma) values
+   * and row_cls[B*N] maps every token row to its class.  The per-token form (n_t == N) makes the engine read the
+   * timesteps back and de-duplicate them on the host every call; a sampling loop whose denoise mask is fixed builds
+   * the map once and only rescales the class values per step (ltx-2-mlx_b200/sampling.py), so the forward never
+   * synchronises with the host.  Same result as timesteps[b,t] = class_value[row_cls[b,t]]. */
+  const int32_t* row_cls;    /* [B * N] or NULL */
+  int32_t n_cls;             /* 0 = not given; <= 64 */
 } LtxModalityView;
 
 int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out);
@@ -121,6 +128,19 @@ int ltx2_dit_forward(LtxDit* dit, const LtxModalityView* video, const LtxModalit
                      const LtxDitSkip* skip /* nullable */, int32_t x0, float* out_video, float* out_audio /* nullable */,
                      void* stream);
 
+/* Text-context reuse across denoising steps.  In the V1 model the text context is sigma-independent
+ * (transformer.py:427-455: K/V come from the caption-projected context without modulation), so the caption projection
+ * and the 48 text K/V projections + k-norm are identical for every step of a sample.  A caller that passes the SAME
+ * context contents again may say so with a non-zero tag: when the tag, batch and S match the previous forward, the
+ * engine reuses the cached projected K/V (per block: K [B,H,S,Dh] after k-norm, V rows) instead of recomputing them.
+ * tag 0 (default) = never reuse.  Ignored for cross_attention_adaln models (their K/V depend on sigma).  The host layer
+ * derives the tag from the identity and version counter of the caller's context tensor. */
+int ltx2_dit_set_context_tag(LtxDit* dit, uint64_t tag);
+
+/* Diagnostics (bench.py parity leg): run only the first `n` transformer blocks (then the output head); n <= 0 or
+ * n >= num_layers restores the full model. */
+int ltx2_dit_set_layer_limit(LtxDit* dit, int32_t n);
+
 /* OneStagePipeline pokes block._cross_attn_scale (one_stage.py:207-222; transformer.py:526-528). */
 int ltx2_dit_set_cross_attn_scale(LtxDit* dit, int32_t block, float scale /* NaN = unset */);
 
@@ -140,10 +160,18 @@ int64_t ltx2_launch_count(void);
  *   3. ltx2_dit_forward is then called with the LOCAL token slice (tokens = N/P) on every rank, collectively.
  * When context_tokens (S) is given and S % P == 0, the text-context K/V projection of every block is also sharded:
  * each rank projects S/P context rows and its GEMM epilogue stores them into all ranks' buffers.
- * Round-1 limits: video-only, non-gated model (LTX-2 19B), N % P == 0, H % P == 0, P <= 8. */
+ * The audio+video (V2.3) model is supported as well: the audio stream is replicated, the v2a keys/values are projected
+ * per token slice and broadcast to all ranks.  Limits: N % P == 0, H % P == 0, P <= 8. */
 int ltx2_dit_cp_init(LtxDit* dit, int32_t rank, int32_t world, int32_t batch, int32_t n_total, int32_t context_tokens,
                      char* handle_out);
 int ltx2_dit_cp_connect(LtxDit* dit, const char* handles);
+/* Orderly teardown: phase 0 on every rank (close the imported peer mappings), a host barrier, then phase 1 (free the own
+ * exchange region; the engine is single-GPU again).  An exported allocation must not be freed while a peer maps it. */
+int ltx2_dit_cp_shutdown(LtxDit* dit, int32_t phase);
+/* Split-K cap of the residual GEMMs on sharded ranks (their M = N/P rows do not fill the SMs otherwise): 1 = off -- the
+ * sharded forward is then BIT-IDENTICAL to the single-GPU forward (bench.py cp_parity, tests/test_cp_gpu.py) --,
+ * 0 = default (8, or the LTX2_CP_SPLIT_K environment variable). */
+int ltx2_dit_cp_set_split_k(LtxDit* dit, int32_t max_splits);
 
 /* =====================================================================================
  * Video-VAE decoder engine -- replaces LTX_2_MLX/model/video_vae/simple_decoder.py:
@@ -186,6 +214,16 @@ int ltx2_vae_output_shape(LtxVae* vae, const int64_t in_shape[5], int64_t out_sh
  * timestep conditioning is on (:496-498); pass NULL or s = 0 for the deterministic decode the parity test uses. */
 int ltx2_vae_decode(LtxVae* vae, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream);
+
+/* Conv3dSimple.__call__ (simple_decoder.py:90-180) as one op, for unit parity of the implicit-GEMM conv kernel at
+ * production shapes: x [B,T,H,W,Cin] bf16 channels-last, weight in PyTorch layout [Cout,Cin,3,3,3] and bias [Cout]
+ * (dtype codes), out [B,T,H,W,Cout] bf16.  Padding as in the decoder: reflect H/W, replicate T (causal: frame 0 twice
+ * in front, nothing behind).  workspace: >= ltx2_conv3d_workspace_bytes(...) bytes of device memory (padded input,
+ * packed weight, packed bias).  C_in % 64 == 0, C_out % 8 == 0. */
+int64_t ltx2_conv3d_workspace_bytes(int32_t B, int32_t T, int32_t H, int32_t W, int32_t Cin, int32_t Cout);
+int ltx2_conv3d(const void* x, const void* weight, int32_t w_dtype, const void* bias, int32_t b_dtype, void* out,
+                int32_t B, int32_t T, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t causal, void* workspace,
+                void* stream);
 
 /* Measurement hooks (bench.py): CUDA-event timing of the conv launches of one decode. */
 int ltx2_vae_set_profile(LtxVae* vae, int32_t on);

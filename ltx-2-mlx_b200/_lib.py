@@ -38,6 +38,7 @@ class LtxModalityView(C.Structure):
         ("latent", C.c_void_p), ("latent_dtype", C.c_int32), ("context", C.c_void_p), ("context_dtype", C.c_int32),
         ("timesteps", C.c_void_p), ("sigma", C.c_void_p), ("positions", C.c_void_p), ("batch", C.c_int32),
         ("tokens", C.c_int32), ("context_tokens", C.c_int32), ("n_t", C.c_int32), ("n_dims", C.c_int32),
+        ("row_cls", C.c_void_p), ("n_cls", C.c_int32),
     ]
 
 
@@ -56,35 +57,85 @@ class LtxVaeConfig(C.Structure):
                 ("latent_channels", C.c_int32), ("timestep_conditioning", C.c_int32)]
 
 
-# every symbol include/ltx2_b200.h declares; tests check the library exports all of them
-EXPORTS = [
-    "ltx2_version", "ltx2_last_error",
-    "ltx2_dit_create", "ltx2_dit_destroy", "ltx2_dit_set_weight", "ltx2_dit_missing_weights", "ltx2_dit_weight_keys", "ltx2_dit_weight_shape", "ltx2_dit_get_weight", "ltx2_dit_forward",
-    "ltx2_dit_set_cross_attn_scale", "ltx2_dit_cp_init", "ltx2_dit_cp_connect", "ltx2_dit_set_profile", "ltx2_dit_profile_read", "ltx2_launch_count",
-    "ltx2_vae_create", "ltx2_vae_destroy", "ltx2_vae_set_weight", "ltx2_vae_missing_weights", "ltx2_vae_output_shape",
-    "ltx2_vae_decode", "ltx2_vae_set_profile", "ltx2_vae_profile_read", "ltx2_blend_chunk", "ltx2_video_to_uint8", "ltx2_tile_accumulate", "ltx2_tile_normalize",
-    "ltx2_gemm_bf16", "ltx2_gemm_bf16_splitk", "ltx2_attention", "ltx2_attention_trace", "ltx2_attention_vrows", "ltx2_norm_modulate", "ltx2_headnorm_rope", "ltx2_v_transpose",
-    "ltx2_rope_tables", "ltx2_timestep_sinusoid", "ltx2_small_linear", "ltx2_x0_from_velocity", "ltx2_denoise_update", "ltx2_gemm_plan", "ltx2_attention_plan", "ltx2_silu_mul",
-    "ltx2_gelu_mul", "ltx2_interleaved_rope", "ltx2_cast",
-]
+# Every symbol include/ltx2_b200.h declares, with its C signature (restype, argtypes).  Declaring them once here means
+# ctypes converts Python ints/floats to the right width at every call site (an undeclared `int64_t` argument would be
+# marshalled as a 32-bit int and silently truncated); tests check the library exports all of them.
+_P, _I32, _I64, _U64, _F, _D, _S = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double, C.c_char_p
+SIGNATURES = {
+    "ltx2_version": (_I32, []),
+    "ltx2_last_error": (_S, []),
+    "ltx2_dit_create": (_I32, [_P, _P]),
+    "ltx2_dit_destroy": (None, [_P]),
+    "ltx2_dit_set_weight": (_I32, [_P, _S, _P, _I32, _P, _I32, _P]),
+    "ltx2_dit_weight_keys": (_I64, [_P, _P, _I64]),
+    "ltx2_dit_weight_shape": (_I32, [_P, _S, _P]),
+    "ltx2_dit_get_weight": (_I32, [_P, _S, _P, _I32, _I64, _P]),
+    "ltx2_dit_missing_weights": (_I32, [_P, _P, _I64]),
+    "ltx2_dit_forward": (_I32, [_P, _P, _P, _P, _I32, _P, _P, _P]),
+    "ltx2_dit_set_context_tag": (_I32, [_P, _U64]),
+    "ltx2_dit_set_layer_limit": (_I32, [_P, _I32]),
+    "ltx2_dit_set_cross_attn_scale": (_I32, [_P, _I32, _F]),
+    "ltx2_dit_set_profile": (_I32, [_P, _I32]),
+    "ltx2_dit_profile_read": (_I32, [_P, _P, _P, _P, _I32]),
+    "ltx2_launch_count": (_I64, []),
+    "ltx2_dit_cp_init": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "ltx2_dit_cp_connect": (_I32, [_P, _P]),
+    "ltx2_dit_cp_set_split_k": (_I32, [_P, _I32]),
+    "ltx2_dit_cp_shutdown": (_I32, [_P, _I32]),
+    "ltx2_vae_create": (_I32, [_P, _P]),
+    "ltx2_vae_destroy": (None, [_P]),
+    "ltx2_vae_set_weight": (_I32, [_P, _S, _P, _I32, _P, _I32, _P]),
+    "ltx2_vae_missing_weights": (_I32, [_P, _P, _I64]),
+    "ltx2_vae_output_shape": (_I32, [_P, _P, _P]),
+    "ltx2_vae_decode": (_I32, [_P, _P, _I32, _P, _F, _F, _P, _I32, _P, _P]),
+    "ltx2_conv3d_workspace_bytes": (_I64, [_I32] * 6),
+    "ltx2_conv3d": (_I32, [_P, _P, _I32, _P, _I32, _P] + [_I32] * 7 + [_P, _P]),
+    "ltx2_vae_set_profile": (_I32, [_P, _I32]),
+    "ltx2_vae_profile_read": (_I32, [_P, _P, _P, _P]),
+    "ltx2_blend_chunk": (_I32, [_P, _P] + [_I32] * 6 + [_P]),
+    "ltx2_video_to_uint8": (_I32, [_P, _P, _I32, _I32, _I32, _P]),
+    "ltx2_tile_accumulate": (_I32, [_P, _P, _P] + [_I32] * 13 + [_P, _P, _P, _P]),
+    "ltx2_tile_normalize": (_I32, [_P, _P, _I32, _I64, _P]),
+    "ltx2_gemm_bf16": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _F, _P]),
+    "ltx2_gemm_bf16_splitk": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
+    "ltx2_attention": (_I32, [_P, _P, _P, _P] + [_I32] * 6 + [_F, _P, _P, _P]),
+    "ltx2_attention_vrows": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P] + [_I32] * 5 + [_F, _P, _P, _P]),
+    "ltx2_attention_trace": (_I32, [_P, _P, _P, _P] + [_I32] * 6 + [_F, _P, _P]),
+    "ltx2_norm_modulate": (_I32, [_P, _I32, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _I64, _I64, _P, _P]),
+    "ltx2_headnorm_rope": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
+    "ltx2_v_transpose": (_I32, [_P, _I64, _P] + [_I32] * 5 + [_P]),
+    "ltx2_rope_tables": (_I32, [_P, _I32, _I32, _I32, _I32, _P, _F, _P, _P, _P]),
+    "ltx2_timestep_sinusoid": (_I32, [_P, _I32, _F, _P, _P]),
+    "ltx2_small_linear": (_I32, [_P, _I32, _I32, _P, _P, _P, _I32, _I32, _P]),
+    "ltx2_x0_from_velocity": (_I32, [_P, _P, _P, _P, _I32, _I32, _P]),
+    "ltx2_gemm_plan": (_I32, [_I32] * 5 + [_P]),
+    "ltx2_attention_plan": (_I32, [_I32, _I32, _P, _P]),
+    "ltx2_denoise_update": (_I32, [_P, _P, _P, _F, _P, _P, _F, _F, _P, _P, _I32, _I32, _P]),
+    "ltx2_silu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),
+    "ltx2_gelu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),
+    "ltx2_interleaved_rope": (_I32, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "ltx2_cast": (_I32, [_P, _I32, _P, _I32, _I64, _P]),
+}
+EXPORTS = list(SIGNATURES)
 
 _lib: Optional[C.CDLL] = None
 
 
 def lib() -> C.CDLL:
-    """Load libltx2_b200.so (once).  Raises Ltx2Error if it has not been built."""
+    """Load libltx2_b200.so (once) and declare every export's signature.  Raises Ltx2Error if it has not been built."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise Ltx2Error(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(nvcc, sm_100a). There is no CPU fallback.")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.ltx2_last_error.restype = C.c_char_p
-        _lib.ltx2_dit_destroy.restype = None
-        _lib.ltx2_launch_count.restype = C.c_int64
-        _lib.ltx2_dit_weight_keys.restype = C.c_int64
-        if hasattr(_lib, "ltx2_vae_destroy"):
-            _lib.ltx2_vae_destroy.restype = None
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name, None)
+            if fn is None:
+                raise Ltx2Error(f"{LIB_PATH} does not export {name}: rebuild it (__graft_entry__.build())")
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
     return _lib
 
 

@@ -68,3 +68,24 @@ def enable(model, batch: int, n_total: int, context_tokens: int = 0, group=None)
         torch.cuda.synchronize()
     dist.barrier(group=group)
     model._cp = (rank, world, group, batch, n_total)
+
+
+def set_split_k(model, max_splits: int) -> None:
+    """1 = no split-K in the residual GEMMs (sharded forward bit-identical to the single-GPU one), 0 = default."""
+    from ._lib import check, lib
+    check(lib().ltx2_dit_cp_set_split_k(model._h, int(max_splits)), "ltx2_dit_cp_set_split_k")
+
+
+def disable(model) -> None:
+    """Collective teardown of the exchange region (every rank of the group calls it): close the imported peer mappings,
+    barrier, free the own region.  The model is single-GPU afterwards."""
+    from ._lib import check, lib
+    if model._cp is None:
+        return
+    group = model._cp[2]
+    with torch.cuda.device(model.device):
+        check(lib().ltx2_dit_cp_shutdown(model._h, 0), "ltx2_dit_cp_shutdown")
+        dist.barrier(group=group)
+        check(lib().ltx2_dit_cp_shutdown(model._h, 1), "ltx2_dit_cp_shutdown")
+    dist.barrier(group=group)
+    model._cp = None

@@ -628,14 +628,13 @@ int launch_pair(const void* q, const void* k, const AttnV& v, void* out, int B, 
   const int variant = env_poly ? atoi(env_poly) : 3;
   const char* env_pairs = getenv("LTX2_ATTN_PAIRS");
   const int force_pairs = env_pairs ? atoi(env_pairs) : -2;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<VROWS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<VROWS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<VROWS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<VROWS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_pair_kernel<VROWS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
-    configured = true;
   }
   const uint64_t BH = static_cast<uint64_t>(B) * H;
   CUtensorMap mq, mk, mv;

@@ -381,11 +381,10 @@ int launch_attention(const void* q, const void* k, const AttnV& v, void* out, in
                      float scale, const float* gate_logits, float* lse_out, long long* trace, const AttnOutScatter& sc,
                      cudaStream_t stream) {
   using Cfg = AttnCfg<DH>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DH, VROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    configured = true;
   }
   const uint64_t BH = static_cast<uint64_t>(B) * H;
   CUtensorMap mk, mv;

@@ -96,14 +96,14 @@ int ltx2_v_transpose(const void* v, int64_t ld, void* vt, int32_t B, int32_t T, 
 int ltx2_rope_tables(const float* positions, int32_t B, int32_t n_dims, int32_t T, int32_t dim,
                      const float* max_pos_host, float theta, float* cos, float* sin, void* stream) {
   LTX2_REQUIRE(n_dims >= 1 && n_dims <= 3 && dim % (2 * n_dims) >= 0, "rope_tables: bad n_dims");
-  typedef std::tuple<float, int, int> Key;
+  typedef std::tuple<int, float, int, int> Key;      // the cached grid is a DEVICE pointer: key it by device
   static std::map<Key, float*> cache;
   static std::mutex mu;
   const int n = dim / (2 * n_dims);
   float* dev = nullptr;
   {
     std::lock_guard<std::mutex> lock(mu);
-    Key key(theta, n_dims, dim);
+    Key key(current_device(), theta, n_dims, dim);
     auto it = cache.find(key);
     if (it == cache.end()) {
       std::vector<float> g(n);

@@ -70,31 +70,30 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
   return LTX2_OK;
 }
 
-int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows) {
-  typedef std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t> Key;
-  static std::map<Key, CUtensorMap*> cache;
+  // Encoding a tensor map costs a driver call, so the maps of the (static) weight / workspace buffers are cached.
+  // The descriptor is COPIED out under the lock: callers never hold a pointer into the cache, so the growth guard
+  // below (or a second thread) cannot invalidate a map between two fetches of one launch.
+  typedef std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t> Key;
+  static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  Key key(base, rows, cols, ld, box_rows);
+  Key key(dev, base, rows, cols, ld, box_rows);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
     return LTX2_OK;
   }
-  if (cache.size() > 16384) {  // unbounded growth guard for callers that stream fresh buffers
-    for (auto& kv : cache) delete kv.second;
-    cache.clear();
-  }
-  CUtensorMap* m = new CUtensorMap;
+  if (cache.size() > 16384) cache.clear();  // unbounded growth guard for callers that stream fresh buffers
   uint64_t dims[2] = {cols, rows};
   uint64_t strides[1] = {ld * 2};
   uint32_t box[2] = {64, box_rows};
-  int s = make_tensor_map_bf16(m, base, 2, dims, strides, box);
-  if (s != LTX2_OK) {
-    delete m;
-    return s;
-  }
+  CUtensorMap m;
+  int s = make_tensor_map_bf16(&m, base, 2, dims, strides, box);
+  if (s != LTX2_OK) return s;
   cache[key] = m;
   *out = m;
   return LTX2_OK;
@@ -113,14 +112,21 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace ltx2

@@ -52,10 +52,24 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
                          const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
 
 // cached 2-D row-major [rows, cols] map with row pitch ld (elements), box = [box_rows, 64]
-int get_tensor_map_2d(const CUtensorMap** out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);
 
+// Per-device state: a process may drive several GPUs (DiT on cuda:0, VAE on cuda:1), and
+// cudaFuncSetAttribute / the SM count / cached device pointers are per device.
+constexpr int kMaxDevices = 64;
+int current_device();
 int num_sms();
+// true exactly once per (flag array, current device): guards the per-device cudaFuncSetAttribute opt-ins
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 // Programmatic dependent launch (PDL): the big per-block kernels are launched with the programmatic-stream-serialization
 // attribute, call pdl_trigger() when they start and pdl_wait() before they first touch global memory.  The next kernel's

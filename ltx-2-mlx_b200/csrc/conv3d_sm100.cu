@@ -169,10 +169,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
           v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
         }
         if (p.mode == CONV_EPI_PLAIN || p.mode == CONV_EPI_RESIDUAL) {
+          const int nv = p.Cout - col0;                  // valid columns of this group (C_out % 8 == 0; rows >= C_out are padding)
+          if (nv <= 0) continue;
           if (p.mode == CONV_EPI_RESIDUAL) {
             const __nv_bfloat16* rs = p.residual + pos * p.Cout + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
+              if (j >= nv) break;
               const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
               const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -186,6 +189,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
           __nv_bfloat16* o = p.out + pos * p.Cout + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
+            if (j >= nv) break;
             uint4 q;
             q.x = pack_bf16x2(v[j], v[j + 1]);
             q.y = pack_bf16x2(v[j + 2], v[j + 3]);
@@ -251,11 +255,10 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 template <int BN>
 int launch_conv(const CUtensorMap& tx, const CUtensorMap* tw, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(conv3d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    configured = true;
   }
   const int tiles = p.B * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW) * ((p.Cout_pad + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -287,8 +290,9 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
     const int Cf = p.Cout / (p.ft * p.fh * p.fw);
     LTX2_REQUIRE(Cf % 32 == 0, "conv3d: depth-to-space needs C_out/stride_product %% 32 == 0 (got %d)", Cf);
   }
-  const CUtensorMap* tw;
-  LTX2_PROPAGATE(get_tensor_map_2d(&tw, w_packed, p.Cout_pad, static_cast<uint64_t>(27) * p.Cin,
+  CUtensorMap tw_map;
+  const CUtensorMap* tw = &tw_map;
+  LTX2_PROPAGATE(get_tensor_map_2d(&tw_map, w_packed, p.Cout_pad, static_cast<uint64_t>(27) * p.Cin,
                                    static_cast<uint64_t>(27) * p.Cin, bn));
   switch (bn) {
     case 256: return launch_conv<256>(tx, tw, p, stream);

@@ -225,6 +225,18 @@ struct LtxDit {
   StreamBuf vb, ab;
   float* scratch = nullptr;         // small fp32 scratch for timestep MLPs
   std::vector<float> h_ts;          // host staging for per-token timestep dedupe
+  // text-context reuse across steps (ltx2_dit_set_context_tag): per block K|V projection of the context
+  // [B*S, 2*inner] and the k-normed, head-split K [B,H,S,Dh]; valid for (cached_tag, cached_B, cached_S)
+  uint64_t ctx_tag = 0, cached_tag = 0;
+  int cached_B = 0, cached_S = 0;
+  char* kvc = nullptr;
+  size_t kvc_bytes = 0;
+  bool ctx_cache_on = false, ctx_cache_hit = false;   // state of the forward in flight
+  int layer_limit = 0;              // diagnostics: run only the first n blocks (0 = all)
+  bf16* kvc_kv(int layer, int B, int S) const {
+    return reinterpret_cast<bf16*>(kvc) + size_t(layer) * 3 * size_t(B) * S * D;
+  }
+  bf16* kvc_kh(int layer, int B, int S) const { return kvc_kv(layer, B, S) + size_t(2) * size_t(B) * S * D; }
 };
 
 namespace ltx2 {
@@ -545,6 +557,7 @@ struct AttnCall {
   const bf16* xkv; int64_t ldkv; int Tk;               // key/value-side input [B*Tk, ctx_dim] (== xq for self)
   const float *qcos, *qsin, *kcos, *ksin;              // rope tables or null
   const bf16* kv_pre = nullptr;                        // K|V projection already available ([B*Tk, 2*inner]): skip that GEMM
+  const bf16* kh_pre = nullptr;                        // K already normalised and head-split ([B,H,Tk,Dh]): skip the k-norm
 };
 
 // Attention.__call__ up to (not including) to_out: writes sb.attn [B*Tq, inner]
@@ -576,8 +589,10 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     LTX2_PROPAGATE(qkv_head_scatter(sb.qkv, 3 * inner, w.qnorm, w.knorm, c.qcos, c.qsin, hs, B, c.Tq, H, Dh, eps, st));
   } else {
     LTX2_PROPAGATE(headnorm_rope(qp, ldq, w.qnorm, c.qcos, c.qsin, sb.qh, B, c.Tq, H, Dh, eps, st));
-    LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
+    if (c.kh_pre == nullptr)
+      LTX2_PROPAGATE(headnorm_rope(kp, ldk, w.knorm, c.kcos, c.ksin, sb.kh, B, c.Tk, H, Dh, eps, st));
   }
+  const bf16* kh = c.kh_pre != nullptr ? c.kh_pre : sb.kh;
   // V is consumed in place from the projection output (row form, MN-major MMA operand): no transpose pass
   AttnV av;
   av.ptr = vp;
@@ -597,7 +612,7 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
     gl = sb.gate_logits;
   }
   ProfScope ps(PROF_ATTN, 4.0 * B * H * double(c.Tq) * c.Tk * Dh, st);
-  return attention_bf16_v(sb.qh, sb.kh, av, sb.attn, B, H, c.Tq, c.Tk, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr, st);
+  return attention_bf16_v(sb.qh, kh, av, sb.attn, B, H, c.Tq, c.Tk, Dh, 1.0f / sqrtf((float)Dh), gl, nullptr, st);
 }
 
 }  // namespace
@@ -665,6 +680,7 @@ void ltx2_dit_destroy(LtxDit* e) {
   }
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
+  if (e->kvc) cudaFree(e->kvc);
   if (e->fg_video) cudaFree(e->fg_video);
   if (e->fg_audio) cudaFree(e->fg_audio);
   delete e;
@@ -693,6 +709,7 @@ int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dt
   int r = s.storage == LTX2_BF16 ? cast_to_bf16(data, dtype, s.dst, expect, st)
                                  : cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), expect, st);
   if (r == LTX2_OK) s.loaded = true;
+  e->cached_tag = 0;          // cached context K/V were projected with the old weights (LoRA fuse / restore)
   return r;
 }
 
@@ -771,6 +788,10 @@ int prepare_classes(LtxDit* e, const LtxModalityView& m, int* n_cls, std::vector
   const int B = m.batch, N = m.tokens;
   cls_vals.clear();
   row_cls_host.clear();
+  if (m.n_cls > 0) {         // the caller supplies the classes: nothing to read back
+    *n_cls = m.n_cls;
+    return LTX2_OK;
+  }
   if (m.n_t == 1) {
     *n_cls = B;
     return LTX2_OK;
@@ -804,7 +825,9 @@ struct Prepared {
 int upload_classes(StreamBuf& sb, const LtxModalityView& m, const std::vector<float>& cls_vals,
                    const std::vector<int>& row_cls_host, cudaStream_t st) {
   const int M = m.batch * m.tokens;
-  if (m.n_t == 1) {
+  if (m.n_cls > 0) {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.t_cls, m.timesteps, size_t(m.n_cls) * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (m.n_t == 1) {
     LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.t_cls, m.timesteps, size_t(m.batch) * 4, cudaMemcpyDeviceToDevice, st));
   } else {
     LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.t_cls, cls_vals.data(), cls_vals.size() * 4, cudaMemcpyHostToDevice, st));
@@ -814,7 +837,9 @@ int upload_classes(StreamBuf& sb, const LtxModalityView& m, const std::vector<fl
   fill_row_index_kernel<<<(m.batch * m.context_tokens + 255) / 256, 256, 0, st>>>(sb.ctx_batch,
                                                                                  m.batch * m.context_tokens,
                                                                                  m.context_tokens);
-  if (m.n_t == 1) {
+  if (m.n_cls > 0) {
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.row_cls, m.row_cls, size_t(M) * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (m.n_t == 1) {
     LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.row_cls, sb.row_batch, size_t(M) * 4, cudaMemcpyDeviceToDevice, st));
   } else {
     LTX2_CUDA_CHECK(cudaMemcpyAsync(sb.row_cls, row_cls_host.data(), size_t(M) * 4, cudaMemcpyHostToDevice, st));
@@ -847,6 +872,7 @@ int prepare_stream(LtxDit* e, StreamBuf& sb, const StreamW& w, const LtxModality
       LTX2_CUDA_CHECK(cudaMemcpyAsync(sig, m.sigma, size_t(B) * 4, cudaMemcpyDeviceToDevice, st));
     } else {
       // first token's timestep of every batch element
+      LTX2_REQUIRE(m.n_cls == 0, "timestep classes need Modality.sigma for the prompt adaLN");
       LTX2_CUDA_CHECK(cudaMemcpy2DAsync(sig, 4, m.timesteps, size_t(m.n_t) * 4, 4, B, cudaMemcpyDeviceToDevice, st));
     }
     float* pemb = emb;   // reuse: [B, 2*dim]
@@ -854,11 +880,13 @@ int prepare_stream(LtxDit* e, StreamBuf& sb, const StreamW& w, const LtxModality
     LTX2_PROPAGATE(build_modulation_ex(ptable_arena, int64_t(2) * dim, pemb, int64_t(2) * dim, dim, sb.prompt_mod,
                                        int64_t(B) * 2 * dim, int64_t(2) * dim, L, B, 2, dim, st));
   }
-  // context (caption projection for V1)
+  // context (caption projection for V1); nothing to do when the projected K/V of this context are cached
   const int ctx_ch = w.has_caption ? w.cap1.in : dim;
-  LTX2_PROPAGATE(cast_to_bf16(m.context, m.context_dtype, w.has_caption ? sb.ctx_in : sb.ctx,
-                              int64_t(B) * S * ctx_ch, st));
-  if (w.has_caption) {
+  const bool ctx_cached = !audio_side && e->ctx_cache_on && e->ctx_cache_hit;
+  if (!ctx_cached)
+    LTX2_PROPAGATE(cast_to_bf16(m.context, m.context_dtype, w.has_caption ? sb.ctx_in : sb.ctx,
+                                int64_t(B) * S * ctx_ch, st));
+  if (w.has_caption && !ctx_cached) {
     LTX2_PROPAGATE(linear_bf16(sb.ctx_in, ctx_ch, w.cap1, B * S, sb.ctx_mid, dim, true, st));
     LTX2_PROPAGATE(linear_bf16(sb.ctx_mid, dim, w.cap2, B * S, sb.ctx, dim, false, st));
   }
@@ -883,6 +911,7 @@ int scalar_sigma(const LtxModalityView& m, float* dst, cudaStream_t st) {
   if (m.sigma != nullptr) {
     LTX2_CUDA_CHECK(cudaMemcpyAsync(dst, m.sigma, size_t(m.batch) * 4, cudaMemcpyDeviceToDevice, st));
   } else {
+    LTX2_REQUIRE(m.n_cls == 0, "timestep classes need Modality.sigma for the cross-modal adaLN");
     LTX2_CUDA_CHECK(cudaMemcpy2DAsync(dst, 4, m.timesteps, size_t(m.n_t) * 4, 4, m.batch, cudaMemcpyDeviceToDevice, st));
   }
   return LTX2_OK;
@@ -951,7 +980,7 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
       LTX2_PROPAGATE(gate_scatter(sb.gate_logits, peers, B, N, H, Hl, Nt, cp.rank * cp.n_local, st));
       gl = reinterpret_cast<const float*>(cp.region + cp.off_gate);
     }
-    if (cp.ctx_tokens == S && !v2) {
+    if (cp.ctx_tokens == S && !v2 && !(e->ctx_cache_on && e->ctx_cache_hit)) {
       // text-context K/V for this block: each rank projects S/P context rows and stores the result into EVERY rank's
       // buffer (GEMM epilogue with peer destinations) instead of all ranks repeating the full projection
       const int Sl = S / cp.world;
@@ -1007,8 +1036,27 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, nullptr, 0, 0, 0, nullptr, st));
   }
   AttnCall a{&w.attn2, sb.xn, dim, M, N, ctx, dim, S, nullptr, nullptr, nullptr, nullptr};
-  if (e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !v2 && !skip_self)
+  const bool region_kv = e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !v2 && !skip_self;
+  if (&sb == &e->vb && e->ctx_cache_on) {
+    // V1: the context K/V of this block do not depend on sigma -- computed by the first forward of a sample, reused after
+    bf16* kvl = e->kvc_kv(layer, B, S);
+    bf16* khl = e->kvc_kh(layer, B, S);
+    const AttnW& cw = w.attn2;
+    if (!e->ctx_cache_hit) {
+      if (region_kv) {
+        LTX2_CUDA_CHECK(cudaMemcpyAsync(kvl, e->cp.region + e->cp.off_ckv[layer & 1],
+                                        size_t(B) * S * 2 * cw.inner * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+      } else {
+        LTX2_PROPAGATE(linear_bf16(ctx, dim, cw.kv, B * S, kvl, 2 * cw.inner, false, st));
+      }
+      LTX2_PROPAGATE(headnorm_rope(kvl, 2 * cw.inner, cw.knorm, nullptr, nullptr, khl, B, S, cw.heads, cw.dh,
+                                   c.norm_eps, st));
+    }
+    a.kv_pre = kvl;
+    a.kh_pre = khl;
+  } else if (region_kv) {
     a.kv_pre = reinterpret_cast<const bf16*>(e->cp.region + e->cp.off_ckv[layer & 1]);
+  }
   LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
   return linear_residual(sb.attn, w.attn2.inner, w.attn2.o, M, sb.x, dim, v2 ? mod + 8 * dim : nullptr, ms,
                          sb.row_cls, ca_scale, st);
@@ -1039,7 +1087,11 @@ int run_head(LtxDit* e, StreamBuf& sb, const StreamW& w, const LtxModalityView& 
 int check_view(const LtxModalityView* m, const char* name, int n_dims) {
   LTX2_REQUIRE(m->latent && m->context && m->timesteps && m->positions, "%s modality: null pointer", name);
   LTX2_REQUIRE(m->batch >= 1 && m->tokens >= 1 && m->context_tokens >= 1, "%s modality: empty", name);
-  LTX2_REQUIRE(m->n_t == 1 || m->n_t == m->tokens, "%s modality: timesteps must be (B,) or (B,N)", name);
+  if (m->n_cls > 0) {
+    LTX2_REQUIRE(m->row_cls != nullptr && m->n_cls <= 64, "%s modality: row_cls is null or n_cls > 64", name);
+  } else {
+    LTX2_REQUIRE(m->n_t == 1 || m->n_t == m->tokens, "%s modality: timesteps must be (B,) or (B,N)", name);
+  }
   LTX2_REQUIRE(m->n_dims == n_dims, "%s modality: positions must have %d axes (got %d)", name, n_dims, m->n_dims);
   return LTX2_OK;
 }
@@ -1097,6 +1149,24 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   sh.Na = has_audio ? audio->tokens : 0; sh.Sa = has_audio ? audio->context_tokens : 0;
   sh.n_cls_a = has_audio ? nca : 0;
   LTX2_PROPAGATE(ensure_workspace(e, sh));
+  // text-context reuse (ltx2_dit_set_context_tag)
+  const int n_layers = (e->layer_limit > 0 && e->layer_limit < c.num_layers) ? e->layer_limit : c.num_layers;
+  e->ctx_cache_on = e->ctx_tag != 0 && !c.cross_attention_adaln && n_layers == c.num_layers;
+  e->ctx_cache_hit = false;
+  if (e->ctx_cache_on) {
+    const size_t need = size_t(c.num_layers) * 3 * size_t(sh.B) * sh.S * e->D * sizeof(bf16);
+    if (need > e->kvc_bytes) {
+      if (e->kvc) cudaFree(e->kvc);
+      e->kvc = nullptr; e->kvc_bytes = 0; e->cached_tag = 0;
+      if (cudaMalloc(&e->kvc, need) != cudaSuccess) {
+        set_error("context K/V cache allocation of %zu bytes failed", need);
+        return LTX2_ERR_NOMEM;
+      }
+      e->kvc_bytes = need;
+    }
+    e->ctx_cache_hit = e->cached_tag == e->ctx_tag && e->cached_B == sh.B && e->cached_S == sh.S;
+    e->cached_tag = 0;              // re-validated only when this forward has been enqueued completely
+  }
   StreamBuf& vb = e->vb;
   StreamBuf& ab = e->ab;
   LTX2_PROPAGATE(upload_classes(vb, *video, cls_v, rc_v, st));
@@ -1133,7 +1203,7 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   }
 
   const int D = e->D, Da = e->Da, B = sh.B, N = sh.N, Na = sh.Na;
-  for (int l = 0; l < c.num_layers; ++l) {
+  for (int l = 0; l < n_layers; ++l) {
     const BlockW& w = e->blocks[l];
     const uint64_t bit = uint64_t(1) << l;
     const float cas = isnan(e->cross_attn_scale[l]) ? 1.0f : e->cross_attn_scale[l];
@@ -1204,6 +1274,23 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   }
   LTX2_PROPAGATE(run_head(e, vb, e->vw, *video, x0, out_video, st));
   if (has_audio) LTX2_PROPAGATE(run_head(e, ab, e->aw, *audio, x0, out_audio, st));
+  if (e->ctx_cache_on) {
+    e->cached_tag = e->ctx_tag;
+    e->cached_B = sh.B;
+    e->cached_S = sh.S;
+  }
+  return LTX2_OK;
+}
+
+extern "C" int ltx2_dit_set_context_tag(LtxDit* e, uint64_t tag) {
+  LTX2_REQUIRE(e != nullptr, "dit_set_context_tag: null handle");
+  e->ctx_tag = tag;
+  return LTX2_OK;
+}
+
+extern "C" int ltx2_dit_set_layer_limit(LtxDit* e, int32_t n) {
+  LTX2_REQUIRE(e != nullptr, "dit_set_layer_limit: null handle");
+  e->layer_limit = (n > 0 && n < e->cfg.num_layers) ? n : 0;
   return LTX2_OK;
 }
 
@@ -1283,6 +1370,43 @@ extern "C" int ltx2_dit_cp_init(LtxDit* e, int32_t rank, int32_t world, int32_t 
   cudaIpcMemHandle_t h;
   LTX2_CUDA_CHECK(cudaIpcGetMemHandle(&h, cp.region));
   memcpy(handle_out, &h, 64);
+  return LTX2_OK;
+}
+
+// Orderly teardown of the exchange region.  An exported allocation must not be freed while a peer still maps it, so the
+// host layer calls phase 0 on every rank (close the imported peer mappings), a host barrier, then phase 1 (free the own
+// region; the engine is single-GPU again).
+extern "C" int ltx2_dit_cp_shutdown(LtxDit* e, int32_t phase) {
+  LTX2_REQUIRE(e != nullptr && (phase == 0 || phase == 1), "dit_cp_shutdown: bad argument");
+  CpState& cp = e->cp;
+  if (!cp.region) return LTX2_OK;
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  if (phase == 0) {
+    for (int r = 0; r < cp.world; ++r)
+      if (cp.opened[r]) {
+        cudaIpcCloseMemHandle(cp.peer_base[r]);
+        cp.opened[r] = false;
+        cp.peer_base[r] = nullptr;
+      }
+    cp.connected = false;
+    return LTX2_OK;
+  }
+  cudaFree(cp.region);
+  if (cp.peer_flags_dev) cudaFree(cp.peer_flags_dev);
+  cp = CpState();
+  return LTX2_OK;
+}
+
+// split-K cap of the residual GEMMs on sharded ranks: 1 = off (the sharded forward is then bit-identical to the
+// single-GPU one), 0 = the default (8, or LTX2_CP_SPLIT_K)
+extern "C" int ltx2_dit_cp_set_split_k(LtxDit* e, int32_t max_splits) {
+  LTX2_REQUIRE(e != nullptr && max_splits >= 0 && max_splits <= 16, "dit_cp_set_split_k: bad argument");
+  int k = max_splits;
+  if (k == 0) {
+    k = 8;
+    if (const char* sk = getenv("LTX2_CP_SPLIT_K")) k = std::min(16, std::max(1, atoi(sk)));
+  }
+  e->cp.split_k = k;
   return LTX2_OK;
 }
 

@@ -507,10 +507,9 @@ gemm_t_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
 int launch_gemm_t(const CUtensorMap* tw, const CUtensorMap* tx, int M, int N, int K, int nt, int num_t, int splits,
                   const GemmEpilogue& ep, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm_t_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesT));
-    configured = true;
   }
   const int tiles = (N / BM) * num_t * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -719,10 +718,9 @@ int gemm2_tiles(int M, int N, int tile_w = 256) { return ((M + tile_w - 1) / til
 
 int launch_gemm2(const CUtensorMap* tw, const CUtensorMap* tx128, const CUtensorMap* tx64, int M, int N, int K,
                  int tile_w, const GemmEpilogue& ep, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    configured = true;
   }
   const int tiles = gemm2_tiles(M, N, tile_w);
   const int pairs = num_sms() / 2;
@@ -737,11 +735,10 @@ template <int BN>
 int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int K, int splits, const GemmEpilogue& ep,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -879,27 +876,27 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
   LTX2_REQUIRE(ep.out != nullptr || ep.n_out_peers > 0, "gemm: null output");
   const GemmPlan plan = plan_gemm(M, N, K, ep.mode, ep.max_splits, ep.n_out_peers);
   if (plan.kernel == GEMM_KERNEL_PAIR) {
-    const CUtensorMap *tw, *txf, *txl;
+    CUtensorMap tw, txf, txl;
     LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
     LTX2_PROPAGATE(get_tensor_map_2d(&txf, A, M, K, lda, plan.tile_w / 2));
     LTX2_PROPAGATE(get_tensor_map_2d(&txl, A, M, K, lda, plan.last_w / 2));
-    return launch_gemm2(tw, txf, txl, M, N, K, plan.tile_w, ep, stream);
+    return launch_gemm2(&tw, &txf, &txl, M, N, K, plan.tile_w, ep, stream);
   }
   if (plan.kernel == GEMM_KERNEL_TRANSPOSED) {
-    const CUtensorMap *tw, *tx;
+    CUtensorMap tw, tx;
     LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, BM));
     LTX2_PROPAGATE(get_tensor_map_2d(&tx, A, M, K, lda, plan.tile_w));
-    return launch_gemm_t(tw, tx, M, N, K, plan.tile_w, plan.num_t, plan.splits, ep, stream);
+    return launch_gemm_t(&tw, &tx, M, N, K, plan.tile_w, plan.num_t, plan.splits, ep, stream);
   }
   const int bn = plan.bn, splits = plan.splits;
-  const CUtensorMap *ta, *tb;
+  CUtensorMap ta, tb;
   LTX2_PROPAGATE(get_tensor_map_2d(&ta, A, M, K, lda, BM));
   LTX2_PROPAGATE(get_tensor_map_2d(&tb, W, N, K, ldw, bn));
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, M, N, K, splits, ep, stream);
-    case 128: return launch_gemm<128>(ta, tb, M, N, K, splits, ep, stream);
-    case 64: return launch_gemm<64>(ta, tb, M, N, K, splits, ep, stream);
-    default: return launch_gemm<32>(ta, tb, M, N, K, splits, ep, stream);
+    case 256: return launch_gemm<256>(&ta, &tb, M, N, K, splits, ep, stream);
+    case 128: return launch_gemm<128>(&ta, &tb, M, N, K, splits, ep, stream);
+    case 64: return launch_gemm<64>(&ta, &tb, M, N, K, splits, ep, stream);
+    default: return launch_gemm<32>(&ta, &tb, M, N, K, splits, ep, stream);
   }
 }
 

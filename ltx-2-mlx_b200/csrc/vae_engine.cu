@@ -478,6 +478,38 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   return conv(e->conv_out, xp, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
 }
 
+// Conv3dSimple.__call__ (simple_decoder.py:90-180) as ONE op, for unit parity of the conv kernel at production shapes:
+// pad (reflect H/W, replicate T) -> implicit-GEMM conv -> bias.  The workspace holds the padded input, the packed
+// weight and the packed bias.
+int64_t ltx2_conv3d_workspace_bytes(int32_t B, int32_t T, int32_t H, int32_t W, int32_t Cin, int32_t Cout) {
+  const size_t pad = align256(size_t(B) * (T + 2) * (H + 2) * (W + 2) * Cin * 2);
+  const size_t wt = align256(size_t(pad32(Cout)) * 27 * Cin * 2);
+  return static_cast<int64_t>(pad + wt + align256(size_t(pad32(Cout)) * 4) + 1024);
+}
+
+int ltx2_conv3d(const void* x, const void* weight, int32_t w_dtype, const void* bias, int32_t b_dtype, void* out,
+                int32_t B, int32_t T, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t causal, void* workspace,
+                void* stream) {
+  LTX2_REQUIRE(x && weight && bias && out && workspace, "conv3d: null argument");
+  LTX2_REQUIRE(B >= 1 && T >= 1 && H >= 2 && W >= 2, "conv3d: grid too small (reflect padding needs H, W >= 2)");
+  LTX2_REQUIRE(Cin % 64 == 0 && Cin <= 1024 && Cout % 8 == 0, "conv3d: C_in %% 64 == 0 (<= 1024), C_out %% 8 == 0");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VArena ws;
+  ws.base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  const int Cp = pad32(Cout);
+  bf16* xp = reinterpret_cast<bf16*>(ws.take(size_t(B) * (T + 2) * (H + 2) * (W + 2) * Cin * 2));
+  bf16* wp = reinterpret_cast<bf16*>(ws.take(size_t(Cp) * 27 * Cin * 2));
+  float* bp = reinterpret_cast<float*>(ws.take(size_t(Cp) * 4));
+  LTX2_PROPAGATE(pack_conv_weight(weight, w_dtype, wp, Cout, Cp, Cin, 1, st));
+  LTX2_PROPAGATE(pack_conv_bias(bias, b_dtype, bp, Cout, Cp, 1, st));
+  LTX2_PROPAGATE(norm_act_pad(x, xp, B, T, H, W, Cin, 0, nullptr, 0, 0, 0, 1e-6f, causal, st));
+  ConvParams p;
+  p.B = B; p.T = T; p.H = H; p.W = W;
+  p.Cin = Cin; p.Cout = Cout; p.Cout_pad = Cp;
+  p.mode = CONV_EPI_PLAIN; p.bias = bp; p.out = reinterpret_cast<bf16*>(out);
+  return conv3d_bf16(xp, wp, p, st);
+}
+
 int ltx2_vae_set_profile(LtxVae* e, int32_t on) {
   LTX2_REQUIRE(e != nullptr, "vae_set_profile: null handle");
   e->prof.on = on != 0;

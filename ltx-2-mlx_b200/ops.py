@@ -170,3 +170,18 @@ def interleaved_rope(x, cos, sin):
     check(lib().ltx2_interleaved_rope(ptr(x), ptr(cos), ptr(sin), ptr(out), C.c_int64(x.numel()), dtype_code(x),
                                       stream_ptr()), "ltx2_interleaved_rope")
     return out
+
+
+def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, causal: bool = False) -> torch.Tensor:
+    """Conv3dSimple (simple_decoder.py:90-180) as one op: x [B,T,H,W,Cin] bf16 channels-last, weight [Cout,Cin,3,3,3]
+    (PyTorch layout, any float dtype), bias [Cout] -> [B,T,H,W,Cout] bf16."""
+    _cuda(x, weight, bias)
+    assert x.dtype == torch.bfloat16 and x.ndim == 5 and weight.ndim == 5
+    B, T, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    out = torch.empty(B, T, H, W, Cout, device=x.device, dtype=torch.bfloat16)
+    nbytes = int(lib().ltx2_conv3d_workspace_bytes(B, T, H, W, Cin, Cout))
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    check(lib().ltx2_conv3d(ptr(x), ptr(weight), dtype_code(weight), ptr(bias), dtype_code(bias), ptr(out), B, T, H, W,
+                            Cin, Cout, int(causal), ptr(ws), stream_ptr()), "ltx2_conv3d")
+    return out

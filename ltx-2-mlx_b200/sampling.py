@@ -6,7 +6,7 @@ Mirrors, with the same names and argument meaning:
   * ``post_process_latent``       pipelines/common.py:169-190
 and adds ``denoise_update`` (guide -> masked blend -> Euler step in ONE kernel, ``ltx2_denoise_update``) plus
 ``euler_denoising_loop``, the distilled pipeline's loop (pipelines/distilled.py:214-253) with every tensor resident on
-the GPU: per step one X0Model call and one update kernel, no host round trip.  Pipelines that keep their own loop can
+the GPU: per step one X0Model call and one update kernel, and no host synchronisation inside the loop.  Pipelines that keep their own loop can
 swap in the three mirrors one by one; all arithmetic is fp32 like the reference's.
 """
 from __future__ import annotations
@@ -82,28 +82,58 @@ def post_process_latent(denoised, denoise_mask, clean_latent):
     return (denoised * denoise_mask + clean_latent * (1 - denoise_mask)).to(denoised.dtype)
 
 
+def timestep_classes_from_mask(mask: torch.Tensor):
+    """(B, T) denoise mask -> (unit class values (n_cls,), row_cls (B, T) int32): the distinct (batch, mask value) pairs.
+    timesteps_from_mask (pipelines/common.py:193-203) is mask * sigma, so for a fixed mask the class structure is the
+    same at every step and only the values scale with sigma.  One host synchronisation per LOOP (torch.unique), none per
+    step."""
+    B, T = mask.shape
+    keyed = mask.double() + 4.0 * torch.arange(B, device=mask.device, dtype=torch.float64)[:, None]   # mask in [0, 1]
+    uniq, inv = torch.unique(keyed.reshape(-1), return_inverse=True)
+    vals = (uniq - 4.0 * torch.floor(uniq / 4.0)).to(torch.float32)
+    if vals.numel() > 64:
+        return None
+    return vals.contiguous(), inv.reshape(B, T).to(torch.int32).contiguous()
+
+
 def euler_denoising_loop(x0_model, latent, context, positions, sigmas: Sequence[float], *, denoise_mask=None,
                          clean_latent=None, negative_context=None, cfg_scale: float = 1.0) -> torch.Tensor:
     """pipelines/distilled.py:214-253 (video only) with optional CFG (pipelines/one_stage.py:267-326): for every sigma,
-    x0 = model(Modality(latent, timesteps = mask * sigma, ...)), then the fused update.  Returns the final latent."""
+    x0 = model(Modality(latent, timesteps = mask * sigma, ...)), then the fused update.  Returns the final latent.
+
+    Nothing in the loop synchronises with the host: without a mask the timesteps are the scalar (B,) form; with a mask
+    the (batch, sigma) classes are built once (timestep_classes_from_mask) and only rescaled per step; CFG runs cond and
+    uncond as ONE batch-of-2 forward (BASELINE.json north_star), which also keeps the context tensor -- and so the
+    engine's cached text K/V -- the same object for every step."""
     dev = torch.device("cuda", torch.cuda.current_device())
     x = _f32(latent, dev)
     B, T, _ = x.shape
-    mask = _f32(denoise_mask, dev).reshape(B, T) if denoise_mask is not None else torch.ones(B, T, device=dev)
-    clean = _f32(clean_latent, dev) if clean_latent is not None else None
     use_mask = denoise_mask is not None
+    mask = _f32(denoise_mask, dev).reshape(B, T) if use_mask else None
+    clean = _f32(clean_latent, dev) if clean_latent is not None else None
     if use_mask and clean is None:
         raise ValueError("denoise_mask needs clean_latent")
     ctx, pos = to_device(context, dev), to_device(positions, dev)
-    nctx = to_device(negative_context, dev) if negative_context is not None else None
+    cfg = negative_context is not None and cfg_scale != 1.0
+    if cfg:
+        ctx = torch.cat([ctx, to_device(negative_context, dev)], dim=0).contiguous()      # (2B, S, C): cond | uncond
+        pos = torch.cat([pos, pos], dim=0).contiguous()
+    rep = 2 if cfg else 1
+    classes = timestep_classes_from_mask(mask.repeat(rep, 1)) if use_mask else None
     for i in range(len(sigmas) - 1):
         sigma = float(sigmas[i])
-        ts = mask * sigma                                                   # timesteps_from_mask, common.py:193-203
-        sig = torch.full((B,), sigma, device=dev)
-        cond = x0_model(Modality(latent=x, context=ctx, context_mask=None, timesteps=ts, positions=pos, sigma=sig))
-        uncond = None
-        if nctx is not None and cfg_scale != 1.0:
-            uncond = x0_model(Modality(latent=x, context=nctx, context_mask=None, timesteps=ts, positions=pos, sigma=sig))
+        sig = torch.full((B * rep,), sigma, device=dev)
+        xin = torch.cat([x, x], dim=0) if cfg else x
+        if not use_mask:
+            mod = Modality(latent=xin, context=ctx, context_mask=None, timesteps=sig, positions=pos, sigma=sig)
+        elif classes is not None:
+            mod = Modality(latent=xin, context=ctx, context_mask=None, timesteps=sig, positions=pos, sigma=sig,
+                           timestep_classes=(classes[0] * sigma, classes[1]))
+        else:                                                       # > 64 distinct mask values: per-token form
+            mod = Modality(latent=xin, context=ctx, context_mask=None, timesteps=mask.repeat(rep, 1) * sigma,
+                           positions=pos, sigma=sig)
+        out = x0_model(mod)
+        cond, uncond = (out[:B], out[B:]) if cfg else (out, None)
         x = denoise_update(x, cond, sigma, float(sigmas[i + 1]), uncond_x0=uncond, cfg_scale=cfg_scale,
-                           denoise_mask=mask if use_mask else None, clean_latent=clean)
+                           denoise_mask=mask, clean_latent=clean)
     return x

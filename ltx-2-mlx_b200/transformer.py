@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from enum import Enum
 from typing import Any, Dict, Iterable, List, Optional, Tuple, Union
@@ -55,6 +56,11 @@ class Modality:
     positions: Any         # (B, n_dims, T, 2) [start, end) bounds
     enabled: bool = True
     sigma: Any = None      # (B,) scalar noise level (V2 prompt adaLN)
+    # Engine extension (not in the reference): (class_values (n_cls,) fp32, row_cls (B, T) int32) with
+    # timesteps[b, t] == class_values[row_cls[b, t]].  A sampling loop with a fixed denoise mask builds row_cls once
+    # and rescales class_values per step, so the forward needs no host-side de-duplication of (B, T) timesteps
+    # (sampling.euler_denoising_loop).  When given, `timesteps` is only used for its shape checks.
+    timestep_classes: Any = None
 
 
 # ---- STG perturbations (components/perturbations.py) ------------------------------------
@@ -250,6 +256,9 @@ class LTXModel:
         cfg.timestep_scale_multiplier = float(timestep_scale_multiplier)
         cfg.av_ca_timestep_scale_multiplier = float(av_ca_timestep_scale_multiplier)
         self._cfg = cfg
+        # text-context reuse across steps (V1 models; ltx2_dit_set_context_tag): on unless LTX2_CTX_CACHE=0
+        self.reuse_context = os.environ.get("LTX2_CTX_CACHE", "1") != "0"
+        self._ctx_ref = None                 # keeps the tagged context tensor alive so its id() stays unique
         self._cp = None                      # (rank, world, group, batch, n_total) once context_parallel.enable() ran
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -349,6 +358,29 @@ class LTXModel:
         n = lib().ltx2_dit_missing_weights(self._h, buf, C.c_int64(len(buf)))
         return [s for s in buf.value.decode().split("\n") if s] if n else []
 
+    def _context_tag(self, context) -> int:
+        """Non-zero tag when `context` is provably the tensor (same object, same torch version counter) whose projected
+        K/V the engine may hold from the previous call; 0 = recompute.  Only torch tensors carry a version counter, so
+        numpy / mx arrays are never reused.  (Writes that bypass torch, e.g. through a numpy view of the same memory,
+        are invisible to the counter: call reset_context_cache() after such a write.)"""
+        if not self.reuse_context or not isinstance(context, torch.Tensor):
+            self._ctx_ref = None
+            return 0
+        self._ctx_ref = context
+        key = (id(context), context._version, context.data_ptr(), tuple(context.shape), str(context.dtype),
+               getattr(self, "_ctx_salt", 0))
+        return (hash(key) & 0x7FFFFFFFFFFFFFFF) | 1
+
+    def reset_context_cache(self) -> None:
+        self._ctx_ref = None
+        check(lib().ltx2_dit_set_context_tag(self._h, 0), "ltx2_dit_set_context_tag")
+        # a forward with tag 0 drops the cached K/V; until then make sure no stale tag can match
+        self._ctx_salt = getattr(self, "_ctx_salt", 0) + 1
+
+    def set_layer_limit(self, n: Optional[int]) -> None:
+        """Diagnostics (bench.py parity leg): run only the first n blocks, then the head; None/0 = all."""
+        check(lib().ltx2_dit_set_layer_limit(self._h, int(n or 0)), "ltx2_dit_set_layer_limit")
+
     def _set_cross_attn_scale(self, idx: int, value) -> None:
         check(lib().ltx2_dit_set_cross_attn_scale(self._h, idx, C.c_float(float("nan") if value is None else float(value))),
               "set_cross_attn_scale")
@@ -365,6 +397,8 @@ class LTXModel:
                                           "(pipelines/common.py:223-231)")
         latent = to_device(m.latent, dev)
         context = to_device(m.context, dev)
+        if n_dims == 3:
+            check(lib().ltx2_dit_set_context_tag(self._h, self._context_tag(m.context)), "ltx2_dit_set_context_tag")
         if latent.ndim != 3 or context.ndim != 3:
             raise ValueError(f"latent/context must be (B, T, C); got {tuple(latent.shape)} / {tuple(context.shape)}")
         B, N, _ = latent.shape
@@ -376,6 +410,15 @@ class LTXModel:
         ts = ts.reshape(B, -1).contiguous()
         if ts.shape[1] not in (1, N):
             raise ValueError(f"timesteps must be (B,), (B, T) or (B, T, 1); got {tuple(ts.shape)} for T={N}")
+        cls_vals = row_cls = None
+        if getattr(m, "timestep_classes", None) is not None:
+            cls_vals, row_cls = m.timestep_classes
+            cls_vals = to_device(cls_vals, dev, torch.float32).reshape(-1)
+            row_cls = to_device(row_cls, dev, torch.int32).reshape(B, N)
+            if not 1 <= cls_vals.numel() <= 64:
+                raise ValueError("timestep_classes: 1..64 classes")
+            if m.sigma is None:
+                raise ValueError("timestep_classes needs Modality.sigma")
         pos = to_device(m.positions, dev, torch.float32)
         if pos.ndim != 4 or pos.shape[1] != n_dims or pos.shape[-1] != 2:
             # rope.py:229,262-263 assert the same
@@ -395,12 +438,17 @@ class LTXModel:
                 # take it before slicing so every rank uses token 0 of the whole sequence
                 sigma = ts[:, 0].contiguous()
             latent, ts, pos = slice_tokens(latent, ts, pos, rank, world)
+            if row_cls is not None:
+                a = rank * latent.shape[1]
+                row_cls = row_cls[:, a:a + latent.shape[1]].contiguous()
             N = latent.shape[1]
-        keep.extend([latent, context, ts, pos, sigma])
+        keep.extend([latent, context, ts, pos, sigma, cls_vals, row_cls])
         v = LtxModalityView()
         v.latent, v.latent_dtype = latent.data_ptr(), dtype_code(latent)
         v.context, v.context_dtype = context.data_ptr(), dtype_code(context)
-        v.timesteps = ts.data_ptr()
+        v.timesteps = cls_vals.data_ptr() if cls_vals is not None else ts.data_ptr()
+        v.row_cls = row_cls.data_ptr() if row_cls is not None else None
+        v.n_cls = int(cls_vals.numel()) if cls_vals is not None else 0
         v.sigma = sigma.data_ptr() if sigma is not None else None
         v.positions = pos.data_ptr()
         v.batch, v.tokens, v.context_tokens = B, N, context.shape[1]

@@ -156,9 +156,15 @@ def sdpa(q, k, v, heads):
     qh = q.reshape(B, Tq, heads, d).permute(0, 2, 1, 3)
     kh = k.reshape(B, Tk, heads, d).permute(0, 2, 1, 3)
     vh = v.reshape(B, Tk, heads, d).permute(0, 2, 1, 3)
-    s = (qh @ kh.transpose(-1, -2)) * (1.0 / math.sqrt(d))
-    p = torch.softmax(s, dim=-1)
-    return (p @ vh).permute(0, 2, 1, 3).reshape(B, Tq, inner)
+    scale = 1.0 / math.sqrt(d)
+    # same arithmetic per query row; query blocks only bound the (B,H,Tq,Tk) score matrix (19 GB at N = 12288)
+    step = Tq if B * heads * Tq * Tk <= (1 << 29) else max(1, (1 << 29) // (B * heads * Tk))
+    outs = []
+    for q0 in range(0, Tq, step):
+        s = (qh[:, :, q0:q0 + step] @ kh.transpose(-1, -2)) * scale
+        outs.append(torch.softmax(s, dim=-1) @ vh)
+    o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=2)
+    return o.permute(0, 2, 1, 3).reshape(B, Tq, inner)
 
 
 def attention(w, prefix, x, heads, context=None, pe=None, k_pe=None):

@@ -174,3 +174,92 @@ def test_weight_readback_and_lora_style_update():
     assert torch.equal(m(mod), before)
     with pytest.raises(KeyError):
         m.get_weight("no.such.key")
+
+
+def test_timestep_classes_equal_per_token_form_and_context_cache_is_safe():
+    """Engine extensions behind the reference call surface: (1) Modality.timestep_classes (pre-computed (batch, sigma)
+    classes, no host round trip) is bit-identical to the per-token (B, T) timesteps it stands for; (2) the V1 text
+    K/V reuse keyed on the context tensor's identity + version: same object again -> same bits; in-place change, new
+    tensor, or a weight update -> recomputed."""
+    from ltx2_b200 import sampling, synthetic
+    from ltx2_b200.transformer import Modality
+    cfg = synthetic.DitConfig(num_attention_heads=4, attention_head_dim=128, in_channels=32, out_channels=32,
+                              num_layers=2, cross_attention_dim=512, caption_channels=64)
+    m, w = build(cfg, seed=15)
+    B, F, H, W, S = 2, 3, 4, 6, 40
+    N = F * H * W
+    lat, ctx, pos = video_inputs(cfg, B, F, H, W, S, 150, 64)
+    dev = torch.device("cuda:0")
+    ctx_d = ctx.to(dev)
+    mask = torch.ones(B, N, device=dev)
+    mask[:, :H * W] = 0.0
+    mask[1, H * W:2 * H * W] = 0.5
+    sig = torch.tensor([0.725, 0.725], device=dev)
+    vals, rows = sampling.timestep_classes_from_mask(mask)
+    assert vals.numel() == 5 and rows.shape == (B, N)
+    assert torch.equal(vals[rows.long()], mask)
+    per_tok = m(Modality(latent=lat, context=ctx_d, context_mask=None, timesteps=mask * 0.725, positions=pos, sigma=sig))
+    by_cls = m(Modality(latent=lat, context=ctx_d, context_mask=None, timesteps=sig, positions=pos, sigma=sig,
+                        timestep_classes=(vals * 0.725, rows)))
+    assert torch.equal(per_tok, by_cls)
+
+    # ---- context K/V reuse ----
+    mod = Modality(latent=lat, context=ctx_d, context_mask=None, timesteps=torch.tensor([0.9, 0.4]), positions=pos)
+    first = m(mod)
+    assert torch.equal(m(mod), first)                       # hit
+    m.reuse_context = False
+    assert torch.equal(m(mod), first)                       # recomputed: same bits as the cached path
+    m.reuse_context = True
+    m(mod)
+    ctx_d.mul_(0.5)                                         # in-place change bumps the version -> miss
+    changed = m(mod)
+    assert not torch.equal(changed, first)
+    m.reuse_context = False
+    assert torch.equal(m(mod), changed)
+    m.reuse_context = True
+    ctx2 = (ctx_d * 2.0).contiguous()                       # the original values in a new tensor
+    again = m(Modality(latent=lat, context=ctx2, context_mask=None, timesteps=torch.tensor([0.9, 0.4]), positions=pos))
+    assert torch.equal(again, first)
+    # a weight update of the text K projection invalidates the cached K/V
+    k = "transformer_blocks.0.attn2.to_k.weight"
+    base = m.get_weight(k)
+    mod2 = Modality(latent=lat, context=ctx2, context_mask=None, timesteps=torch.tensor([0.9, 0.4]), positions=pos)
+    m.load_weights([(k, base * 1.5)])
+    assert not torch.equal(m(mod2), first)
+    m.load_weights([(k, base)])
+    assert torch.equal(m(mod2), first)
+
+
+def test_load_transformer_weights_from_safetensors_file(tmp_path):
+    """load_transformer_weights(model, path) (loader/weight_converter.py:318-326 call surface) on a temporary safetensors
+    file with the reference's checkpoint key names, including an FP8-style tensor with its weight_scale
+    (loader/fp8_loader.py:14-32: weight * weight_scale)."""
+    from safetensors.torch import save_file
+    from ltx2_b200 import synthetic
+    from ltx2_b200.loader import load_transformer_weights
+    from ltx2_b200.transformer import LTXModel, Modality
+    cfg = synthetic.DitConfig(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32,
+                              num_layers=1, cross_attention_dim=128, caption_channels=64)
+    m, w_ref = build(cfg, seed=16)
+    w = synthetic.dit_weights(cfg, seed=16)
+    sd = {k: v.to(torch.bfloat16).contiguous() for k, v in w.items()}
+    fp8_key = "model.diffusion_model.transformer_blocks.0.ff.net.0.proj.weight"
+    scale = 0.03125
+    sd[fp8_key] = (w[fp8_key] / scale).to(torch.float8_e4m3fn)
+    sd[fp8_key.replace(".weight", ".weight_scale")] = torch.tensor(scale)
+    sd["vae.decoder.conv_in.conv.bias"] = torch.zeros(4)                 # foreign tensors are ignored
+    path = str(tmp_path / "ckpt.safetensors")
+    save_file(sd, path)
+    kw = dict(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32, num_layers=1,
+              cross_attention_dim=128, caption_channels=64)
+    m2 = LTXModel(**kw)
+    load_transformer_weights(m2, path, strict=True, use_fp8=True)
+    assert m2.missing_weights() == []
+    deq = sd[fp8_key].float() * scale
+    got = m2.get_weight("transformer_blocks.0.ff.project_in.proj.weight").cpu()
+    assert torch.equal(got, deq.to(torch.bfloat16).float())
+    # same forward as a model loaded from the in-memory dict, up to the FP8 rounding of that one matrix
+    m.load_weights([("transformer_blocks.0.ff.project_in.proj.weight", deq)])
+    lat, ctx, pos = video_inputs(cfg, 1, 2, 3, 4, 24, 160, 64)
+    mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.5]), positions=pos)
+    assert torch.equal(m2(mod), m(mod))

@@ -86,3 +86,23 @@ def test_euler_denoising_loop_matches_oracle_loop():
         x = O.euler_step(x, d, sigmas, i)
     assert torch.isfinite(out).all()
     assert float((out - x).abs().max()) < 1e-4 * max(1.0, float(x.abs().max()))
+
+
+def test_timestep_classes_from_mask_cpu():
+    """Host logic of the sync-free loop: the (batch, mask value) classes reproduce timesteps_from_mask
+    (pipelines/common.py:193-203: mask * sigma) exactly, per batch element."""
+    from ltx2_b200 import sampling
+    mask = torch.ones(3, 40)
+    mask[:, :8] = 0.0
+    mask[1, 8:16] = 0.25
+    mask[2] = 1.0
+    vals, rows = sampling.timestep_classes_from_mask(mask)
+    assert rows.dtype == torch.int32 and rows.shape == (3, 40)
+    assert torch.equal(vals[rows.long()], mask)
+    # classes never mix batch elements (sigma differs per batch element in general)
+    owners = [set(rows[b].tolist()) for b in range(3)]
+    assert not (owners[0] & owners[1]) and not (owners[1] & owners[2]) and len(owners[2]) == 1
+    for sigma in (1.0, 0.421875):
+        assert torch.equal((vals * sigma)[rows.long()], mask * sigma)
+    many = torch.rand(1, 100)
+    assert sampling.timestep_classes_from_mask(many) is None          # > 64 classes: caller falls back to per-token

@@ -145,3 +145,22 @@ def test_decode_tiled_matches_oracle():
     # no tiling needed -> identical to a plain decode
     one = next(decode_tiled(lat, dec, TilingConfig(SpatialTilingConfig(512, 64), None), timestep=0.05))
     assert torch.allclose(one, dec(lat, timestep=0.05), atol=1e-6)
+
+
+def test_load_vae_decoder_weights_from_safetensors_file(tmp_path):
+    """load_vae_decoder_weights(decoder, path) (simple_decoder.py:566 call surface) on a temporary safetensors file."""
+    from safetensors.torch import save_file
+    from ltx2_b200 import synthetic
+    from ltx2_b200.video_vae import SimpleVideoDecoder, load_vae_decoder_weights
+    dec, _ = build(BLOCKS_V20, 64, True, seed=27)
+    cfg = synthetic.VaeConfig(decoder_blocks=BLOCKS_V20, base_channels=64, timestep_conditioning=True)
+    sd = {k: v.contiguous() for k, v in synthetic.vae_weights(cfg, seed=27).items()}
+    sd["model.diffusion_model.proj_out.bias"] = torch.zeros(4)            # foreign tensors are ignored
+    path = str(tmp_path / "vae.safetensors")
+    save_file(sd, path)
+    dec2 = SimpleVideoDecoder(decoder_blocks=BLOCKS_V20, base_channels=64, timestep_conditioning=True)
+    load_vae_decoder_weights(dec2, path)
+    assert dec2.missing_weights() == []
+    dec2.decode_noise_scale = 0.0
+    lat = synthetic.latents((1, 128, 2, 2, 3), seed=270)
+    assert torch.equal(dec2(lat, timestep=0.05), dec(lat, timestep=0.05))

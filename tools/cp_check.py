@@ -77,6 +77,7 @@ def av_cases(rank, world, dev):
             print(f"rank {rank} AV case B={B} N={N} Na={Na} per_token={per_token} split_k={split_k or 'default'} {name}: "
                   f"video rel {float((ov - rv).norm() / rv.norm()):.2e} audio rel {float((oa - ra).norm() / ra.norm()):.2e} "
                   f"audio identical across ranks {same} {'OK' if good and same else 'MISMATCH'}", flush=True)
+        context_parallel.disable(sharded)
         del single, sharded
     return ok
 
@@ -134,6 +135,7 @@ def main():
             ok = ok and good
             print(f"rank {rank} case B={B} N={N} per_token={per_token} split_k={split_k or 'default'} step {step}: max|diff| {d:.3e} x0 {d0:.3e} "
                   f"(max|ref| {scale:.3e}, rel L2 {rl2:.2e}) {'OK' if good else 'MISMATCH'}", flush=True)
+        context_parallel.disable(sharded)
         del single, sharded
     ok = av_cases(rank, world, dev) and ok
     t = torch.tensor([1 if ok else 0], device=dev)
