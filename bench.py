@@ -521,6 +521,8 @@ class DitBench:
 
     def step_e2e(self, i):
         import torch
+        if i % self.n_sig == 0:
+            self.model.reset_context_cache()      # a new sample (see run_steps)
         v, a = self.modalities(i, self.lat_h, self.alat_h if self.c["av"] else None, host=True)
         out = self.x0model(v, a) if a is not None else self.x0model(v)
         if a is not None:

@@ -12,6 +12,8 @@
 //   B tile: weights re-laid at load time as [C_out, 27*C_in] (tap-major, channel-minor) -> 2-D box {64, BN}
 // so the main loop is the GEMM's (gemm_sm100.cu): TMA producer warp, single-thread tcgen05.mma issuer with fp32
 // accumulators in TMEM (double-buffered), 4 epilogue warps.  K = 27*C_in.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,6 +33,218 @@ struct ConvCfg {
   static constexpr int kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
+
+// Epilogue of one accumulator tile for the calling thread's row (= one output position): TMEM -> bias / residual /
+// depth-to-space / unpatchify (/ fused padded producer) -> global.  Shared by the 1-CTA and the SM-pair kernels.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int mt, int nt, int r, bool tile_ok) {
+  const int tiles_w = (p.W + CTW - 1) / CTW;
+  const int tiles_h = (p.H + CTH - 1) / CTH;
+  const int sp = p.ft * p.fh * p.fw;
+  const int wx = mt % tiles_w;
+  const int hy = (mt / tiles_w) % tiles_h;
+  const int bt = mt / (tiles_w * tiles_h);
+  const int b = bt / p.T, t = bt % p.T;
+  const int h = hy * CTH + r / CTW, w = wx * CTW + r % CTW;
+  const bool pos_ok = tile_ok && h < p.H && w < p.W;
+  const int64_t pos = ((static_cast<int64_t>(bt) * p.H + h) * p.W + w);     // unpadded NDHWC position index
+  if (p.pad_out != nullptr) {
+    // ---- fused producer: this thread's accumulator row holds ALL channels of its position (BN == C_out) ----
+    // pass 1: v = bf16(acc + bias [+ residual]) -> raw output (optional), sum of squares, v back into TMEM
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32(t_row + c, rr);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c + j));
+        v[j] = __uint_as_float(rr[j]) + bb.x;
+        v[j + 1] = __uint_as_float(rr[j + 1]) + bb.y;
+        v[j + 2] = __uint_as_float(rr[j + 2]) + bb.z;
+        v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
+      }
+      if (p.mode == CONV_EPI_RESIDUAL && pos_ok) {
+        const __nv_bfloat16* rs = p.residual + pos * p.Cout + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(hh[q]);
+            v[j + 2 * q] += f.x;
+            v[j + 2 * q + 1] += f.y;
+          }
+        }
+      }
+      // the normalisation sees exactly the stored (bf16) activation, like the separate norm_act_pad pass
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[j]));
+        rr[2 * j] = __float_as_uint(f.x);
+        rr[2 * j + 1] = __float_as_uint(f.y);
+        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+      }
+      if (p.out != nullptr && pos_ok) {
+        __nv_bfloat16* o = p.out + pos * p.Cout + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+      tmem_st_32x32(t_row + c, rr);
+    }
+    tmem_st_wait();
+    const float rstd = rsqrtf(ss * (1.0f / BN) + p.pad_eps);
+    // destinations in the padded tensor: the interior copy plus the border copies this position feeds
+    // (reflect: row 1 -> pad row 0, row H-2 -> pad row H+1; T: first / last frame replicated)
+    const int Hp = p.H + 2, Wp = p.W + 2;
+    int tps[3], nt_ = 0, hps[3], nh_ = 0, wps[3], nw_ = 0;
+    if (p.pad_causal) {
+      tps[nt_++] = t + 2;
+      if (t == 0) { tps[nt_++] = 0; tps[nt_++] = 1; }
+    } else {
+      tps[nt_++] = t + 1;
+      if (t == 0) tps[nt_++] = 0;
+      if (t == p.T - 1) tps[nt_++] = p.T + 1;
+    }
+    hps[nh_++] = h + 1;
+    if (h == 1) hps[nh_++] = 0;
+    if (h == p.H - 2) hps[nh_++] = p.H + 1;
+    wps[nw_++] = w + 1;
+    if (w == 1) wps[nw_++] = 0;
+    if (w == p.W - 2) wps[nw_++] = p.W + 1;
+    // (with H == 3 row 1 is both "1" and "H-2": three copies along that axis)
+    const float* mrow = p.pad_act ? p.pad_mod + static_cast<int64_t>(b) * p.pad_mod_stride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32(t_row + c, rr);
+      tmem_ld_wait();
+      if (!pos_ok) continue;
+      uint32_t pk[16];
+      if (p.pad_act) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + p.pad_shift_off + c + j));
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + p.pad_scale_off + c + j));
+          float y0 = fmaf(__uint_as_float(rr[j]) * rstd, 1.f + sc.x, sh.x);
+          float y1 = fmaf(__uint_as_float(rr[j + 1]) * rstd, 1.f + sc.y, sh.y);
+          float y2 = fmaf(__uint_as_float(rr[j + 2]) * rstd, 1.f + sc.z, sh.z);
+          float y3 = fmaf(__uint_as_float(rr[j + 3]) * rstd, 1.f + sc.w, sh.w);
+          y0 = __fdividef(y0, 1.f + __expf(-y0));
+          y1 = __fdividef(y1, 1.f + __expf(-y1));
+          y2 = __fdividef(y2, 1.f + __expf(-y2));
+          y3 = __fdividef(y3, 1.f + __expf(-y3));
+          pk[j / 2] = pack_bf16x2(y0, y1);
+          pk[j / 2 + 1] = pack_bf16x2(y2, y3);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(rr[2 * j]), __uint_as_float(rr[2 * j + 1]));
+      }
+      for (int a = 0; a < nt_; ++a)
+        for (int bh = 0; bh < nh_; ++bh)
+          for (int bw = 0; bw < nw_; ++bw) {
+            __nv_bfloat16* o = p.pad_out +
+                (((static_cast<int64_t>(b) * (p.T + 2) + tps[a]) * Hp + hps[bh]) * Wp + wps[bw]) * p.Cout + c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(t_row + c, rr);
+    tmem_ld_wait();
+    const int col0 = nt * BN + c;
+    if (!pos_ok || col0 >= p.Cout_pad) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      v[j] = __uint_as_float(rr[j]) + bb.x;
+      v[j + 1] = __uint_as_float(rr[j + 1]) + bb.y;
+      v[j + 2] = __uint_as_float(rr[j + 2]) + bb.z;
+      v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
+    }
+    if (p.mode == CONV_EPI_PLAIN || p.mode == CONV_EPI_RESIDUAL) {
+      const int nv = p.Cout - col0;                  // valid columns of this group (C_out % 8 == 0; rows >= C_out are padding)
+      if (nv <= 0) continue;
+      if (p.mode == CONV_EPI_RESIDUAL) {
+        const __nv_bfloat16* rs = p.residual + pos * p.Cout + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j >= nv) break;
+          const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(hh[q]);
+            v[j + 2 * q] += f.x;
+            v[j + 2 * q + 1] += f.y;
+          }
+        }
+      }
+      __nv_bfloat16* o = p.out + pos * p.Cout + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (j >= nv) break;
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(o + j) = q;
+      }
+    } else if (p.mode == CONV_EPI_D2S) {
+      // weight rows were permuted at load time to (sub-position major, output channel minor):
+      // col = sub * Cf + c, sub = (a*fh + bb)*fw + d  ->  32 consecutive columns share one output pixel.
+      const int Cf = p.Cout / sp;
+      const int sub = col0 / Cf, c0 = col0 % Cf;
+      const int a = sub / (p.fh * p.fw), bb2 = (sub / p.fw) % p.fh, d = sub % p.fw;
+      const int drop = (p.ft > 1) ? 1 : 0;
+      const int to = t * p.ft + a - drop;
+      if (to < 0) continue;
+      const int To = p.T * p.ft - drop, Ho = p.H * p.fh, Wo = p.W * p.fw;
+      if (p.c_d2s > 0) {
+        // residual = depth_to_space(x) tiled along channels: source channel (c % c_d2s)*sp + sub of THIS position
+        const __nv_bfloat16* rs = p.residual + pos * p.Cin;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rs[((c0 + j) % p.c_d2s) * sp + sub]);
+      }
+      __nv_bfloat16* o = p.out + (((static_cast<int64_t>(b) * To + to) * Ho + (h * p.fh + bb2)) * Wo + (w * p.fw + d)) * Cf + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(v[j], v[j + 1]);
+        q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(o + j) = q;
+      }
+    } else {  // CONV_EPI_UNPATCHIFY: col = (ch*4 + rw)*4 + rh -> out_f32[b, ch, t, h*4+rh, w*4+rw]
+      const int Hp = p.H * 4, Wp = p.W * 4;
+#pragma unroll
+      for (int j = 0; j < 32; j += 16) {
+        const int ch = (col0 + j) / 16;
+        if (ch >= p.Cout / 16) break;
+        float* o = p.out_f32 + ((static_cast<int64_t>(b) * (p.Cout / 16) + ch) * p.T + t) * Hp * static_cast<int64_t>(Wp);
+#pragma unroll
+        for (int rh = 0; rh < 4; ++rh)
+          *reinterpret_cast<float4*>(o + static_cast<int64_t>(h * 4 + rh) * Wp + w * 4) =
+              make_float4(v[j + rh], v[j + 4 + rh], v[j + 8 + rh], v[j + 12 + rh]);
+      }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -138,105 +352,12 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int sp = p.ft * p.fh * p.fw;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % num_m, nt = tile / num_m;
-      const int wx = mt % tiles_w;
-      const int hy = (mt / tiles_w) % tiles_h;
-      const int bt = mt / (tiles_w * tiles_h);
-      const int b = bt / p.T, t = bt % p.T;
-      const int r = quarter * 32 + lane;
-      const int h = hy * CTH + r / CTW, w = wx * CTW + r % CTW;
-      const bool pos_ok = h < p.H && w < p.W;
-      const int64_t pos = ((static_cast<int64_t>(bt) * p.H + h) * p.W + w);     // unpadded NDHWC position index
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(t_row + c, rr);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c;
-        if (!pos_ok || col0 >= p.Cout_pad) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-          v[j] = __uint_as_float(rr[j]) + bb.x;
-          v[j + 1] = __uint_as_float(rr[j + 1]) + bb.y;
-          v[j + 2] = __uint_as_float(rr[j + 2]) + bb.z;
-          v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
-        }
-        if (p.mode == CONV_EPI_PLAIN || p.mode == CONV_EPI_RESIDUAL) {
-          const int nv = p.Cout - col0;                  // valid columns of this group (C_out % 8 == 0; rows >= C_out are padding)
-          if (nv <= 0) continue;
-          if (p.mode == CONV_EPI_RESIDUAL) {
-            const __nv_bfloat16* rs = p.residual + pos * p.Cout + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j >= nv) break;
-              const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(hh[q]);
-                v[j + 2 * q] += f.x;
-                v[j + 2 * q + 1] += f.y;
-              }
-            }
-          }
-          __nv_bfloat16* o = p.out + pos * p.Cout + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (j >= nv) break;
-            uint4 q;
-            q.x = pack_bf16x2(v[j], v[j + 1]);
-            q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = q;
-          }
-        } else if (p.mode == CONV_EPI_D2S) {
-          // weight rows were permuted at load time to (sub-position major, output channel minor):
-          // col = sub * Cf + c, sub = (a*fh + bb)*fw + d  ->  32 consecutive columns share one output pixel.
-          const int Cf = p.Cout / sp;
-          const int sub = col0 / Cf, c0 = col0 % Cf;
-          const int a = sub / (p.fh * p.fw), bb2 = (sub / p.fw) % p.fh, d = sub % p.fw;
-          const int drop = (p.ft > 1) ? 1 : 0;
-          const int to = t * p.ft + a - drop;
-          if (to < 0) continue;
-          const int To = p.T * p.ft - drop, Ho = p.H * p.fh, Wo = p.W * p.fw;
-          if (p.c_d2s > 0) {
-            // residual = depth_to_space(x) tiled along channels: source channel (c % c_d2s)*sp + sub of THIS position
-            const __nv_bfloat16* rs = p.residual + pos * p.Cin;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __bfloat162float(rs[((c0 + j) % p.c_d2s) * sp + sub]);
-          }
-          __nv_bfloat16* o = p.out + (((static_cast<int64_t>(b) * To + to) * Ho + (h * p.fh + bb2)) * Wo + (w * p.fw + d)) * Cf + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            q.x = pack_bf16x2(v[j], v[j + 1]);
-            q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = q;
-          }
-        } else {  // CONV_EPI_UNPATCHIFY: col = (ch*4 + rw)*4 + rh -> out_f32[b, ch, t, h*4+rh, w*4+rw]
-          const int Hp = p.H * 4, Wp = p.W * 4;
-#pragma unroll
-          for (int j = 0; j < 32; j += 16) {
-            const int ch = (col0 + j) / 16;
-            if (ch >= p.Cout / 16) break;
-            float* o = p.out_f32 + ((static_cast<int64_t>(b) * (p.Cout / 16) + ch) * p.T + t) * Hp * static_cast<int64_t>(Wp);
-#pragma unroll
-            for (int rh = 0; rh < 4; ++rh)
-              *reinterpret_cast<float4*>(o + static_cast<int64_t>(h * 4 + rh) * Wp + w * 4) =
-                  make_float4(v[j + rh], v[j + 4 + rh], v[j + 8 + rh], v[j + 12 + rh]);
-          }
-        }
-      }
+      conv_epilogue_row<BN>(p, t_row, mt, nt, quarter * 32 + lane, true);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -250,6 +371,193 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SM-pair variant (tcgen05 cta_group::2) for convs whose C_out fits one weight tile (BN == C_out_pad: the 128- and
+// 256-channel stages).  With 128 x 128 tiles a single CTA reads 4 KB of A and 4 KB of B from shared memory per 64-clock
+// MMA -- 128 B/clk, the shared-memory limit (tensor pipe 67 % active on the last stage, profiles/r1c_kernels.json).  A
+// cluster of two CTAs issues ONE MMA with M = 256: CTA r supplies ITS 128 output positions (A) and HALF of the weight
+// rows (B: BN/2 rows), so each SM reads 4 + 2 KB per MMA and receives 24 instead of 32 KB per K block from TMA / L2.
+// Roles as in gemm2_bf16_kernel (gemm_sm100.cu):
+//   warp 0 (both CTAs)  TMA producer of the CTA's A tile and weight half -> own `full` barriers
+//   warp 1, CTA 1       relay: own `full` complete -> remote arrive on CTA 0's `peer_full`
+//   warp 1, CTA 0       MMA issuer: waits full + peer_full, commits multicast to `empty` / `acc_full` of both CTAs
+//   warps 2-5           epilogue of the CTA's own 128 positions; `acc_empty` lives in CTA 0, counts all 8 epilogue warps
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct ConvPairCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = CBM * CBK * 2;
+  static constexpr int kBBytes = (BN / 2) * CBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;                  // 256 or 512
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, ConvParams p) {
+  using Cfg = ConvPairCfg<BN>;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                          // [stages]  own TMA -> MMA (CTA 0) / relay (CTA 1)
+  uint64_t* peer_full = full_bar + Cfg::kStages;      // [stages]  CTA 1 relay -> CTA 0 MMA (used in CTA 0 only)
+  uint64_t* empty_bar = peer_full + Cfg::kStages;     // [stages]  MMA (multicast) -> own TMA
+  uint64_t* acc_full = empty_bar + Cfg::kStages;      // [2]       MMA (multicast) -> own epilogue
+  uint64_t* acc_empty = acc_full + 2;                 // [2]       all 8 epilogue warps -> MMA (used in CTA 0 only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int tiles_w = (p.W + CTW - 1) / CTW;
+  const int tiles_h = (p.H + CTH - 1) / CTH;
+  const int num_m = p.B * p.T * tiles_h * tiles_w;
+  const int num_pairs = (num_m + 1) / 2;              // pair pt = position tiles 2 pt (CTA 0) and 2 pt + 1 (CTA 1)
+  const int cchunks = p.Cin / CBK;
+  const int num_kb = 27 * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&peer_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // both CTAs are running and their barriers exist
+  if (warp == 1) tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ============ TMA producer (both CTAs): own position tile, own half of the weight rows ============
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      const int mt = min(2 * pt + static_cast<int>(rank), num_m - 1);     // odd tile count: CTA 1 repeats the last tile
+      const int wx = mt % tiles_w;
+      const int hy = (mt / tiles_w) % tiles_h;
+      const int bt = mt / (tiles_w * tiles_h);
+      const int b = bt / p.T, t = bt % p.T;
+      const int plane0 = b * (p.T + 2) + t;
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw, hy * CTH + kh,
+                      plane0 + kt);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * CBK,
+                      static_cast<int>(rank) * (BN / 2));
+        }
+        if (++cc == cchunks) { cc = 0; ++tap; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ===================== relay (CTA 1): my tiles have landed -> tell the MMA issuer in CTA 0 =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        if (leader) mbar_arrive_cluster_relaxed(mapa_u32(&peer_full[stage], 0));
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0): M = 256 positions of the pair, N = BN channels =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_cluster(&peer_full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < CBK / 16; ++k) umma2_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma2_commit_both(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma2_commit_both(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5, both CTAs): the CTA's own 128 positions =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
+      const int mt = 2 * pt + static_cast<int>(rank);
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      conv_epilogue_row<BN>(p, t_row, min(mt, num_m - 1), 0, quarter * 32 + lane, mt < num_m);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // nobody leaves while the peer may still touch my barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_conv_pair(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvPairCfg<BN>;
+  static PerDeviceOnce configured;
+  if (configured.first()) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(conv3d_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
+  }
+  const int num_m = p.B * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW);
+  const int pairs = (num_m + 1) / 2, clusters = num_sms() / 2;
+  const int grid = 2 * (pairs < clusters ? pairs : clusters);
+  LTX2_CUDA_CHECK(launch_pdl(conv3d_pair_kernel<BN>, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, stream, tx, tw, p));
+  count_launch();
+  return LTX2_OK;
 }
 
 template <int BN>
@@ -282,6 +590,15 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
     uint32_t box[4] = {CBK, CTW, CTH, 1};
     LTX2_PROPAGATE(make_tensor_map_bf16(&tx, x_padded, 4, dims, str, box));
   }
+  if (p.pad_out != nullptr) {
+    LTX2_REQUIRE((p.mode == CONV_EPI_PLAIN || p.mode == CONV_EPI_RESIDUAL) && p.Cout == p.Cout_pad &&
+                     (p.Cout == 128 || p.Cout == 256) && p.H >= 2 && p.W >= 2,
+                 "conv3d: the fused padded output needs C_out = 128 or 256 (got %d), H, W >= 2 and a plain/residual epilogue",
+                 p.Cout);
+    LTX2_REQUIRE(!p.pad_act || p.pad_mod != nullptr, "conv3d: fused activation without modulation rows");
+  } else {
+    LTX2_REQUIRE(p.out != nullptr || p.out_f32 != nullptr, "conv3d: null output");
+  }
   int bn = 256;
   if (p.Cout_pad % 256 != 0) bn = 128;
   if (p.Cout_pad % 128 != 0) bn = 64;
@@ -289,6 +606,19 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
   if (p.mode == CONV_EPI_D2S) {
     const int Cf = p.Cout / (p.ft * p.fh * p.fw);
     LTX2_REQUIRE(Cf % 32 == 0, "conv3d: depth-to-space needs C_out/stride_product %% 32 == 0 (got %d)", Cf);
+  }
+  // SM-pair kernel when one weight tile covers C_out (LTX2_CONV_PAIR: 0 = never, 1 = 128-channel convs (default),
+  // 2 = also 256-channel convs)
+  {
+    const char* env = getenv("LTX2_CONV_PAIR");
+    const int lvl = env ? atoi(env) : 1;
+    const bool pair = p.Cout_pad == bn && ((bn == 128 && lvl >= 1) || (bn == 256 && lvl >= 2));
+    if (pair) {
+      CUtensorMap twp;
+      LTX2_PROPAGATE(get_tensor_map_2d(&twp, w_packed, p.Cout_pad, static_cast<uint64_t>(27) * p.Cin,
+                                       static_cast<uint64_t>(27) * p.Cin, bn / 2));
+      return bn == 128 ? launch_conv_pair<128>(tx, twp, p, stream) : launch_conv_pair<256>(tx, twp, p, stream);
+    }
   }
   CUtensorMap tw_map;
   const CUtensorMap* tw = &tw_map;

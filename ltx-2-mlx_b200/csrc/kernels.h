@@ -202,6 +202,17 @@ struct ConvParams {
   const __nv_bfloat16* residual = nullptr;   // RESIDUAL: [.,Cout];  D2S: the UNPADDED conv input [.,Cin]
   int ft = 1, fh = 1, fw = 1;           // D2S strides
   int c_d2s = 0;                        // D2S residual: Cin / (ft*fh*fw); 0 = no residual
+  // Fused producer (PLAIN / RESIDUAL, C_out == 128 or 256 so that one accumulator row holds every channel of its
+  // position): the epilogue ALSO writes the padded input of the next conv, [B,T+2,H+2,W+2,Cout] bf16 with reflect H/W
+  // and replicate T borders, optionally through pixel-norm * (1+scale) + shift and SiLU -- what norm_act_pad would do
+  // in a separate pass over HBM (simple_decoder.py:105-134, 229-231, 339-342).  `out` may then be null (the raw
+  // activation of a ResBlock's first conv has no other reader).
+  __nv_bfloat16* pad_out = nullptr;
+  int pad_act = 0;                      // 1: silu(pixel_norm(v) * (1 + scale[b]) + shift[b]); 0: plain copy
+  const float* pad_mod = nullptr;       // fp32 [B, pad_mod_stride]
+  int64_t pad_mod_stride = 0, pad_shift_off = 0, pad_scale_off = 0;
+  float pad_eps = 1e-6f;
+  int pad_causal = 0;
 };
 
 // x_padded: bf16 [B, T+2, H+2, W+2, Cin]; w_packed: bf16 [Cout_pad, 27*Cin] (tap-major, channel-minor)

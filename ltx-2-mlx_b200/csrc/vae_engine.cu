@@ -369,8 +369,8 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   }
   max_mod = std::max(max_mod, size_t(B) * 2 * e->Cf);
   const int maxC = e->conv_in.Cout;
-  const size_t need = align256(max_act * 2) * 2 + align256(max_pad * 2) + align256(max_mod * 4) +
-                      align256(size_t(B) * (256 + 4 * maxC * 2 + 8) * 4) + 4096;
+  const size_t need = align256(max_act * 2) * 2 + align256(max_pad * 2) * 2 + align256(max_mod * 4) +
+                      align256(size_t(B) * 2 * e->Cf * 4) + align256(size_t(B) * (256 + 4 * maxC * 2 + 8) * 4) + 4096;
   if (need > e->ws_bytes) {
     if (e->ws) cudaFree(e->ws);
     e->ws = nullptr; e->ws_bytes = 0;
@@ -385,7 +385,9 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   bf16* cur = reinterpret_cast<bf16*>(ws.take(max_act * 2));
   bf16* other = reinterpret_cast<bf16*>(ws.take(max_act * 2));
   bf16* xp = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
+  bf16* xp2 = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
   float* mod = reinterpret_cast<float*>(ws.take(max_mod * 4));
+  float* mod_final = reinterpret_cast<float*>(ws.take(size_t(B) * 2 * e->Cf * 4));
   float* tdev = reinterpret_cast<float*>(ws.take(size_t(B) * 4 + 16));
   float* sinus = reinterpret_cast<float*>(ws.take(size_t(B) * 256 * 4));
   float* hid = reinterpret_cast<float*>(ws.take(size_t(B) * 4 * maxC * 4));
@@ -402,9 +404,19 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
     LTX2_PROPAGATE(small_linear(sinus, B, 256, m.w1, m.b1, hid, m.hidden, 0, st));
     return small_linear(hid, B, m.hidden, m.w2, m.b2, temb, m.out, 1, st);
   };
+  struct PadOut {                 // fused producer of the next conv's padded input (conv3d_sm100.cu)
+    bf16* dst = nullptr;
+    int act = 0;
+    const float* mod = nullptr;
+    int64_t stride = 0, shift_off = 0, scale_off = 0;
+  };
   auto conv = [&](const ConvW& w, const bf16* xin_padded, const Dims& dd, int mode, bf16* o, const bf16* residual,
-                  float* o32, const StageW* up) -> int {
+                  float* o32, const StageW* up, const PadOut* po = nullptr) -> int {
     ConvParams p;
+    if (po != nullptr && po->dst != nullptr) {
+      p.pad_out = po->dst; p.pad_act = po->act; p.pad_mod = po->mod; p.pad_mod_stride = po->stride;
+      p.pad_shift_off = po->shift_off; p.pad_scale_off = po->scale_off; p.pad_eps = 1e-6f; p.pad_causal = causal;
+    }
     p.B = B; p.T = dd.T; p.H = dd.H; p.W = dd.W;
     p.Cin = w.Cin; p.Cout = w.Cout; p.Cout_pad = w.Cout_pad;
     p.mode = mode; p.bias = w.b; p.out = o; p.out_f32 = o32; p.residual = residual;
@@ -439,42 +451,87 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   LTX2_PROPAGATE(conv(e->conv_in, xp, d, CONV_EPI_PLAIN, cur, nullptr, nullptr, nullptr));
   d.C = e->conv_in.Cout;
 
-  for (auto& s : e->stages) {
-    if (s.kind == 0) {
-      const int C = s.C;
-      if (use_t && s.temb.present) {
-        LTX2_PROPAGATE(run_mlp(s.temb));
-        LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod,
-                                           int64_t(B) * 4 * C, int64_t(4) * C, s.num_layers, B, 4, C, st));
-      } else {
-        LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 4 * C * 4, st));
-        LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod,
-                                           int64_t(B) * 4 * C, int64_t(4) * C, s.num_layers, B, 4, C, st));
-      }
-      for (int j = 0; j < s.num_layers; ++j) {
-        const float* mj = mod + size_t(j) * B * 4 * C;
-        LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, 0, C, 1e-6f, causal, st));
-        LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, other, nullptr, nullptr, nullptr));
-        LTX2_PROPAGATE(norm_act_pad(other, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, int64_t(2) * C,
-                                    int64_t(3) * C, 1e-6f, causal, st));
-        LTX2_PROPAGATE(conv(s.conv2[j], xp, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr));
-      }
-    } else {
-      LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, s.C, 0, nullptr, 0, 0, 0, 1e-6f, causal, st));
-      LTX2_PROPAGATE(conv(s.up, xp, d, CONV_EPI_D2S, other, cur, nullptr, &s));
-      std::swap(cur, other);
-      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
-    }
-  }
-  // final norm + scale/shift + SiLU, conv_out, unpatchify (simple_decoder.py:528-552)
+  // Final norm / scale-shift rows (simple_decoder.py:528-542), computed up front: the last conv of the last group
+  // produces the activated, padded input of conv_out in its epilogue.
   const int Cf = e->Cf;
   if (use_t && e->last_temb.present) {
     LTX2_PROPAGATE(run_mlp(e->last_temb));
   } else {
     LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 2 * Cf * 4, st));
   }
-  LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod, 0, int64_t(2) * Cf, 1, B, 2, Cf, st));
-  LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, Cf, 1, mod, int64_t(2) * Cf, 0, Cf, 1e-6f, causal, st));
+  LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod_final, 0, int64_t(2) * Cf, 1, B, 2,
+                                     Cf, st));
+  // Stages with 128 or 256 channels (83 % of the conv FLOPs, all of the large activations) run FUSED: every conv's
+  // epilogue writes the next conv's input already pixel-normalised, modulated, SiLU-activated and padded, so the
+  // separate norm_act_pad pass (one read + one write of the activation per conv) only runs once per group.
+  // LTX2_VAE_FUSE=0 restores the unfused sequence (A/B and debugging).
+  const char* fuse_env = getenv("LTX2_VAE_FUSE");
+  const bool fuse_on = !(fuse_env && fuse_env[0] == '0');
+  bool xp_ready = false;           // xp already holds the padded input of the next consumer
+  const size_t n_stages = e->stages.size();
+  for (size_t si = 0; si < n_stages; ++si) {
+    StageW& s = e->stages[si];
+    if (s.kind == 0) {
+      const int C = s.C;
+      if (use_t && s.temb.present) {
+        LTX2_PROPAGATE(run_mlp(s.temb));
+      } else {
+        LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 4 * C * 4, st));
+      }
+      LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod, int64_t(B) * 4 * C,
+                                         int64_t(4) * C, s.num_layers, B, 4, C, st));
+      const bool fuse = fuse_on && (C == 128 || C == 256);
+      if (!fuse) {
+        for (int j = 0; j < s.num_layers; ++j) {
+          const float* mj = mod + size_t(j) * B * 4 * C;
+          LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, 0, C, 1e-6f, causal, st));
+          LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, other, nullptr, nullptr, nullptr));
+          LTX2_PROPAGATE(norm_act_pad(other, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, int64_t(2) * C,
+                                      int64_t(3) * C, 1e-6f, causal, st));
+          LTX2_PROPAGATE(conv(s.conv2[j], xp, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr));
+        }
+        xp_ready = false;
+        continue;
+      }
+      LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mod, int64_t(4) * C, 0, C, 1e-6f, causal, st));
+      for (int j = 0; j < s.num_layers; ++j) {
+        const float* mj = mod + size_t(j) * B * 4 * C;
+        // conv1: xp -> xp2 = act(norm2_j(.)); its raw output has no other reader
+        PadOut p1;
+        p1.dst = xp2; p1.act = 1; p1.mod = mj; p1.stride = int64_t(4) * C; p1.shift_off = int64_t(2) * C;
+        p1.scale_off = int64_t(3) * C;
+        LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, nullptr, nullptr, nullptr, nullptr, &p1));
+        // conv2: xp2 -> cur = residual + conv (raw, the next residual) and xp = padded input of the next consumer
+        PadOut p2;
+        p2.dst = xp;
+        if (j + 1 < s.num_layers) {
+          p2.act = 1; p2.mod = mod + size_t(j + 1) * B * 4 * C; p2.stride = int64_t(4) * C; p2.shift_off = 0;
+          p2.scale_off = C;
+          xp_ready = true;
+        } else if (si + 1 == n_stages) {
+          p2.act = 1; p2.mod = mod_final; p2.stride = int64_t(2) * Cf; p2.shift_off = 0; p2.scale_off = Cf;
+          xp_ready = true;
+        } else if (e->stages[si + 1].kind == 1) {
+          p2.act = 0;                       // the depth-to-space conv reads the raw activation, padded
+          xp_ready = true;
+        } else {
+          p2.dst = nullptr;                 // another res group follows: its rows are not built yet
+          xp_ready = false;
+        }
+        LTX2_PROPAGATE(conv(s.conv2[j], xp2, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr, &p2));
+      }
+    } else {
+      if (!xp_ready)
+        LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, s.C, 0, nullptr, 0, 0, 0, 1e-6f, causal, st));
+      xp_ready = false;
+      LTX2_PROPAGATE(conv(s.up, xp, d, CONV_EPI_D2S, other, cur, nullptr, &s));
+      std::swap(cur, other);
+      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
+    }
+  }
+  // final norm + scale/shift + SiLU (unless the last conv already produced it), conv_out, unpatchify (:528-552)
+  if (!xp_ready)
+    LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, Cf, 1, mod_final, int64_t(2) * Cf, 0, Cf, 1e-6f, causal, st));
   return conv(e->conv_out, xp, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
 }
 

@@ -240,7 +240,6 @@ def test_load_transformer_weights_from_safetensors_file(tmp_path):
     from ltx2_b200.transformer import LTXModel, Modality
     cfg = synthetic.DitConfig(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=32,
                               num_layers=1, cross_attention_dim=128, caption_channels=64)
-    m, w_ref = build(cfg, seed=16)
     w = synthetic.dit_weights(cfg, seed=16)
     sd = {k: v.to(torch.bfloat16).contiguous() for k, v in w.items()}
     fp8_key = "model.diffusion_model.transformer_blocks.0.ff.net.0.proj.weight"
@@ -258,8 +257,12 @@ def test_load_transformer_weights_from_safetensors_file(tmp_path):
     deq = sd[fp8_key].float() * scale
     got = m2.get_weight("transformer_blocks.0.ff.project_in.proj.weight").cpu()
     assert torch.equal(got, deq.to(torch.bfloat16).float())
-    # same forward as a model loaded from the in-memory dict, up to the FP8 rounding of that one matrix
-    m.load_weights([("transformer_blocks.0.ff.project_in.proj.weight", deq)])
+    # same forward as a model loaded from the same (bf16 / dequantised FP8) values held in memory
+    from ltx2_b200.loader import load_transformer_state_dict
+    m3 = LTXModel(**kw)
+    mem = {k: v for k, v in sd.items() if not k.endswith(".weight_scale")}
+    mem[fp8_key] = deq
+    load_transformer_state_dict(m3, mem)
     lat, ctx, pos = video_inputs(cfg, 1, 2, 3, 4, 24, 160, 64)
     mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.5]), positions=pos)
-    assert torch.equal(m2(mod), m(mod))
+    assert torch.equal(m2(mod), m3(mod))

@@ -164,3 +164,23 @@ def test_load_vae_decoder_weights_from_safetensors_file(tmp_path):
     dec2.decode_noise_scale = 0.0
     lat = synthetic.latents((1, 128, 2, 2, 3), seed=270)
     assert torch.equal(dec2(lat, timestep=0.05), dec(lat, timestep=0.05))
+
+
+def test_fused_conv_producer_matches_unfused_sequence(monkeypatch):
+    """The conv epilogue that writes the next conv's normalised / activated / padded input (128- and 256-channel
+    stages) against the separate norm_act_pad pass it replaces (LTX2_VAE_FUSE=0): same stored bf16 activations go into
+    the norm, so the two agree to bf16 rounding of the normalised values; both match the oracle."""
+    from ltx2_b200 import synthetic
+    from oracle import vae_oracle as V
+    dec, w = build(BLOCKS_V20, 64, True, seed=28)
+    for shape, causal in (((1, 128, 3, 2, 3), False), ((2, 128, 1, 3, 2), True), ((1, 128, 2, 5, 4), False)):
+        lat = synthetic.latents(shape, seed=280)
+        monkeypatch.setenv("LTX2_VAE_FUSE", "1")
+        fused = dec(lat, timestep=0.05, causal=causal)
+        monkeypatch.setenv("LTX2_VAE_FUSE", "0")
+        plain = dec(lat, timestep=0.05, causal=causal)
+        monkeypatch.delenv("LTX2_VAE_FUSE")
+        ref = V.vae_decode(w, lat, decoder_blocks=BLOCKS_V20, base_channels=64, timestep=0.05, causal=causal)
+        assert rel(fused, plain) < 1e-2, rel(fused, plain)
+        assert rel(fused, ref) < 3e-2 and rel(plain, ref) < 3e-2, (rel(fused, ref), rel(plain, ref))
+        assert pearson(fused, ref) > 0.999
