@@ -228,6 +228,7 @@ int ltx2_conv3d(const void* x, const void* weight, int32_t w_dtype, const void* 
 /* Measurement hooks (bench.py): CUDA-event timing of the conv launches of one decode. */
 int ltx2_vae_set_profile(LtxVae* vae, int32_t on);
 int ltx2_vae_profile_read(LtxVae* vae, double* ms_out, double* flops_out, int64_t* launches_out);
+int ltx2_vae_profile_launch(LtxVae* vae, int32_t i, double* ms_out, double* flops_out);   /* conv launch i of that decode */
 
 /* decode_latent's chunk stitching (:749-790): dst [BC,T_dst,HW] <- cross-fade of src [BC,T_src,HW] placed at frame t0,
  * linear ramp over the first `overlap` frames, plain copy after; and the uint8 conversion (:793-798):

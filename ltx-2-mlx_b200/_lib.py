@@ -92,6 +92,7 @@ SIGNATURES = {
     "ltx2_conv3d": (_I32, [_P, _P, _I32, _P, _I32, _P] + [_I32] * 7 + [_P, _P]),
     "ltx2_vae_set_profile": (_I32, [_P, _I32]),
     "ltx2_vae_profile_read": (_I32, [_P, _P, _P, _P]),
+    "ltx2_vae_profile_launch": (_I32, [_P, _I32, _P, _P]),
     "ltx2_blend_chunk": (_I32, [_P, _P] + [_I32] * 6 + [_P]),
     "ltx2_video_to_uint8": (_I32, [_P, _P, _I32, _I32, _I32, _P]),
     "ltx2_tile_accumulate": (_I32, [_P, _P, _P] + [_I32] * 13 + [_P, _P, _P, _P]),

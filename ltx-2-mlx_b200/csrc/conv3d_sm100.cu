@@ -31,13 +31,30 @@ struct ConvCfg {
   static constexpr int kBBytes = BN * CBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 3 * BN * 4;
 };
+
+// Rows the fused epilogue needs for every position of batch element b, staged once in shared memory by the 128
+// epilogue threads (r = 0..127): bias, shift and 1 + scale.  Named barrier 1 orders it against the readers.
+template <int BN>
+__device__ __forceinline__ void conv_stage_mod(const ConvParams& p, int b, float* s_mod, int r) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int c = r; c < BN; c += 128) {
+    s_mod[c] = p.bias[c];
+    if (p.pad_act) {
+      const float* m = p.pad_mod + static_cast<int64_t>(b) * p.pad_mod_stride;
+      s_mod[BN + c] = m[p.pad_shift_off + c];
+      s_mod[2 * BN + c] = 1.f + m[p.pad_scale_off + c];
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 
 // Epilogue of one accumulator tile for the calling thread's row (= one output position): TMEM -> bias / residual /
 // depth-to-space / unpatchify (/ fused padded producer) -> global.  Shared by the 1-CTA and the SM-pair kernels.
 template <int BN>
-__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int mt, int nt, int r, bool tile_ok) {
+__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int mt, int nt, int r, bool tile_ok,
+                                                  const float* s_mod, uint64_t* acc_full_bar, uint32_t acc_phase) {
   const int tiles_w = (p.W + CTW - 1) / CTW;
   const int tiles_h = (p.H + CTH - 1) / CTH;
   const int sp = p.ft * p.fh * p.fw;
@@ -50,33 +67,55 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
   const int64_t pos = ((static_cast<int64_t>(bt) * p.H + h) * p.W + w);     // unpadded NDHWC position index
   if (p.pad_out != nullptr) {
     // ---- fused producer: this thread's accumulator row holds ALL channels of its position (BN == C_out) ----
+    // s_mod (shared memory, staged by conv_stage_mod): [0,BN) bias, [BN,2BN) shift, [2BN,3BN) 1 + scale
+    // The residual row comes from DRAM (written two convs ago): its first chunk is requested BEFORE the wait for the
+    // accumulator, the rest of the row is pulled into L2 meanwhile, and chunk c+1 is loaded while chunk c is processed.
+    const bool has_res = p.mode == CONV_EPI_RESIDUAL && pos_ok;
+    const __nv_bfloat16* rs = p.residual + pos * p.Cout;
+    uint4 rnext[4];
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rnext[j] = *reinterpret_cast<const uint4*>(rs + 8 * j);
+#pragma unroll
+      for (int l = 128; l < BN * 2; l += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rs) + l));
+    }
+    mbar_wait(acc_full_bar, acc_phase);
+    tc_fence_after();
     // pass 1: v = bf16(acc + bias [+ residual]) -> raw output (optional), sum of squares, v back into TMEM
     float ss = 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t rr[32];
       tmem_ld_32x32(t_row + c, rr);
+      uint4 rcur[4];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        if (c + 32 < BN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rnext[j] = *reinterpret_cast<const uint4*>(rs + c + 32 + 8 * j);
+        }
+      }
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c + j));
+        const float4 bb = *reinterpret_cast<const float4*>(s_mod + c + j);
         v[j] = __uint_as_float(rr[j]) + bb.x;
         v[j + 1] = __uint_as_float(rr[j + 1]) + bb.y;
         v[j + 2] = __uint_as_float(rr[j + 2]) + bb.z;
         v[j + 3] = __uint_as_float(rr[j + 3]) + bb.w;
       }
-      if (p.mode == CONV_EPI_RESIDUAL && pos_ok) {
-        const __nv_bfloat16* rs = p.residual + pos * p.Cout + c;
+      if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 u = *reinterpret_cast<const uint4*>(rs + j);
-          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rcur[j]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float2 f = __bfloat1622float2(hh[q]);
-            v[j + 2 * q] += f.x;
-            v[j + 2 * q + 1] += f.y;
+            v[8 * j + 2 * q] += f.x;
+            v[8 * j + 2 * q + 1] += f.y;
           }
         }
       }
@@ -119,7 +158,6 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
     if (w == 1) wps[nw_++] = 0;
     if (w == p.W - 2) wps[nw_++] = p.W + 1;
     // (with H == 3 row 1 is both "1" and "H-2": three copies along that axis)
-    const float* mrow = p.pad_act ? p.pad_mod + static_cast<int64_t>(b) * p.pad_mod_stride : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t rr[32];
@@ -130,12 +168,12 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
       if (p.pad_act) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + p.pad_shift_off + c + j));
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + p.pad_scale_off + c + j));
-          float y0 = fmaf(__uint_as_float(rr[j]) * rstd, 1.f + sc.x, sh.x);
-          float y1 = fmaf(__uint_as_float(rr[j + 1]) * rstd, 1.f + sc.y, sh.y);
-          float y2 = fmaf(__uint_as_float(rr[j + 2]) * rstd, 1.f + sc.z, sh.z);
-          float y3 = fmaf(__uint_as_float(rr[j + 3]) * rstd, 1.f + sc.w, sh.w);
+          const float4 sh = *reinterpret_cast<const float4*>(s_mod + BN + c + j);
+          const float4 sc = *reinterpret_cast<const float4*>(s_mod + 2 * BN + c + j);       // 1 + scale
+          float y0 = fmaf(__uint_as_float(rr[j]) * rstd, sc.x, sh.x);
+          float y1 = fmaf(__uint_as_float(rr[j + 1]) * rstd, sc.y, sh.y);
+          float y2 = fmaf(__uint_as_float(rr[j + 2]) * rstd, sc.z, sh.z);
+          float y3 = fmaf(__uint_as_float(rr[j + 3]) * rstd, sc.w, sh.w);
           y0 = __fdividef(y0, 1.f + __expf(-y0));
           y1 = __fdividef(y1, 1.f + __expf(-y1));
           y2 = __fdividef(y2, 1.f + __expf(-y2));
@@ -159,6 +197,8 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
     }
     return;
   }
+  mbar_wait(acc_full_bar, acc_phase);
+  tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
     uint32_t rr[32];
@@ -261,6 +301,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
   uint64_t* acc_full = bars + 2 * Cfg::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_mod = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);   // [3][BN] (fused epilogue)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform role (see gemm_sm100.cu)
   const int lane = threadIdx.x & 31;
@@ -352,12 +393,18 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int staged_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % num_m, nt = tile / num_m;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+      if (p.pad_out != nullptr) {
+        const int b = mt / (tiles_w * tiles_h * p.T);
+        if (b != staged_b) {
+          conv_stage_mod<BN>(p, b, s_mod, quarter * 32 + lane);
+          staged_b = b;
+        }
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      conv_epilogue_row<BN>(p, t_row, mt, nt, quarter * 32 + lane, true);
+      conv_epilogue_row<BN>(p, t_row, mt, nt, quarter * 32 + lane, true, s_mod, &acc_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -392,7 +439,7 @@ struct ConvPairCfg {
   static constexpr int kBBytes = (BN / 2) * CBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;                  // 256 or 512
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512 + 3 * BN * 4;
 };
 
 template <int BN>
@@ -411,6 +458,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint64_t* acc_full = empty_bar + Cfg::kStages;      // [2]       MMA (multicast) -> own epilogue
   uint64_t* acc_empty = acc_full + 2;                 // [2]       all 8 epilogue warps -> MMA (used in CTA 0 only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_mod = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 512);   // [3][BN] (fused epilogue)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -522,12 +570,19 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int staged_b = -1;
     for (int pt = cluster_id; pt < num_pairs; pt += num_clusters) {
       const int mt = 2 * pt + static_cast<int>(rank);
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+      const int mtc = min(mt, num_m - 1);
+      if (p.pad_out != nullptr) {
+        const int b = mtc / (tiles_w * tiles_h * p.T);
+        if (b != staged_b) {
+          conv_stage_mod<BN>(p, b, s_mod, quarter * 32 + lane);
+          staged_b = b;
+        }
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      conv_epilogue_row<BN>(p, t_row, min(mt, num_m - 1), 0, quarter * 32 + lane, mt < num_m);
+      conv_epilogue_row<BN>(p, t_row, mtc, 0, quarter * 32 + lane, mt < num_m, s_mod, &acc_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
@@ -607,11 +662,12 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
     const int Cf = p.Cout / (p.ft * p.fh * p.fw);
     LTX2_REQUIRE(Cf % 32 == 0, "conv3d: depth-to-space needs C_out/stride_product %% 32 == 0 (got %d)", Cf);
   }
-  // SM-pair kernel when one weight tile covers C_out (LTX2_CONV_PAIR: 0 = never, 1 = 128-channel convs (default),
-  // 2 = also 256-channel convs)
+  // SM-pair kernel when one weight tile covers C_out (LTX2_CONV_PAIR: 0 = never, 1 = 128-channel convs only,
+  // 2 = also 256-channel convs (default)).  Measured on B200 (tools/vae_ab.py, profiles/r2_vae_ab.txt): with the fused
+  // epilogue 1603 -> 1714 (128) -> 1746 frames/s (128 + 256) for the 65-frame decode.
   {
     const char* env = getenv("LTX2_CONV_PAIR");
-    const int lvl = env ? atoi(env) : 1;
+    const int lvl = env ? atoi(env) : 2;
     const bool pair = p.Cout_pad == bn && ((bn == 128 && lvl >= 1) || (bn == 256 && lvl >= 2));
     if (pair) {
       CUtensorMap twp;

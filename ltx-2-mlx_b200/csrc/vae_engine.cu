@@ -588,6 +588,17 @@ int ltx2_vae_profile_read(LtxVae* e, double* ms_out, double* flops_out, int64_t*
   return LTX2_OK;
 }
 
+// per-launch detail of the last profiled decode: conv launch i -> its time (ms) and algorithmic FLOPs
+int ltx2_vae_profile_launch(LtxVae* e, int32_t i, double* ms_out, double* flops_out) {
+  LTX2_REQUIRE(e && ms_out && flops_out && i >= 0 && size_t(i) * 2 < e->prof.used, "vae_profile_launch: bad index");
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  float ms = 0.f;
+  LTX2_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof.events[2 * i], e->prof.events[2 * i + 1]));
+  *ms_out = ms;
+  *flops_out = e->prof.flops[i];
+  return LTX2_OK;
+}
+
 int ltx2_blend_chunk(float* dst, const float* src, int32_t BC, int32_t T_dst, int32_t T_src, int32_t HW, int32_t t0,
                      int32_t overlap, void* stream) {
   return blend_chunk(dst, src, BC, T_dst, T_src, HW, t0, overlap, reinterpret_cast<cudaStream_t>(stream));

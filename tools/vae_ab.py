@@ -45,7 +45,14 @@ def main():
         dec(lat[:, :, :7].contiguous(), timestep=0.05)
         pm, pf, pl = C.c_double(), C.c_double(), C.c_int64()
         _lib.check(L.ltx2_vae_profile_read(dec._h, C.byref(pm), C.byref(pf), C.byref(pl)))
+        per = []
+        for i in range(pl.value):
+            a, b = C.c_double(), C.c_double()
+            _lib.check(L.ltx2_vae_profile_launch(dec._h, i, C.byref(a), C.byref(b)))
+            per.append((a.value, b.value))
         _lib.check(L.ltx2_vae_set_profile(dec._h, 0))
+        if os.environ.get("VAE_AB_DETAIL"):
+            print("   per launch ms (TF/s): " + " ".join(f"{a * 1e3:.0f}us({b / a / 1e9:.0f})" for a, b in per))
         print(f"fuse={fuse} pair={pair}: {65e3 / ms:7.1f} frames/s ({ms:.2f} ms)  conv class {pm.value:.2f} ms "
               f"({pf.value / pm.value / 1e9:.0f} TF/s, {pl.value} launches)  rel diff to unfused/1-CTA {diff:.2e}", flush=True)
 
