@@ -35,6 +35,7 @@ extern "C" {
 #define LTX2_DTYPE_F32 0
 #define LTX2_DTYPE_BF16 1
 #define LTX2_DTYPE_F16 2
+#define LTX2_DTYPE_F8E4M3 3 /* only as the source dtype of ltx2_dit_set_weight_scaled / the operands of ltx2_gemm_e4m3 */
 
 int ltx2_version(void);
 const char* ltx2_last_error(void);
@@ -69,6 +70,12 @@ typedef struct LtxDitConfig {
   float audio_max_pos;              /* 20 (model.py:434) */
   float timestep_scale_multiplier;  /* 1000 */
   float av_ca_timestep_scale_multiplier; /* 1 (model.py:452); the CLI passes 1000 */
+  /* Engine option (no reference counterpart; the reference widens FP8 checkpoints to bf16/fp16 at load,
+   * loader/fp8_loader.py:14-130): keep the linears that are fed by a norm kernel -- self-attention QKV, text-attention Q,
+   * FFN up-projection -- as E4M3 bytes with their weight_scale, quantise their input rows to E4M3 with a per-token
+   * dynamic scale inside the adaLN/RMSNorm kernel, and run them on tcgen05.mma kind::f8f6f4 (twice the bf16 tensor
+   * rate); both scales are applied to the fp32 accumulator in the epilogue.  All other linears stay bf16. */
+  int32_t fp8_linear;
 } LtxDitConfig;
 
 /* One `Modality` (model.py:59-69), flattened.  latent/context dtype per *_dtype. */
@@ -104,6 +111,11 @@ void ltx2_dit_destroy(LtxDit* dit);
  * control of `data` to the caller on `stream`. */
 int ltx2_dit_set_weight(LtxDit* dit, const char* key, const void* data, int32_t dtype, const int64_t* shape,
                         int32_t ndim, void* stream);
+/* An FP8 checkpoint tensor (dtype LTX2_DTYPE_F8E4M3, value = e4m3 * weight_scale; loader/fp8_loader.py:14-32).  With
+ * cfg.fp8_linear the FP8-computed linears keep these bytes as they are; every other Linear weight is widened to bf16 on
+ * the device.  Float dtypes are accepted with weight_scale == 1 (same as ltx2_dit_set_weight). */
+int ltx2_dit_set_weight_scaled(LtxDit* dit, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                               int32_t ndim, float weight_scale, void* stream);
 /* Read-back of the flat {reference_key: tensor} view the LoRA fuse/restore code needs (`velocity_model.parameters()`,
  * scripts/generate.py:1198-1200; pipelines/two_stage.py:180-186): list of keys, shape of one key (returns ndim), and
  * a copy of its values converted to dst_dtype (matrices are stored as bf16, so that is their precision). */
@@ -144,8 +156,9 @@ int ltx2_dit_set_layer_limit(LtxDit* dit, int32_t n);
 /* OneStagePipeline pokes block._cross_attn_scale (one_stage.py:207-222; transformer.py:526-528). */
 int ltx2_dit_set_cross_attn_scale(LtxDit* dit, int32_t block, float scale /* NaN = unset */);
 
-/* Measurement hooks (bench.py): per-class CUDA-event timing of one forward (class 0 = GEMM launches,
- * 1 = attention launches) and the number of kernels this library has launched since load. */
+/* Measurement hooks (bench.py): per-class CUDA-event timing of one forward (class 0 = bf16 GEMM launches,
+ * 1 = attention launches, 2 = FP8 GEMM launches -- counted in class 0 when n_classes == 2) and the number of kernels
+ * this library has launched since load. */
 int ltx2_dit_set_profile(LtxDit* dit, int32_t on);
 int ltx2_dit_profile_read(LtxDit* dit, double* ms_out, double* flops_out, int64_t* launches_out, int32_t n_classes);
 int64_t ltx2_launch_count(void);
@@ -254,6 +267,20 @@ int ltx2_tile_normalize(float* out, const float* wsum, int32_t BC, int64_t plane
 int ltx2_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
                    int32_t mode, const float* bias, void* out, int64_t ldo, const float* gate, int64_t gate_stride,
                    const int32_t* row_cls, float alpha, void* stream);
+
+/* The same GEMM with E4M3 operands (A8 [M,K], W8 [N,K] bytes) on tcgen05.mma kind::f8f6f4:
+ * C = (A8 W8^T) * row_scale[m] * col_scale[n] (+ bias, epilogue modes 0..2 as above).  K % 16 == 0. */
+int ltx2_gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                   int32_t mode, const float* bias, const float* row_scale, const float* col_scale, void* out,
+                   int64_t ldo, void* stream);
+/* FP8 operand preparation: norm_modulate with per-row E4M3 quantisation (out8 [M,D] bytes, row_scale [M] = absmax/448;
+ * out_bf16 optional), and a weight matrix [rows,K] (dtype code) -> E4M3 with one scale per row. */
+int ltx2_norm_modulate_q8(const void* x, int32_t x_dtype, int64_t ldx, void* out8, int64_t ldo8, float* row_scale,
+                          void* out_bf16, int64_t ldo16, int32_t M, int32_t D, int32_t norm_kind, float eps,
+                          const float* mod, int64_t mod_stride, int64_t shift_off, int64_t scale_off,
+                          const int32_t* row_cls, void* stream);
+int ltx2_quantize_rows_e4m3(const void* w, int32_t dtype, int64_t rows, int64_t K, void* out8, float* row_scale,
+                            void* stream);
 
 /* Mode 3 with split-K allowed (up to max_splits K slices accumulate into `out` with vector reductions).  Used by the
  * context-parallel ranks, whose M = N/P rows do not fill the SMs otherwise; accumulation order is not deterministic. */

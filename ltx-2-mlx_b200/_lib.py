@@ -14,7 +14,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libltx2_b200.so")
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, F8E4M3 = 0, 1, 2, 3
 
 
 class Ltx2Error(RuntimeError):
@@ -30,6 +30,7 @@ class LtxDitConfig(C.Structure):
         ("audio_in_channels", C.c_int32), ("audio_out_channels", C.c_int32), ("norm_eps", C.c_float),
         ("positional_embedding_theta", C.c_float), ("max_pos", C.c_float * 3), ("audio_max_pos", C.c_float),
         ("timestep_scale_multiplier", C.c_float), ("av_ca_timestep_scale_multiplier", C.c_float),
+        ("fp8_linear", C.c_int32),
     ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
     "ltx2_dit_create": (_I32, [_P, _P]),
     "ltx2_dit_destroy": (None, [_P]),
     "ltx2_dit_set_weight": (_I32, [_P, _S, _P, _I32, _P, _I32, _P]),
+    "ltx2_dit_set_weight_scaled": (_I32, [_P, _S, _P, _I32, _P, _I32, _F, _P]),
     "ltx2_dit_weight_keys": (_I64, [_P, _P, _I64]),
     "ltx2_dit_weight_shape": (_I32, [_P, _S, _P]),
     "ltx2_dit_get_weight": (_I32, [_P, _S, _P, _I32, _I64, _P]),
@@ -98,6 +100,10 @@ SIGNATURES = {
     "ltx2_tile_accumulate": (_I32, [_P, _P, _P] + [_I32] * 13 + [_P, _P, _P, _P]),
     "ltx2_tile_normalize": (_I32, [_P, _P, _I32, _I64, _P]),
     "ltx2_gemm_bf16": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _F, _P]),
+    "ltx2_gemm_e4m3": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
+    "ltx2_norm_modulate_q8": (_I32, [_P, _I32, _I64, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _I64, _I64,
+                                     _P, _P]),
+    "ltx2_quantize_rows_e4m3": (_I32, [_P, _I32, _I64, _I64, _P, _P, _P]),
     "ltx2_gemm_bf16_splitk": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
     "ltx2_attention": (_I32, [_P, _P, _P, _P] + [_I32] * 6 + [_F, _P, _P, _P]),
     "ltx2_attention_vrows": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P] + [_I32] * 5 + [_F, _P, _P, _P]),
@@ -155,7 +161,7 @@ def ptr(t) -> C.c_void_p:
 
 def dtype_code(t) -> int:
     import torch
-    return {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}[t.dtype]
+    return {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.float8_e4m3fn: F8E4M3}[t.dtype]
 
 
 def stream_ptr() -> C.c_void_p:

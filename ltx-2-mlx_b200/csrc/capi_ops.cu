@@ -51,6 +51,34 @@ int ltx2_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw
   return gemm_bf16(A, lda, W, ldw, M, N, K, ep, S(stream));
 }
 
+int ltx2_gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, int32_t M, int32_t N, int32_t K,
+                   int32_t mode, const float* bias, const float* row_scale, const float* col_scale, void* out,
+                   int64_t ldo, void* stream) {
+  LTX2_REQUIRE(mode >= 0 && mode <= 2, "gemm_e4m3: epilogue mode %d unsupported", mode);
+  GemmEpilogue ep;
+  ep.mode = mode;
+  ep.bias = bias;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.row_scale = row_scale;
+  ep.col_scale = col_scale;
+  return gemm_e4m3(A8, lda, W8, ldw, M, N, K, ep, S(stream));
+}
+
+int ltx2_norm_modulate_q8(const void* x, int32_t x_dtype, int64_t ldx, void* out8, int64_t ldo8, float* row_scale,
+                          void* out_bf16, int64_t ldo16, int32_t M, int32_t D, int32_t norm_kind, float eps,
+                          const float* mod, int64_t mod_stride, int64_t shift_off, int64_t scale_off,
+                          const int32_t* row_cls, void* stream) {
+  LTX2_REQUIRE(x_dtype == LTX2_F32 || x_dtype == LTX2_BF16, "norm_modulate_q8: x must be f32 or bf16");
+  return norm_modulate_q8(x, x_dtype == LTX2_BF16, ldx, out8, ldo8, row_scale, out_bf16, ldo16, M, D, norm_kind, eps,
+                          mod, mod_stride, shift_off, scale_off, row_cls, S(stream));
+}
+
+int ltx2_quantize_rows_e4m3(const void* w, int32_t dtype, int64_t rows, int64_t K, void* out8, float* row_scale,
+                            void* stream) {
+  return quantize_rows_e4m3(w, dtype, rows, K, out8, row_scale, S(stream));
+}
+
 int ltx2_attention(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
                    int32_t Tk, int32_t Tkp, int32_t Dh, float scale, const float* gate_logits, float* lse_out,
                    void* stream) {

@@ -45,6 +45,11 @@ static EncodeTiledFn encode_fn() {
 
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  return make_tensor_map(out, base, 2, rank, dims, strides_bytes, box, swizzle128);
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -58,7 +63,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+  CUresult r = fn(out, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -71,17 +76,17 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 }
 
 int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows) {
+                      uint32_t box_rows, int elem_bytes) {
   // Encoding a tensor map costs a driver call, so the maps of the (static) weight / workspace buffers are cached.
   // The descriptor is COPIED out under the lock: callers never hold a pointer into the cache, so the growth guard
   // below (or a second thread) cannot invalidate a map between two fetches of one launch.
-  typedef std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t> Key;
+  typedef std::tuple<int, const void*, uint64_t, uint64_t, uint64_t, uint32_t, int> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  Key key(dev, base, rows, cols, ld, box_rows);
+  Key key(dev, base, rows, cols, ld, box_rows, elem_bytes);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -89,10 +94,10 @@ int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   }
   if (cache.size() > 16384) cache.clear();  // unbounded growth guard for callers that stream fresh buffers
   uint64_t dims[2] = {cols, rows};
-  uint64_t strides[1] = {ld * 2};
-  uint32_t box[2] = {64, box_rows};
+  uint64_t strides[1] = {ld * elem_bytes};
+  uint32_t box[2] = {static_cast<uint32_t>(128 / elem_bytes), box_rows};      // 128-byte rows (one swizzle atom)
   CUtensorMap m;
-  int s = make_tensor_map_bf16(&m, base, 2, dims, strides, box);
+  int s = make_tensor_map(&m, base, elem_bytes, 2, dims, strides, box, true);
   if (s != LTX2_OK) return s;
   cache[key] = m;
   *out = m;

@@ -51,9 +51,13 @@ void set_error(const char* fmt, ...);
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
 
-// cached 2-D row-major [rows, cols] map with row pitch ld (elements), box = [box_rows, 64]
+int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
+
+// cached 2-D row-major [rows, cols] map with row pitch ld (elements), box = [box_rows, 128 bytes of columns];
+// elem_bytes 2 = bf16, 1 = 8-bit (FP8 E4M3 operands)
 int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows);
+                      uint32_t box_rows, int elem_bytes = 2);
 
 // Per-device state: a process may drive several GPUs (DiT on cuda:0, VAE on cuda:1), and
 // cudaFuncSetAttribute / the SM count / cached device pointers are per device.
@@ -235,6 +239,21 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// E4M3 x E4M3 -> fp32 (kind::f8f6f4: A/B format fields 0 = E4M3), both operands K-major, K = 32 per instruction
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");

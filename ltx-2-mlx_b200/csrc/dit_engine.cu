@@ -38,6 +38,7 @@ namespace {
 
 struct Slot {
   void* dst = nullptr;
+  float* cscale = nullptr;        // storage LTX2_F8E4M3: one scale per output row
   int storage = LTX2_F32;
   int64_t rows = 0, cols = 0;     // cols == 0 -> 1-D of `rows`
   bool loaded = false;
@@ -61,6 +62,8 @@ inline T* offset_ptr(T* p, size_t elems) {
 
 struct LinearW {
   bf16* w = nullptr;
+  uint8_t* w8 = nullptr;          // FP8 mode (cfg.fp8_linear) for the norm-fed linears: E4M3 [out,in] instead of `w`
+  float* cscale = nullptr;        //   and one scale per output row (checkpoint weight_scale, or absmax/448 per row)
   float* b = nullptr;
   int out = 0, in = 0;
 };
@@ -104,6 +107,8 @@ struct StreamBuf {
   int B = 0, N = 0, S = 0, dim = 0, heads = 0, dh = 0, n_cls = 0;
   float* x = nullptr;           // [M, dim] fp32 residual
   bf16* xn = nullptr;           // [M, dim]
+  uint8_t* xq = nullptr;        // [M, dim] E4M3 row-quantised GEMM input (FP8 mode)
+  float* xs = nullptr;          // [M] its per-row scales
   bf16* qkv = nullptr;          // [M, 3*dim]
   bf16* attn = nullptr;         // [M, dim]
   bf16* hidden = nullptr;       // [M, 4*dim]
@@ -174,7 +179,7 @@ struct ProfScope {
     if (on) g_prof->end(e0, st);
   }
 };
-enum { PROF_GEMM = 0, PROF_ATTN = 1 };
+enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_GEMM8 = 2 };   // class 2: FP8 GEMM launches (folded into 0 by 2-class readers)
 
 // Context-parallel state: a cudaMalloc'ed exchange region with the same layout on every rank, mapped into each
 // process through CUDA IPC, so kernels can store into a peer's buffers over NVLink.
@@ -224,6 +229,7 @@ struct LtxDit {
   size_t ws_bytes = 0;
   StreamBuf vb, ab;
   float* scratch = nullptr;         // small fp32 scratch for timestep MLPs
+  float* scale1 = nullptr;          // one device float: per-tensor scale of an FP8 tensor being widened at ingest
   std::vector<float> h_ts;          // host staging for per-token timestep dedupe
   // text-context reuse across steps (ltx2_dit_set_context_tag): per block K|V projection of the context
   // [B*S, 2*inner] and the k-normed, head-split K [B,H,S,Dh]; valid for (cached_tag, cached_B, cached_S)
@@ -275,10 +281,28 @@ struct Layout {
     slot(prefix + ".bias", L.b, LTX2_F32, out, 0);
     return L;
   }
-  LinearW linear(const std::string& prefix, int out, int in) {
+  LinearW linear(const std::string& prefix, int out, int in, bool q8 = false) {
+    if (q8) {
+      uint8_t* w8 = reinterpret_cast<uint8_t*>(ar->take(size_t(out) * in));
+      float* cs = reinterpret_cast<float*>(ar->take(sizeof(float) * out));
+      float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * out));
+      return linear_q8_at(prefix, out, in, w8, cs, b);
+    }
     bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(out) * in));
     float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * out));
     return linear_at(prefix, out, in, w, b);
+  }
+  LinearW linear_q8_at(const std::string& prefix, int out, int in, uint8_t* w8_at, float* cs_at, float* b_at) {
+    LinearW L;
+    L.out = out; L.in = in;
+    L.w8 = w8_at; L.cscale = cs_at; L.b = b_at;
+    if (!dry) {
+      Slot s;
+      s.dst = w8_at; s.cscale = cs_at; s.storage = LTX2_F8E4M3; s.rows = out; s.cols = in;
+      e->slots[prefix + ".weight"] = s;
+    }
+    slot(prefix + ".bias", L.b, LTX2_F32, out, 0);
+    return L;
   }
   AdaLNW adaln(const std::string& prefix, int dim, int n_emb) {
     AdaLNW a;
@@ -289,19 +313,27 @@ struct Layout {
     return a;
   }
   AttnW attention(const std::string& prefix, int query_dim, int ctx_dim, int heads, int dh, bool self_attn,
-                  bool gated) {
+                  bool gated, bool q8 = false) {
     AttnW a;
     a.heads = heads; a.dh = dh; a.inner = heads * dh;
     const int inner = a.inner;
     a.fused_qkv = self_attn;
-    if (self_attn) {
+    if (self_attn && q8) {
+      // fused QKV in E4M3: one byte matrix [3*inner, query_dim], scales and biases [3*inner]
+      uint8_t* w8 = reinterpret_cast<uint8_t*>(ar->take(size_t(3) * inner * query_dim));
+      float* cs = reinterpret_cast<float*>(ar->take(sizeof(float) * 3 * inner));
+      float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * 3 * inner));
+      a.q = linear_q8_at(prefix + ".to_q", inner, query_dim, w8, cs, b);
+      a.kv = linear_q8_at(prefix + ".to_k", inner, ctx_dim, w8 + size_t(inner) * query_dim, cs + inner, b + inner);
+      linear_q8_at(prefix + ".to_v", inner, ctx_dim, w8 + size_t(2) * inner * query_dim, cs + 2 * inner, b + 2 * inner);
+    } else if (self_attn) {
       bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(3) * inner * query_dim));
       float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * 3 * inner));
       a.q = linear_at(prefix + ".to_q", inner, query_dim, w, b);
       a.kv = linear_at(prefix + ".to_k", inner, ctx_dim, offset_ptr(w, size_t(inner) * query_dim), offset_ptr(b, inner));
       linear_at(prefix + ".to_v", inner, ctx_dim, offset_ptr(w, size_t(2) * inner * query_dim), offset_ptr(b, 2 * inner));
     } else {
-      a.q = linear(prefix + ".to_q", inner, query_dim);
+      a.q = linear(prefix + ".to_q", inner, query_dim, q8);
       bf16* w = reinterpret_cast<bf16*>(ar->take(sizeof(bf16) * size_t(2) * inner * ctx_dim));
       float* b = reinterpret_cast<float*>(ar->take(sizeof(float) * 2 * inner));
       a.kv = linear_at(prefix + ".to_k", inner, ctx_dim, w, b);
@@ -321,6 +353,7 @@ void build_layout(LtxDit* e, Arena* ar, bool dry) {
   const LtxDitConfig& c = e->cfg;
   const int D = e->D, Da = e->Da, n = e->n_ada, nl = c.num_layers;
   const bool v2 = c.cross_attention_adaln != 0, gated = c.apply_gated_attention != 0, audio = c.audio_enabled != 0;
+  const bool q8 = c.fp8_linear != 0;     // E4M3 storage + FP8 MMA for the linears fed by a norm kernel
 
   auto stream_w = [&](StreamW& s, const std::string& p, int dim, int in_ch, int out_ch) {
     s.patchify = L.linear(p + "patchify_proj", dim, in_ch);
@@ -356,18 +389,18 @@ void build_layout(LtxDit* e, Arena* ar, bool dry) {
     BlockW tmp;
     BlockW& b = dry ? tmp : e->blocks[i];
     const std::string P = "transformer_blocks." + std::to_string(i) + ".";
-    b.v.attn1 = L.attention(P + "attn1", D, D, c.num_attention_heads, c.attention_head_dim, true, gated);
+    b.v.attn1 = L.attention(P + "attn1", D, D, c.num_attention_heads, c.attention_head_dim, true, gated, q8);
     b.v.attn2 = L.attention(P + "attn2", D, c.cross_attention_dim, c.num_attention_heads, c.attention_head_dim,
-                            false, gated);
-    b.v.ff1 = L.linear(P + "ff.project_in.proj", 4 * D, D);
+                            false, gated, q8);
+    b.v.ff1 = L.linear(P + "ff.project_in.proj", 4 * D, D, q8);
     b.v.ff2 = L.linear(P + "ff.project_out", D, 4 * D);
     b.v.table = L.f32_at(P + "scale_shift_table", offset_ptr(e->table_arena_v, size_t(i) * n * D), n, D);
     if (v2)
       b.v.prompt_table = L.f32_at(P + "prompt_scale_shift_table", offset_ptr(e->ptable_arena_v, size_t(i) * 2 * D), 2, D);
     if (audio) {
-      b.a.attn1 = L.attention(P + "audio_attn1", Da, Da, c.audio_heads, c.audio_head_dim, true, gated);
-      b.a.attn2 = L.attention(P + "audio_attn2", Da, Da, c.audio_heads, c.audio_head_dim, false, gated);
-      b.a.ff1 = L.linear(P + "audio_ff.project_in.proj", 4 * Da, Da);
+      b.a.attn1 = L.attention(P + "audio_attn1", Da, Da, c.audio_heads, c.audio_head_dim, true, gated, q8);
+      b.a.attn2 = L.attention(P + "audio_attn2", Da, Da, c.audio_heads, c.audio_head_dim, false, gated, q8);
+      b.a.ff1 = L.linear(P + "audio_ff.project_in.proj", 4 * Da, Da, q8);
       b.a.ff2 = L.linear(P + "audio_ff.project_out", Da, 4 * Da);
       b.a.table = L.f32_at(P + "audio_scale_shift_table", offset_ptr(e->table_arena_a, size_t(i) * n * Da), n, Da);
       if (v2)
@@ -423,6 +456,8 @@ size_t layout_stream_buf(StreamBuf& sb, Arena& ar, const LtxDitConfig& c, int di
   auto T = [&](size_t bytes) { return ar.take(bytes); };
   sb.x = (float*)T(M * dim * 4);
   sb.xn = (bf16*)T(M * dim * 2);
+  sb.xq = c.fp8_linear ? (uint8_t*)T(M * dim) : nullptr;
+  sb.xs = c.fp8_linear ? (float*)T(M * 4) : nullptr;
   sb.qkv = (bf16*)T(M * 3 * dim * 2);
   sb.attn = (bf16*)T(M * dim * 2);
   sb.hidden = (bf16*)T(M * 4 * dim * 2);
@@ -507,6 +542,21 @@ inline int linear_bf16(const bf16* A, int64_t lda, const LinearW& L, int M, bf16
   return gemm_bf16(A, lda, L.w + size_t(row_off) * L.in, L.in, M, N, L.in, ep, st);
 }
 
+// the same linear with E4M3 operands: A8 [M, in] row-quantised by norm_modulate_q8 (scales a_scale[M]), weight L.w8
+inline int linear_q8(const uint8_t* A8, const float* a_scale, int64_t lda, const LinearW& L, int M, bf16* out, int64_t ldo,
+                     bool gelu, cudaStream_t st, int n_rows = -1, int row_off = 0) {
+  GemmEpilogue ep;
+  ep.mode = gelu ? GEMM_EPI_BF16_GELU : GEMM_EPI_BF16;
+  ep.bias = L.b + row_off;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.row_scale = a_scale;
+  ep.col_scale = L.cscale + row_off;
+  const int N = n_rows < 0 ? L.out : n_rows;
+  ProfScope ps(PROF_GEMM8, 2.0 * M * double(N) * L.in, st);
+  return gemm_e4m3(A8, lda, L.w8 + size_t(row_off) * L.in, L.in, M, N, L.in, ep, st);
+}
+
 inline int linear_residual(const bf16* A, int64_t lda, const LinearW& L, int M, float* x, int64_t ldx,
                            const float* gate, int64_t gate_stride, const int* row_cls, float alpha, cudaStream_t st) {
   GemmEpilogue ep;
@@ -558,6 +608,8 @@ struct AttnCall {
   const float *qcos, *qsin, *kcos, *ksin;              // rope tables or null
   const bf16* kv_pre = nullptr;                        // K|V projection already available ([B*Tk, 2*inner]): skip that GEMM
   const bf16* kh_pre = nullptr;                        // K already normalised and head-split ([B,H,Tk,Dh]): skip the k-norm
+  const uint8_t* xq8 = nullptr;                        // FP8 mode: the query-side input row-quantised to E4M3 ...
+  const float* xq8_scale = nullptr;                    // ... and its per-row scales (norm_modulate_q8)
 };
 
 // Attention.__call__ up to (not including) to_out: writes sb.attn [B*Tq, inner]
@@ -567,12 +619,19 @@ int run_attention_core(LtxDit* e, StreamBuf& sb, const AttnCall& c, int B, cudaS
   const float eps = e->cfg.norm_eps;
   const bf16 *qp, *kp, *vp;
   int64_t ldq, ldk;
+  LTX2_REQUIRE(w.q.w8 == nullptr || c.xq8 != nullptr, "attention: FP8 projection without a quantised input");
   if (w.fused_qkv) {
-    LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    if (w.q.w8 != nullptr)
+      LTX2_PROPAGATE(linear_q8(c.xq8, c.xq8_scale, c.ldq, w.q, c.Mq, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    else
+      LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
     qp = sb.qkv; kp = sb.qkv + inner; vp = sb.qkv + 2 * inner;
     ldq = ldk = 3 * inner;
   } else {
-    LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, inner, false, st));
+    if (w.q.w8 != nullptr)
+      LTX2_PROPAGATE(linear_q8(c.xq8, c.xq8_scale, c.ldq, w.q, c.Mq, sb.qkv, inner, false, st));
+    else
+      LTX2_PROPAGATE(linear_bf16(c.xq, c.ldq, w.q, c.Mq, sb.qkv, inner, false, st));
     const bf16* kvp = c.kv_pre;
     if (kvp == nullptr) {
       LTX2_PROPAGATE(linear_bf16(c.xkv, c.ldkv, w.kv, B * c.Tk, sb.kv, 2 * inner, false, st));
@@ -631,6 +690,9 @@ int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out) {
                "dit_create: audio_head_dim must be 64 or 128");
   LTX2_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 64, "dit_create: num_layers must be in 1..64");
   LTX2_REQUIRE(cfg->in_channels % 8 == 0 && cfg->out_channels % 32 == 0, "dit_create: in_channels %% 8, out_channels %% 32");
+  LTX2_REQUIRE(!cfg->fp8_linear || ((cfg->num_attention_heads * cfg->attention_head_dim) % 16 == 0 &&
+                                    (!cfg->audio_enabled || (cfg->audio_heads * cfg->audio_head_dim) % 16 == 0)),
+               "dit_create: fp8_linear needs model widths that are multiples of 16");
   LtxDit* e = new LtxDit();
   e->cfg = *cfg;
   e->D = cfg->num_attention_heads * cfg->attention_head_dim;
@@ -656,6 +718,7 @@ int ltx2_dit_create(const LtxDitConfig* cfg, LtxDit** out) {
   std::vector<float> gv = make_freq_grid(cfg->positional_embedding_theta, 3, e->D);
   e->nf_video = (int)gv.size();
   int s = upload(gv, &e->fg_video);
+  if (s == LTX2_OK && cudaMalloc(&e->scale1, 16) != cudaSuccess) s = LTX2_ERR_NOMEM;
   if (s == LTX2_OK && cfg->audio_enabled) {
     std::vector<float> ga = make_freq_grid(cfg->positional_embedding_theta, 1, e->Da);
     e->nf_audio = (int)ga.size();
@@ -681,13 +744,14 @@ void ltx2_dit_destroy(LtxDit* e) {
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   if (e->kvc) cudaFree(e->kvc);
+  if (e->scale1) cudaFree(e->scale1);
   if (e->fg_video) cudaFree(e->fg_video);
   if (e->fg_audio) cudaFree(e->fg_audio);
   delete e;
 }
 
-int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
-                        int32_t ndim, void* stream) {
+static int set_weight_impl(LtxDit* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                           int32_t ndim, float scale, void* stream) {
   LTX2_REQUIRE(e && key && data, "dit_set_weight: null argument");
   auto it = e->slots.find(key);
   if (it == e->slots.end()) {
@@ -706,11 +770,40 @@ int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dt
     return LTX2_ERR_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int r = s.storage == LTX2_BF16 ? cast_to_bf16(data, dtype, s.dst, expect, st)
-                                 : cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), expect, st);
+  int r;
+  if (dtype == LTX2_F8E4M3) {
+    // an FP8 checkpoint tensor: value = e4m3 * weight_scale (loader/fp8_loader.py:14-32)
+    LTX2_REQUIRE(s.cols != 0, "dit_set_weight: '%s' is not a matrix; FP8 data is only accepted for Linear weights", key);
+    if (s.storage == LTX2_F8E4M3) {
+      // kept quantised: the checkpoint's own bytes feed the FP8 MMA, the scale goes to the epilogue
+      LTX2_CUDA_CHECK(cudaMemcpyAsync(s.dst, data, size_t(expect), cudaMemcpyDeviceToDevice, st));
+      r = fill_f32(s.cscale, scale, s.rows, st);
+    } else if (s.storage == LTX2_BF16) {
+      LTX2_PROPAGATE(fill_f32(e->scale1, scale, 1, st));
+      r = dequant_e4m3(data, e->scale1, 0, s.rows, s.cols, s.dst, LTX2_BF16, st);
+    } else {
+      set_error("dit_set_weight: '%s' is stored as fp32; FP8 data not accepted", key);
+      return LTX2_ERR_INVALID;
+    }
+  } else {
+    LTX2_REQUIRE(scale == 1.0f, "dit_set_weight: a weight_scale is only meaningful for FP8 data");
+    if (s.storage == LTX2_F8E4M3) r = quantize_rows_e4m3(data, dtype, s.rows, s.cols, s.dst, s.cscale, st);
+    else if (s.storage == LTX2_BF16) r = cast_to_bf16(data, dtype, s.dst, expect, st);
+    else r = cast_to_f32(data, dtype, reinterpret_cast<float*>(s.dst), expect, st);
+  }
   if (r == LTX2_OK) s.loaded = true;
   e->cached_tag = 0;          // cached context K/V were projected with the old weights (LoRA fuse / restore)
   return r;
+}
+
+int ltx2_dit_set_weight(LtxDit* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                        int32_t ndim, void* stream) {
+  return set_weight_impl(e, key, data, dtype, shape, ndim, 1.0f, stream);
+}
+
+int ltx2_dit_set_weight_scaled(LtxDit* e, const char* key, const void* data, int32_t dtype, const int64_t* shape,
+                               int32_t ndim, float weight_scale, void* stream) {
+  return set_weight_impl(e, key, data, dtype, shape, ndim, weight_scale, stream);
 }
 
 // read a tensor back (engine storage -> dst_dtype); used by the LoRA fuse/restore flows that read
@@ -727,6 +820,7 @@ int ltx2_dit_get_weight(LtxDit* e, const char* key, void* dst, int32_t dst_dtype
   LTX2_REQUIRE(n == expect, "dit_get_weight: '%s' has %lld elements, buffer holds %lld", key, (long long)expect, (long long)n);
   LTX2_REQUIRE(s.loaded, "dit_get_weight: '%s' has not been set", key);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (s.storage == LTX2_F8E4M3) return dequant_e4m3(s.dst, s.cscale, 1, s.rows, s.cols, dst, dst_dtype, st);
   if (dst_dtype == LTX2_F32) return cast_to_f32(s.dst, s.storage, reinterpret_cast<float*>(dst), n, st);
   if (dst_dtype == LTX2_BF16) return cast_to_bf16(s.dst, s.storage, dst, n, st);
   set_error("dit_get_weight: destination dtype %d unsupported", dst_dtype);
@@ -935,6 +1029,15 @@ int prepare_cross_mod(LtxDit* e, StreamBuf& sb, const AdaLNW& ss, const AdaLNW& 
   return LTX2_OK;
 }
 
+// RMSNorm + modulation of the residual stream as the E4M3 input of an FP8 linear: sb.xq / sb.xs (and the bf16 copy in
+// `out16` when a bf16 consumer of the same rows exists, e.g. the gate-logit projection)
+int rms_mod_q8(const LtxDit* e, const StreamBuf& sb, bf16* out16, const float* mod, int64_t mod_stride, int shift_row,
+               int scale_row, const int* cls, cudaStream_t st) {
+  const int M = sb.B * sb.N;
+  return norm_modulate_q8(sb.x, 0, sb.dim, sb.xq, sb.dim, sb.xs, out16, sb.dim, M, sb.dim, NORM_RMS, e->cfg.norm_eps, mod,
+                          mod_stride, int64_t(shift_row) * sb.dim, int64_t(scale_row) * sb.dim, cls, st);
+}
+
 int rms_mod(const LtxDit* e, const StreamBuf& sb, bf16* out, const float* mod, int64_t mod_stride, int shift_row,
             int scale_row, const int* cls, cudaStream_t st) {
   const int M = sb.B * sb.N;
@@ -955,8 +1058,13 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     CpState& cp = e->cp;
     const AttnW& aw = w.attn1;
     const int H = aw.heads, Dh = aw.dh, inner = aw.inner, Hl = cp.heads_local, Nt = cp.n_total;
-    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
-    LTX2_PROPAGATE(linear_bf16(sb.xn, dim, aw.q, M, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    if (aw.q.w8 != nullptr) {
+      LTX2_PROPAGATE(rms_mod_q8(e, sb, aw.gate.w != nullptr ? sb.xn : nullptr, mod, ms, 0, 1, sb.row_cls, st));
+      LTX2_PROPAGATE(linear_q8(sb.xq, sb.xs, dim, aw.q, M, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    } else {
+      LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
+      LTX2_PROPAGATE(linear_bf16(sb.xn, dim, aw.q, M, sb.qkv, 3 * inner, false, st, 3 * inner, 0));
+    }
     HeadScatter hs = {};
     for (int r = 0; r < cp.world; ++r) {
       hs.q[r] = reinterpret_cast<bf16*>(cp.peer_base[r] + cp.off_q);
@@ -1019,23 +1127,37 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     LTX2_PROPAGATE(cp_barrier(e->cp.peer_flags_dev, reinterpret_cast<uint32_t*>(e->cp.region + e->cp.off_flags),
                               e->cp.rank, e->cp.world, ++e->cp.epoch, st));
   } else if (!skip_self) {
-    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
     AttnCall a{&w.attn1, sb.xn, dim, M, N, sb.xn, dim, N, sb.cos, sb.sin, sb.cos, sb.sin};
+    if (w.attn1.q.w8 != nullptr) {
+      LTX2_PROPAGATE(rms_mod_q8(e, sb, w.attn1.gate.w != nullptr ? sb.xn : nullptr, mod, ms, 0, 1, sb.row_cls, st));
+      a.xq8 = sb.xq;
+      a.xq8_scale = sb.xs;
+    } else {
+      LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 0, 1, sb.row_cls, st));
+    }
     LTX2_PROPAGATE(run_attention_core(e, sb, a, B, st));
     LTX2_PROPAGATE(linear_residual(sb.attn, w.attn1.inner, w.attn1.o, M, sb.x, dim, mod + 2 * dim, ms, sb.row_cls,
                                    1.0f, st));
   }
   const bf16* ctx = sb.ctx;
+  const bool tq8 = w.attn2.q.w8 != nullptr;
+  bf16* txn = (!tq8 || w.attn2.gate.w != nullptr) ? sb.xn : nullptr;      // bf16 rows only if somebody reads them
   if (v2) {
-    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 6, 7, sb.row_cls, st));
+    if (tq8) LTX2_PROPAGATE(rms_mod_q8(e, sb, txn, mod, ms, 6, 7, sb.row_cls, st));
+    else LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 6, 7, sb.row_cls, st));
     const float* pm = sb.prompt_mod + size_t(layer) * B * 2 * dim;
     LTX2_PROPAGATE(norm_modulate(sb.ctx, 1, dim, sb.ctx_mod, dim, B * S, dim, NORM_NONE, c.norm_eps, pm,
                                  int64_t(2) * dim, 0, dim, sb.ctx_batch, st));
     ctx = sb.ctx_mod;
   } else {
-    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, nullptr, 0, 0, 0, nullptr, st));
+    if (tq8) LTX2_PROPAGATE(rms_mod_q8(e, sb, txn, nullptr, 0, 0, 0, nullptr, st));
+    else LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, nullptr, 0, 0, 0, nullptr, st));
   }
   AttnCall a{&w.attn2, sb.xn, dim, M, N, ctx, dim, S, nullptr, nullptr, nullptr, nullptr};
+  if (tq8) {
+    a.xq8 = sb.xq;
+    a.xq8_scale = sb.xs;
+  }
   const bool region_kv = e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !v2 && !skip_self;
   if (&sb == &e->vb && e->ctx_cache_on) {
     // V1: the context K/V of this block do not depend on sigma -- computed by the first forward of a sample, reused after
@@ -1066,8 +1188,13 @@ int run_ffn(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer, cudaStre
   const int dim = sb.dim, M = sb.B * sb.N, n = e->n_ada;
   const float* mod = sb.mod + size_t(layer) * sb.n_cls * n * dim;
   const int64_t ms = int64_t(n) * dim;
-  LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 3, 4, sb.row_cls, st));
-  LTX2_PROPAGATE(linear_bf16(sb.xn, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
+  if (w.ff1.w8 != nullptr) {
+    LTX2_PROPAGATE(rms_mod_q8(e, sb, nullptr, mod, ms, 3, 4, sb.row_cls, st));
+    LTX2_PROPAGATE(linear_q8(sb.xq, sb.xs, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
+  } else {
+    LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 3, 4, sb.row_cls, st));
+    LTX2_PROPAGATE(linear_bf16(sb.xn, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
+  }
   return linear_residual(sb.hidden, 4 * dim, w.ff2, M, sb.x, dim, mod + 5 * dim, ms, sb.row_cls, 1.0f, st);
 }
 
@@ -1310,9 +1437,10 @@ extern "C" int ltx2_dit_profile_read(LtxDit* e, double* ms_out, double* flops_ou
   for (auto& r : e->prof.recs) {
     float ms = 0.f;
     LTX2_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof.events[r.e0], e->prof.events[r.e0 + 1]));
-    ms_out[r.cat] += ms;
-    flops_out[r.cat] += r.work;
-    launches_out[r.cat] += 1;
+    const int cat = r.cat < n_classes ? r.cat : 0;
+    ms_out[cat] += ms;
+    flops_out[cat] += r.work;
+    launches_out[cat] += 1;
   }
   return LTX2_OK;
 }

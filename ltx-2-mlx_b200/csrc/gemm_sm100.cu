@@ -52,6 +52,14 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& ep, uint32_t t_
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ep.row_scale != nullptr) {            // FP8 operands: de-scale the accumulator (fp8ops.cu)
+        const float rsc = __ldg(ep.row_scale + row);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.col_scale + col0 + j));
+          v[j] *= rsc * cs.x; v[j + 1] *= rsc * cs.y; v[j + 2] *= rsc * cs.z; v[j + 3] *= rsc * cs.w;
+        }
+      }
       if (ep.bias != nullptr && first_slice) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -108,11 +116,14 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& ep, uint32_t t_
   }
 }
 
-template <int BN>
+// FP8 = true: the same pipeline with E4M3 operands -- a 128-byte smem row holds 128 K elements instead of 64, the MMA is
+// kind::f8f6f4 with K = 32 per instruction, so a K block feeds twice the FLOPs for the same bytes and tensor clocks.
+template <int BN, bool FP8 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  int M, int N, int K, int splits, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
+  constexpr int BKE = FP8 ? 2 * BK : BK;              // K elements per 128-byte row
   pdl_trigger();                                     // the next kernel may become resident under my tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -135,7 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // output with vector reductions, so small-M GEMMs (context-parallel ranks) still fill the SMs
   const int num_mn = num_m * num_n;
   const int num_tiles = num_mn * splits;
-  const int num_kb = (K + BK - 1) / BK;
+  const int num_kb = (K + BKE - 1) / BKE;
   const int kb_per = (num_kb + splits - 1) / splits;
 
   if (warp == 0 && lane == 0) {
@@ -175,8 +186,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BK, n0);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BKE, m0);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BKE, n0);
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -184,7 +195,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = FP8 ? umma_idesc_e4m3(BM, BN) : umma_idesc_bf16(BM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -203,8 +214,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (leader) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per K=16 step inside the 128B swizzle atom (descriptor address is in 16 B units)
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            // +32 B per MMA K step (16 bf16 / 32 E4M3 elements) inside the 128B swizzle atom (address in 16 B units)
+            if (FP8) umma_f8_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -668,19 +680,19 @@ int launch_gemm2(const CUtensorMap* tw, const CUtensorMap* tx128, const CUtensor
   return LTX2_OK;
 }
 
-template <int BN>
+template <int BN, bool FP8 = false>
 int launch_gemm(const CUtensorMap* ta, const CUtensorMap* tb, int M, int N, int K, int splits, const GemmEpilogue& ep,
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static PerDeviceOnce configured;
   if (configured.first()) {
-    LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  LTX2_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, *ta, *tb, M, N, K,
-                             splits, ep));
+  LTX2_CUDA_CHECK(launch_pdl(gemm_bf16_kernel<BN, FP8>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, *ta, *tb, M,
+                             N, K, splits, ep));
   count_launch();
   return LTX2_OK;
 }
@@ -834,6 +846,28 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
     case 128: return launch_gemm<128>(&ta, &tb, M, N, K, splits, ep, stream);
     case 64: return launch_gemm<64>(&ta, &tb, M, N, K, splits, ep, stream);
     default: return launch_gemm<32>(&ta, &tb, M, N, K, splits, ep, stream);
+  }
+}
+
+int gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t stream) {
+  LTX2_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_e4m3: empty problem M=%d N=%d K=%d", M, N, K);
+  LTX2_REQUIRE(N % 32 == 0, "gemm_e4m3: N=%d must be a multiple of 32", N);
+  LTX2_REQUIRE(K % 16 == 0 && lda % 16 == 0 && ldw % 16 == 0, "gemm_e4m3: K/lda/ldw must be multiples of 16 (16 B rows)");
+  LTX2_REQUIRE((reinterpret_cast<uintptr_t>(A8) & 15) == 0 && (reinterpret_cast<uintptr_t>(W8) & 15) == 0,
+               "gemm_e4m3: operands must be 16-byte aligned");
+  LTX2_REQUIRE(ep.out != nullptr && ep.row_scale != nullptr && ep.col_scale != nullptr,
+               "gemm_e4m3: output, row_scale and col_scale are required");
+  // the standard 128-token-row kernel only (n_out_peers = 1 removes the shard-shaped bf16 candidates from the plan)
+  const GemmPlan plan = plan_gemm(M, N, (K + 1) / 2, ep.mode, ep.max_splits, 1);
+  CUtensorMap ta, tb;
+  LTX2_PROPAGATE(get_tensor_map_2d(&ta, A8, M, K, lda, BM, 1));
+  LTX2_PROPAGATE(get_tensor_map_2d(&tb, W8, N, K, ldw, plan.bn, 1));
+  switch (plan.bn) {
+    case 256: return launch_gemm<256, true>(&ta, &tb, M, N, K, plan.splits, ep, stream);
+    case 128: return launch_gemm<128, true>(&ta, &tb, M, N, K, plan.splits, ep, stream);
+    case 64: return launch_gemm<64, true>(&ta, &tb, M, N, K, plan.splits, ep, stream);
+    default: return launch_gemm<32, true>(&ta, &tb, M, N, K, plan.splits, ep, stream);
   }
 }
 

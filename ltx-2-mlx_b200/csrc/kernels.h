@@ -30,9 +30,18 @@ struct GemmEpilogue {
   void* out_peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int n_out_peers = 0;             // bf16 modes: > 0 replicates the store into every out_peers[i] (peer-memory broadcast)
   int max_splits = 1;              // > 1 allows split-K for the residual mode (accumulation order then varies run to run)
+  // FP8 path (gemm_e4m3): acc * row_scale[row] * col_scale[col] before the bias -- the dynamic per-token scale of the
+  // E4M3 activation row and the (per-tensor or per-output-channel) scale of the E4M3 weight
+  const float* row_scale = nullptr;
+  const float* col_scale = nullptr;
 };
 
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
+              cudaStream_t stream);
+
+// Same contract with E4M3 operands (A [M,K], W [N,K] bytes; tcgen05.mma kind::f8f6f4, fp32 accumulate, K = 32 per
+// instruction: twice the bf16 tensor rate); ep.row_scale / ep.col_scale are required.  K % 16 == 0.
+int gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
               cudaStream_t stream);
 
 // Which kernel and tiling gemm_bf16 takes for a problem (pure host logic: needs no GPU, uses 148 SMs when no device
@@ -173,6 +182,20 @@ int denoise_update(const float* sample, const float* cond, const float* uncond, 
                    const float* clean, float sigma, float sigma_next, float* out, float* denoised_out, int M, int C,
                    cudaStream_t stream);
 
+// ---- FP8 operand preparation (fp8ops.cu) ----
+// norm_modulate + per-row E4M3 quantisation: out8 [M,D] bytes, row_scale [M] = absmax/448; out_bf16 (optional) also
+// receives the unquantised bf16 row (consumers that stay bf16, e.g. the gate-logit projection)
+int norm_modulate_q8(const void* x, int x_is_bf16, int64_t ldx, void* out8, int64_t ldo8, float* row_scale,
+                     void* out_bf16, int64_t ldo16, int M, int D, int norm_kind, float eps, const float* mod,
+                     int64_t mod_stride, int64_t shift_off, int64_t scale_off, const int* row_cls, cudaStream_t stream);
+// weight [rows,K] (dtype code) -> E4M3 bytes with one scale per row
+int quantize_rows_e4m3(const void* w, int dtype, int64_t rows, int64_t K, void* out8, float* row_scale,
+                       cudaStream_t stream);
+// dst = e4m3(src) * scale[row * scale_stride]  (scale_stride 0 = per-tensor scale); dst fp32 or bf16
+int dequant_e4m3(const void* src8, const float* scale, int scale_stride, int64_t rows, int64_t K, void* dst,
+                 int dst_dtype, cudaStream_t stream);
+int fill_f32(float* dst, float v, int64_t n, cudaStream_t stream);
+
 int cast_to_bf16(const void* src, int src_dtype, void* dst, int64_t n, cudaStream_t stream);
 int cast_to_f32(const void* src, int src_dtype, float* dst, int64_t n, cudaStream_t stream);
 
@@ -249,6 +272,6 @@ int tile_normalize(float* out, const float* wsum, int BC, int64_t plane, cudaStr
 int video_to_uint8(const float* video, uint8_t* out, int T, int H, int W, cudaStream_t stream);
 
 // dtype codes shared with the C ABI
-enum { LTX2_F32 = 0, LTX2_BF16 = 1, LTX2_F16 = 2 };
+enum { LTX2_F32 = 0, LTX2_BF16 = 1, LTX2_F16 = 2, LTX2_F8E4M3 = 3 };
 
 }  // namespace ltx2

@@ -5,6 +5,8 @@ Mirrors the call surface of ``load_transformer_weights(model, path, ...)``
 (LTX_2_MLX/model/video_vae/simple_decoder.py:566).  Tensors stream one at a time from the
 file to the device; the engine converts to its storage type (bf16 matrices, fp32
 biases/norm weights/adaLN tables) on the GPU, so there is no torch->numpy->fp32 hop.
+FP8 (E4M3) checkpoint tensors are handed over as bytes + weight_scale (``loader/fp8_loader.py:14-130``
+semantics): an engine built with ``fp8_linear`` keeps them quantised for its FP8 GEMMs.
 """
 from __future__ import annotations
 
@@ -37,14 +39,19 @@ def convert_pytorch_key_to_mlx(pytorch_key: str, include_audio: bool = False) ->
 
 
 def iter_engine_weights(tensors: Iterable[Tuple[str, torch.Tensor]], include_audio: bool,
-                        fp8_scales: Optional[Dict[str, float]] = None) -> Iterator[Tuple[str, torch.Tensor]]:
+                        fp8_scales: Optional[Dict[str, float]] = None) -> Iterator[tuple]:
     for ck, t in tensors:
         if not ck.startswith(DIT_PREFIX) or ck.endswith(".weight_scale"):
             continue
         key = convert_pytorch_key_to_mlx(ck[len(DIT_PREFIX):], include_audio=include_audio)
         if key is None:
             continue
-        if fp8_scales and ck in fp8_scales:               # fp8_loader.py:14-32: weight * weight_scale
+        if t.dtype == torch.float8_e4m3fn:
+            # fp8_loader.py:14-32: value = weight_fp8 * weight_scale.  The bytes and the scale go to the engine as they
+            # are: FP8-computed linears keep them (cfg.fp8_linear), all other layers widen to bf16 on the device.
+            yield key, t, float(fp8_scales.get(ck, 1.0)) if fp8_scales else 1.0
+            continue
+        if fp8_scales and ck in fp8_scales:
             t = t.to(torch.float32) * fp8_scales[ck]
         elif t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             t = t.to(torch.float32)

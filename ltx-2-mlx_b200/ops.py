@@ -185,3 +185,45 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, causal: bo
     check(lib().ltx2_conv3d(ptr(x), ptr(weight), dtype_code(weight), ptr(bias), dtype_code(bias), ptr(out), B, T, H, W,
                             Cin, Cout, int(causal), ptr(ws), stream_ptr()), "ltx2_conv3d")
     return out
+
+
+# ---- FP8 (E4M3) path --------------------------------------------------------------------------------------------
+def quantize_rows_e4m3(w: torch.Tensor):
+    """[rows, K] float tensor -> (E4M3 bytes as torch.float8_e4m3fn [rows, K], per-row scales fp32 [rows])."""
+    _cuda(w)
+    rows, K = w.shape
+    out = torch.empty(rows, K, device=w.device, dtype=torch.uint8)
+    scale = torch.empty(rows, device=w.device, dtype=torch.float32)
+    check(lib().ltx2_quantize_rows_e4m3(ptr(w), dtype_code(w), rows, K, ptr(out), ptr(scale), stream_ptr()),
+          "ltx2_quantize_rows_e4m3")
+    return out.view(torch.float8_e4m3fn), scale
+
+
+def norm_modulate_q8(x: torch.Tensor, *, kind: int, eps: float = 1e-6, mod: Optional[torch.Tensor] = None,
+                     shift_row: int = 0, scale_row: int = 1, row_cls: Optional[torch.Tensor] = None,
+                     want_bf16: bool = False):
+    """norm_modulate whose output row is quantised to E4M3 with a per-row scale: (q [M,D] float8_e4m3fn, scale [M]
+    [, bf16 copy])."""
+    _cuda(x, mod, row_cls)
+    M, D = x.shape
+    q = torch.empty(M, D, device=x.device, dtype=torch.uint8)
+    sc = torch.empty(M, device=x.device, dtype=torch.float32)
+    o16 = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    ms = mod.stride(0) if mod is not None else 0
+    check(lib().ltx2_norm_modulate_q8(ptr(x), dtype_code(x), x.stride(0), ptr(q), D, ptr(sc), ptr(o16), D, M, D, kind,
+                                      eps, ptr(mod), ms, shift_row * D, scale_row * D, ptr(row_cls), stream_ptr()),
+          "ltx2_norm_modulate_q8")
+    q = q.view(torch.float8_e4m3fn)
+    return (q, sc, o16) if want_bf16 else (q, sc)
+
+
+def gemm_e4m3(a8: torch.Tensor, a_scale: torch.Tensor, w8: torch.Tensor, w_scale: torch.Tensor,
+              bias: Optional[torch.Tensor] = None, *, mode: int = EPI_BF16) -> torch.Tensor:
+    """C = (A8 W8^T) * a_scale[:, None] * w_scale[None, :] (+ bias, epilogue modes 0..2) on the FP8 tensor pipe."""
+    _cuda(a8, w8, a_scale, w_scale, bias)
+    M, K = a8.shape
+    N = w8.shape[0]
+    out = torch.empty(M, N, device=a8.device, dtype=torch.float32 if mode == EPI_F32 else torch.bfloat16)
+    check(lib().ltx2_gemm_e4m3(ptr(a8), a8.stride(0), ptr(w8), w8.stride(0), M, N, K, mode, ptr(bias), ptr(a_scale),
+                               ptr(w_scale), ptr(out), out.stride(0), stream_ptr()), "ltx2_gemm_e4m3")
+    return out

@@ -212,7 +212,11 @@ class LTXModel:
         cross_attention_adaln: bool = False,
         apply_gated_attention: bool = False,
         device: Union[str, torch.device] = "cuda",
+        fp8_linear: Optional[bool] = None,
     ):
+        """`fp8_linear` (engine option, default: environment LTX2_FP8=1): keep the norm-fed linears (self-attention QKV,
+        text-attention Q, FFN up) as E4M3 with their weight_scale and run them on the FP8 tensor pipe with per-token
+        dynamic activation scales; FP8 checkpoint tensors of those layers are then ingested byte-for-byte."""
         if getattr(model_type, "name", None) in LTXModelType.__members__ and not isinstance(model_type, LTXModelType):
             model_type = LTXModelType[model_type.name]          # accept the reference's own enum
         if model_type == LTXModelType.AudioOnly:
@@ -255,6 +259,10 @@ class LTXModel:
         cfg.audio_max_pos = float(self.AUDIO_CROSS_PE_MAX_POS)
         cfg.timestep_scale_multiplier = float(timestep_scale_multiplier)
         cfg.av_ca_timestep_scale_multiplier = float(av_ca_timestep_scale_multiplier)
+        if fp8_linear is None:
+            fp8_linear = os.environ.get("LTX2_FP8", "0") == "1"
+        self.fp8_linear = bool(fp8_linear)
+        cfg.fp8_linear = int(self.fp8_linear)
         self._cfg = cfg
         # text-context reuse across steps (V1 models; ltx2_dit_set_context_tag): on unless LTX2_CTX_CACHE=0
         self.reuse_context = os.environ.get("LTX2_CTX_CACHE", "1") != "0"
@@ -281,11 +289,17 @@ class LTXModel:
         reference's MLX-side names.  Returns the number of tensors consumed."""
         n = 0
         with torch.cuda.device(self.device):
-            for key, value in (weights.items() if isinstance(weights, dict) else weights):
-                t = to_device(value, self.device)
+            for item in (weights.items() if isinstance(weights, dict) else weights):
+                # (key, tensor) or (key, fp8_tensor, weight_scale): an FP8 checkpoint tensor with its per-tensor scale
+                key, value = item[0], item[1]
+                scale = float(item[2]) if len(item) > 2 else 1.0
+                if isinstance(value, torch.Tensor) and value.dtype == torch.float8_e4m3fn:
+                    t = value.to(self.device, non_blocking=True).contiguous()
+                else:
+                    t = to_device(value, self.device)
                 shape = (C.c_int64 * max(t.ndim, 1))(*(t.shape if t.ndim else (1,)))
-                st = lib().ltx2_dit_set_weight(self._h, key.encode(), ptr(t), dtype_code(t), shape, max(t.ndim, 1),
-                                               stream_ptr())
+                st = lib().ltx2_dit_set_weight_scaled(self._h, key.encode(), ptr(t), dtype_code(t), shape,
+                                                      max(t.ndim, 1), scale, stream_ptr())
                 if st == -2 and not strict:       # LTX2_ERR_NOKEY: not a tensor of this model
                     continue
                 check(st, f"set_weight({key})")

@@ -168,3 +168,26 @@ def test_vae_base128_v20_stack_matches_oracle():
     assert out.shape == ref.shape == (1, 3, 9, 512, 768)
     assert rel(out, ref) < 3e-2, rel(out, ref)
     assert pearson(out, ref) > 0.999
+
+
+def test_fp8_linears_19b_width_four_blocks():
+    """The FP8 linear path (E4M3 weights kept quantised, per-token E4M3 activations, tcgen05.mma kind::f8f6f4) at the
+    benchmarked width: 4 blocks, N = 3456, against the oracle on the DEQUANTISED weights read back from the engine.
+    Tolerance: rel L2 <= 6e-2, Pearson >= 0.995 (tests/test_fp8_gpu.py explains the bound)."""
+    from ltx2_b200 import synthetic
+    from ltx2_b200.loader import iter_engine_weights
+    from ltx2_b200.transformer import LTXModel, LTXModelType, Modality
+    from oracle import dit_oracle as O
+    dev = torch.device("cuda:0")
+    cfg = synthetic.DitConfig(num_layers=4)
+    m = LTXModel(model_type=LTXModelType.VideoOnly, num_layers=4, device=dev, fp8_linear=True)
+    m.load_weights(iter_engine_weights(synthetic.iter_dit_weights(cfg, seed=5, device=dev, dtype=torch.bfloat16), False))
+    assert m.missing_weights() == []
+    w = {k: m.get_weight(k).cpu() for k in m.weight_keys()}
+    lat, ctx, pos = video_inputs(1, 9, 16, 24, 1024, 3840, 410)
+    ts = torch.tensor([0.909375])
+    ref = O.dit_forward(w, dict(latent=lat, context=ctx, timesteps=ts, positions=pos), num_layers=4, heads=32)
+    out = m(Modality(latent=lat, context=ctx, context_mask=None, timesteps=ts, positions=pos))
+    r, p = rel(out, ref), pearson(out, ref)
+    print(f"fp8 4 blocks @ D=4096, N=3456: rel L2 {r:.3e}, pearson {p:.5f}")
+    assert r < 6e-2 and p > 0.995, (r, p)
