@@ -783,10 +783,11 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
     }
     if fp8:
         g8 = pf[2] / (pm[2] * 1e-3) / 1e12 if pm[2] > 0 else 0.0
-        out["dtype"] = "fp8-e4m3 x fp8-e4m3 (self-attn QKV, text-attn Q, FFN up; per-token activation scales) + bf16 (rest)"
-        out["config"]["gemm_operands"] = ("E4M3 weights (one scale per output row) x E4M3 activations (dynamic scale per "
-                                          "token) on tcgen05.mma kind::f8f6f4 for the norm-fed linears; bf16 elsewhere; "
-                                          "fp32 accumulate")
+        out["dtype"] = "fp8-e4m3 x fp8-e4m3 (self-attn QKV, text-attn Q, FFN up + down) + bf16 (attention, out-projections, rest)"
+        out["config"]["gemm_operands"] = ("E4M3 weights (one scale per output row) x E4M3 activations (dynamic absmax scale "
+                                          "per token from the norm kernel; FFN hidden against a per-token Cauchy-Schwarz "
+                                          "bound) on tcgen05.mma kind::f8f6f4 for QKV / text-Q / FFN up / FFN down; bf16 "
+                                          "for the attention out-projections, text K/V, head; fp32 accumulate")
         out["parity"]["tolerance"] = {"rel_l2": 6e-2, "pearson": 0.995}
         out["parity"]["ok"] = bool(out["parity"]["rel_l2"] < 6e-2 and out["parity"]["pearson"] > 0.995)
         out["parity"]["what"] += ("; the oracle runs on the DEQUANTISED E4M3 weights read back from the engine, so the "

@@ -91,6 +91,7 @@ struct StreamW {               // per-modality weights outside the blocks
 struct BlockStreamW {          // per-block, per-modality
   AttnW attn1, attn2;
   LinearW ff1, ff2;
+  float* ff_coef = nullptr;      // FP8 mode: two device floats, scale bound of the E4M3 FFN hidden (e4m3_bound_coef)
   float* table = nullptr;        // [n_ada, dim]
   float* prompt_table = nullptr; // [2, dim]
 };
@@ -109,6 +110,8 @@ struct StreamBuf {
   bf16* xn = nullptr;           // [M, dim]
   uint8_t* xq = nullptr;        // [M, dim] E4M3 row-quantised GEMM input (FP8 mode)
   float* xs = nullptr;          // [M] its per-row scales
+  float* xl2 = nullptr;         // [M] L2 norm of those rows (bound of the E4M3 FFN hidden)
+  uint8_t* hq = nullptr;        // [M, 4*dim] E4M3 FFN hidden (written by the up-projection's epilogue)
   bf16* qkv = nullptr;          // [M, 3*dim]
   bf16* attn = nullptr;         // [M, dim]
   bf16* hidden = nullptr;       // [M, 4*dim]
@@ -239,6 +242,7 @@ struct LtxDit {
   size_t kvc_bytes = 0;
   bool ctx_cache_on = false, ctx_cache_hit = false;   // state of the forward in flight
   int layer_limit = 0;              // diagnostics: run only the first n blocks (0 = all)
+  bool coef_dirty = true;           // FP8 mode: a weight changed -> recompute the FFN bound coefficients
   bf16* kvc_kv(int layer, int B, int S) const {
     return reinterpret_cast<bf16*>(kvc) + size_t(layer) * 3 * size_t(B) * S * D;
   }
@@ -393,7 +397,8 @@ void build_layout(LtxDit* e, Arena* ar, bool dry) {
     b.v.attn2 = L.attention(P + "attn2", D, c.cross_attention_dim, c.num_attention_heads, c.attention_head_dim,
                             false, gated, q8);
     b.v.ff1 = L.linear(P + "ff.project_in.proj", 4 * D, D, q8);
-    b.v.ff2 = L.linear(P + "ff.project_out", D, 4 * D);
+    b.v.ff2 = L.linear(P + "ff.project_out", D, 4 * D, q8);
+    if (q8) b.v.ff_coef = reinterpret_cast<float*>(ar->take(16));
     b.v.table = L.f32_at(P + "scale_shift_table", offset_ptr(e->table_arena_v, size_t(i) * n * D), n, D);
     if (v2)
       b.v.prompt_table = L.f32_at(P + "prompt_scale_shift_table", offset_ptr(e->ptable_arena_v, size_t(i) * 2 * D), 2, D);
@@ -401,7 +406,8 @@ void build_layout(LtxDit* e, Arena* ar, bool dry) {
       b.a.attn1 = L.attention(P + "audio_attn1", Da, Da, c.audio_heads, c.audio_head_dim, true, gated, q8);
       b.a.attn2 = L.attention(P + "audio_attn2", Da, Da, c.audio_heads, c.audio_head_dim, false, gated, q8);
       b.a.ff1 = L.linear(P + "audio_ff.project_in.proj", 4 * Da, Da, q8);
-      b.a.ff2 = L.linear(P + "audio_ff.project_out", Da, 4 * Da);
+      b.a.ff2 = L.linear(P + "audio_ff.project_out", Da, 4 * Da, q8);
+      if (q8) b.a.ff_coef = reinterpret_cast<float*>(ar->take(16));
       b.a.table = L.f32_at(P + "audio_scale_shift_table", offset_ptr(e->table_arena_a, size_t(i) * n * Da), n, Da);
       if (v2)
         b.a.prompt_table = L.f32_at(P + "audio_prompt_scale_shift_table",
@@ -458,6 +464,8 @@ size_t layout_stream_buf(StreamBuf& sb, Arena& ar, const LtxDitConfig& c, int di
   sb.xn = (bf16*)T(M * dim * 2);
   sb.xq = c.fp8_linear ? (uint8_t*)T(M * dim) : nullptr;
   sb.xs = c.fp8_linear ? (float*)T(M * 4) : nullptr;
+  sb.xl2 = c.fp8_linear ? (float*)T(M * 4) : nullptr;
+  sb.hq = c.fp8_linear ? (uint8_t*)T(M * 4 * dim) : nullptr;
   sb.qkv = (bf16*)T(M * 3 * dim * 2);
   sb.attn = (bf16*)T(M * dim * 2);
   sb.hidden = (bf16*)T(M * 4 * dim * 2);
@@ -793,6 +801,7 @@ static int set_weight_impl(LtxDit* e, const char* key, const void* data, int32_t
   }
   if (r == LTX2_OK) s.loaded = true;
   e->cached_tag = 0;          // cached context K/V were projected with the old weights (LoRA fuse / restore)
+  e->coef_dirty = true;
   return r;
 }
 
@@ -1032,10 +1041,10 @@ int prepare_cross_mod(LtxDit* e, StreamBuf& sb, const AdaLNW& ss, const AdaLNW& 
 // RMSNorm + modulation of the residual stream as the E4M3 input of an FP8 linear: sb.xq / sb.xs (and the bf16 copy in
 // `out16` when a bf16 consumer of the same rows exists, e.g. the gate-logit projection)
 int rms_mod_q8(const LtxDit* e, const StreamBuf& sb, bf16* out16, const float* mod, int64_t mod_stride, int shift_row,
-               int scale_row, const int* cls, cudaStream_t st) {
+               int scale_row, const int* cls, cudaStream_t st, float* row_l2 = nullptr) {
   const int M = sb.B * sb.N;
   return norm_modulate_q8(sb.x, 0, sb.dim, sb.xq, sb.dim, sb.xs, out16, sb.dim, M, sb.dim, NORM_RMS, e->cfg.norm_eps, mod,
-                          mod_stride, int64_t(shift_row) * sb.dim, int64_t(scale_row) * sb.dim, cls, st);
+                          mod_stride, int64_t(shift_row) * sb.dim, int64_t(scale_row) * sb.dim, cls, st, row_l2);
 }
 
 int rms_mod(const LtxDit* e, const StreamBuf& sb, bf16* out, const float* mod, int64_t mod_stride, int shift_row,
@@ -1189,8 +1198,38 @@ int run_ffn(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer, cudaStre
   const float* mod = sb.mod + size_t(layer) * sb.n_cls * n * dim;
   const int64_t ms = int64_t(n) * dim;
   if (w.ff1.w8 != nullptr) {
-    LTX2_PROPAGATE(rms_mod_q8(e, sb, nullptr, mod, ms, 3, 4, sb.row_cls, st));
-    LTX2_PROPAGATE(linear_q8(sb.xq, sb.xs, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
+    // FP8 FFN: norm -> E4M3 rows (+ their L2 norms) -> up-projection whose epilogue writes gelu(.) as E4M3 against the
+    // Cauchy-Schwarz bound |row|_2 max|w_j|_2 + max|b| (no second pass over the 4D-wide hidden) -> FP8 down-projection
+    // with the gated residual epilogue
+    LTX2_PROPAGATE(rms_mod_q8(e, sb, nullptr, mod, ms, 3, 4, sb.row_cls, st, sb.xl2));
+    {
+      GemmEpilogue ep;
+      ep.mode = GEMM_EPI_E4M3_GELU;
+      ep.bias = w.ff1.b;
+      ep.out = sb.hq;
+      ep.ldo = 4 * dim;
+      ep.row_scale = sb.xs;
+      ep.col_scale = w.ff1.cscale;
+      ep.out_l2 = sb.xl2;
+      ep.out_coef = w.ff_coef;
+      ProfScope ps(PROF_GEMM8, 2.0 * M * double(4 * dim) * dim, st);
+      LTX2_PROPAGATE(gemm_e4m3(sb.xq, dim, w.ff1.w8, dim, M, 4 * dim, dim, ep, st));
+    }
+    GemmEpilogue ep;
+    ep.mode = GEMM_EPI_F32_RESIDUAL;
+    ep.bias = w.ff2.b;
+    ep.out = sb.x;
+    ep.ldo = dim;
+    ep.gate = mod + 5 * dim;
+    ep.gate_stride = ms;
+    ep.row_cls = sb.row_cls;
+    ep.alpha = 1.0f;
+    ep.max_splits = g_split_k;
+    ep.row_scale = sb.xl2;
+    ep.row_coef = w.ff_coef;
+    ep.col_scale = w.ff2.cscale;
+    ProfScope ps(PROF_GEMM8, 2.0 * M * double(dim) * 4 * dim, st);
+    return gemm_e4m3(sb.hq, 4 * dim, w.ff2.w8, 4 * dim, M, dim, 4 * dim, ep, st);
   } else {
     LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 3, 4, sb.row_cls, st));
     LTX2_PROPAGATE(linear_bf16(sb.xn, dim, w.ff1, M, sb.hidden, 4 * dim, true, st));
@@ -1257,6 +1296,14 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     LTX2_REQUIRE(video->tokens == e->cp.n_local && video->batch == e->cp.B,
                  "context parallel: expected the local slice of %d tokens (batch %d), got %d (batch %d)",
                  e->cp.n_local, e->cp.B, video->tokens, video->batch);
+  }
+  if (c.fp8_linear && e->coef_dirty) {
+    for (auto& bw : e->blocks) {
+      LTX2_PROPAGATE(e4m3_bound_coef(bw.v.ff1.w8, bw.v.ff1.cscale, bw.v.ff1.b, bw.v.ff1.out, bw.v.ff1.in, bw.v.ff_coef, st));
+      if (c.audio_enabled)
+        LTX2_PROPAGATE(e4m3_bound_coef(bw.a.ff1.w8, bw.a.ff1.cscale, bw.a.ff1.b, bw.a.ff1.out, bw.a.ff1.in, bw.a.ff_coef, st));
+    }
+    e->coef_dirty = false;
   }
   LtxDitSkip sk = {0, 0, 0, 0};
   if (skip) sk = *skip;

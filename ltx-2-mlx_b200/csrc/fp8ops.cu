@@ -16,6 +16,8 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
+#include <algorithm>
+
 namespace ltx2 {
 namespace {
 
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kQThreads)
 norm_modulate_q8_kernel(const void* __restrict__ x_, int64_t ldx, uint8_t* __restrict__ out8, int64_t ldo8,
                         float* __restrict__ row_scale, __nv_bfloat16* __restrict__ out16, int64_t ldo16, int D,
                         int norm_kind, float eps, const float* __restrict__ mod, int64_t mod_stride, int64_t shift_off,
-                        int64_t scale_off, const int* __restrict__ row_cls) {
+                        int64_t scale_off, const int* __restrict__ row_cls, float* __restrict__ row_l2) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;
@@ -135,7 +137,7 @@ norm_modulate_q8_kernel(const void* __restrict__ x_, int64_t ldx, uint8_t* __res
   }
   const float* mrow = nullptr;
   if (mod != nullptr) mrow = mod + static_cast<int64_t>(row_cls ? row_cls[row] : 0) * mod_stride;
-  float amax = 0.f;
+  float amax = 0.f, l2 = 0.f;
 #pragma unroll
   for (int u = 0; u < kQMaxUnits; ++u) {
     const int idx = threadIdx.x + u * kQThreads;
@@ -151,7 +153,7 @@ norm_modulate_q8_kernel(const void* __restrict__ x_, int64_t ldx, uint8_t* __res
         for (int i = 0; i < 8; ++i) v[u][i] = (v[u][i] - mean) * rstd;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[u][i]));
+      for (int i = 0; i < 8; ++i) { amax = fmaxf(amax, fabsf(v[u][i])); l2 = fmaf(v[u][i], v[u][i], l2); }
       if (out16 != nullptr) {
         uint4 q;
         q.x = pack_bf16x2(v[u][0], v[u][1]);
@@ -163,6 +165,10 @@ norm_modulate_q8_kernel(const void* __restrict__ x_, int64_t ldx, uint8_t* __res
     }
   }
   amax = block_max_q<kQThreads>(amax);
+  if (row_l2 != nullptr) {                      // warp-uniform
+    const float2 t = block_sum2_q<kQThreads>(l2, 0.f);
+    if (threadIdx.x == 0) row_l2[row] = sqrtf(t.x);
+  }
   const float scale = amax > 0.f ? amax * (1.0f / kE4M3Max) : 1.0f;
   const float inv = 1.0f / scale;
   if (threadIdx.x == 0) row_scale[row] = scale;
@@ -206,6 +212,27 @@ __global__ void dequant_e4m3_kernel(const uint8_t* __restrict__ src, const float
   }
 }
 
+// bound coefficients of an E4M3 weight: max over rows of |w_row|_2 (dequantised) and max |bias|
+__global__ void __launch_bounds__(kQThreads)
+e4m3_row_norm_max_kernel(const uint8_t* __restrict__ w8, const float* __restrict__ row_scale,
+                         const float* __restrict__ bias, int64_t K, unsigned int* __restrict__ acc /* [2] float bits */) {
+  const int64_t row = blockIdx.x;
+  float ss = 0.f;
+  for (int64_t k = threadIdx.x; k < K; k += kQThreads) {
+    const float f = e4m3_to_float(w8[row * K + k]);
+    ss = fmaf(f, f, ss);
+  }
+  const float2 t = block_sum2_q<kQThreads>(ss, 0.f);
+  if (threadIdx.x == 0) {
+    atomicMax(acc, __float_as_uint(sqrtf(t.x) * row_scale[row]));          // non-negative floats order like their bits
+    atomicMax(acc + 1, __float_as_uint(bias != nullptr ? fabsf(bias[row]) : 0.f));
+  }
+}
+__global__ void e4m3_bound_finish_kernel(const unsigned int* acc, float* coef) {
+  coef[0] = 1.07f * __uint_as_float(acc[0]) * (1.0f / kE4M3Max);
+  coef[1] = fmaxf(__uint_as_float(acc[1]) * (1.0f / kE4M3Max), 1e-30f);
+}
+
 __global__ void fill_f32_kernel(float* dst, float v, int64_t n) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -215,7 +242,8 @@ __global__ void fill_f32_kernel(float* dst, float v, int64_t n) {
 
 int norm_modulate_q8(const void* x, int x_is_bf16, int64_t ldx, void* out8, int64_t ldo8, float* row_scale,
                      void* out_bf16, int64_t ldo16, int M, int D, int norm_kind, float eps, const float* mod,
-                     int64_t mod_stride, int64_t shift_off, int64_t scale_off, const int* row_cls, cudaStream_t stream) {
+                     int64_t mod_stride, int64_t shift_off, int64_t scale_off, const int* row_cls, cudaStream_t stream,
+                     float* row_l2) {
   if (M == 0) return LTX2_OK;
   LTX2_REQUIRE(D % 8 == 0 && D <= kQThreads * 8 * kQMaxUnits, "norm_modulate_q8: D=%d unsupported", D);
   LTX2_REQUIRE(ldx % 8 == 0 && ldo8 % 16 == 0 && ldo16 % 8 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0 &&
@@ -226,12 +254,12 @@ int norm_modulate_q8(const void* x, int x_is_bf16, int64_t ldx, void* out8, int6
     LTX2_CUDA_CHECK(launch_pdl(norm_modulate_q8_kernel<true>, dim3(M), dim3(kQThreads), 0, stream, x, ldx,
                                reinterpret_cast<uint8_t*>(out8), ldo8, row_scale,
                                reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo16, D, norm_kind, eps, mod, mod_stride,
-                               shift_off, scale_off, row_cls));
+                               shift_off, scale_off, row_cls, row_l2));
   else
     LTX2_CUDA_CHECK(launch_pdl(norm_modulate_q8_kernel<false>, dim3(M), dim3(kQThreads), 0, stream, x, ldx,
                                reinterpret_cast<uint8_t*>(out8), ldo8, row_scale,
                                reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo16, D, norm_kind, eps, mod, mod_stride,
-                               shift_off, scale_off, row_cls));
+                               shift_off, scale_off, row_cls, row_l2));
   count_launch();
   return LTX2_OK;
 }
@@ -277,6 +305,18 @@ int dequant_e4m3(const void* src8, const float* scale, int scale_stride, int64_t
   }
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  return LTX2_OK;
+}
+
+int e4m3_bound_coef(const void* w8, const float* row_scale, const float* bias, int64_t rows, int64_t K, float* coef,
+                    cudaStream_t stream) {
+  // coef doubles as the two-word accumulator of the reduction (bit patterns of non-negative floats)
+  LTX2_CUDA_CHECK(cudaMemsetAsync(coef, 0, 8, stream));
+  e4m3_row_norm_max_kernel<<<static_cast<unsigned>(rows), kQThreads, 0, stream>>>(
+      reinterpret_cast<const uint8_t*>(w8), row_scale, bias, K, reinterpret_cast<unsigned int*>(coef));
+  e4m3_bound_finish_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<const unsigned int*>(coef), coef);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
   return LTX2_OK;
 }
 

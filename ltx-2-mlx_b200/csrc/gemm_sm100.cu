@@ -14,6 +14,8 @@
 
 #include <algorithm>
 
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,7 +55,8 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& ep, uint32_t t_
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       if (ep.row_scale != nullptr) {            // FP8 operands: de-scale the accumulator (fp8ops.cu)
-        const float rsc = __ldg(ep.row_scale + row);
+        float rsc = __ldg(ep.row_scale + row);
+        if (ep.row_coef != nullptr) rsc = fmaf(rsc, __ldg(ep.row_coef), __ldg(ep.row_coef + 1));
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.col_scale + col0 + j));
@@ -67,7 +70,22 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& ep, uint32_t t_
           v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
         }
       }
-      if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
+      if (ep.mode == GEMM_EPI_E4M3_GELU) {
+        // FFN up-projection whose consumer is an FP8 GEMM: the activation is written as E4M3 against the row's bound
+        const float inv = 1.0f / fmaf(__ldg(ep.out_l2 + row), __ldg(ep.out_coef), __ldg(ep.out_coef + 1));
+        uint32_t q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t lo = __nv_cvt_float2_to_fp8x2(
+              make_float2(gelu_tanh_f(v[4 * j]) * inv, gelu_tanh_f(v[4 * j + 1]) * inv), __NV_SATFINITE, __NV_E4M3);
+          const uint32_t hi = __nv_cvt_float2_to_fp8x2(
+              make_float2(gelu_tanh_f(v[4 * j + 2]) * inv, gelu_tanh_f(v[4 * j + 3]) * inv), __NV_SATFINITE, __NV_E4M3);
+          q[j] = lo | (hi << 16);
+        }
+        uint8_t* o = reinterpret_cast<uint8_t*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+        *reinterpret_cast<uint4*>(o) = make_uint4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<uint4*>(o + 16) = make_uint4(q[4], q[5], q[6], q[7]);
+      } else if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
         if (ep.mode == GEMM_EPI_BF16_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);

@@ -16,6 +16,7 @@ enum GemmEpilogueMode {
   GEMM_EPI_BF16_GELU = 1,     // out_bf16 = gelu_tanh(acc + bias)
   GEMM_EPI_F32 = 2,           // out_f32  = acc + bias
   GEMM_EPI_F32_RESIDUAL = 3,  // out_f32 += alpha * gate[row_cls[row], col] * (acc + bias)
+  GEMM_EPI_E4M3_GELU = 4,     // out_e4m3 = gelu_tanh(acc + bias) / (out_l2[row] * out_coef[0] + out_coef[1])
 };
 
 struct GemmEpilogue {
@@ -34,6 +35,12 @@ struct GemmEpilogue {
   // E4M3 activation row and the (per-tensor or per-output-channel) scale of the E4M3 weight
   const float* row_scale = nullptr;
   const float* col_scale = nullptr;
+  // row_coef != null: the row factor is row_scale[row] * row_coef[0] + row_coef[1] (two DEVICE floats) -- the scale of
+  // an E4M3 activation that was written by a GEMM epilogue (mode 4) against a bound instead of a measured absmax:
+  // |gelu(a.w + b)| <= |a|_2 max_j|w_j|_2 + max|b|  (Cauchy-Schwarz), with |a|_2 per row from the norm kernel
+  const float* row_coef = nullptr;
+  const float* out_l2 = nullptr;     // mode 4: [M] L2 norm of the GEMM's own input rows
+  const float* out_coef = nullptr;   // mode 4: two device floats
 };
 
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const GemmEpilogue& ep,
@@ -187,7 +194,12 @@ int denoise_update(const float* sample, const float* cond, const float* uncond, 
 // receives the unquantised bf16 row (consumers that stay bf16, e.g. the gate-logit projection)
 int norm_modulate_q8(const void* x, int x_is_bf16, int64_t ldx, void* out8, int64_t ldo8, float* row_scale,
                      void* out_bf16, int64_t ldo16, int M, int D, int norm_kind, float eps, const float* mod,
-                     int64_t mod_stride, int64_t shift_off, int64_t scale_off, const int* row_cls, cudaStream_t stream);
+                     int64_t mod_stride, int64_t shift_off, int64_t scale_off, const int* row_cls, cudaStream_t stream,
+                     float* row_l2 = nullptr /* optional [M]: L2 norm of the output row before quantisation */);
+// coef[0] = 1.07 * max_row |w_row|_2 / 448, coef[1] = max|bias| / 448 for an E4M3 weight [rows,K] with row scales:
+// the per-row scale factors of the E4M3 output of the GEMM that uses this weight (GEMM_EPI_E4M3_GELU)
+int e4m3_bound_coef(const void* w8, const float* row_scale, const float* bias, int64_t rows, int64_t K, float* coef,
+                    cudaStream_t stream);
 // weight [rows,K] (dtype code) -> E4M3 bytes with one scale per row
 int quantize_rows_e4m3(const void* w, int dtype, int64_t rows, int64_t K, void* out8, float* row_scale,
                        cudaStream_t stream);
