@@ -614,12 +614,13 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
     cp_parity = None
     alat = b.alat_d if c["av"] else None
     if cp:
-        # Two comparisons.  (1) EXACT: with the kernel choice pinned (standard GEMM tiles, all-pairs attention items,
-        # no split-K) every output element is computed by the same instruction sequence on one GPU and on P GPUs, so the
+        # Two comparisons.  (1) EXACT: with the kernel choice pinned (standard GEMM tiles, every attention query tile as
+        # a split-KV item -- a pair item and a split-KV item round differently and which tiles pair up depends on the
+        # local token count --, no split-K) every output element is computed by the same instruction sequence on one GPU and on P GPUs, so the
         # sharded forward must be BIT-IDENTICAL -- this checks the sharding, the head exchange and the context broadcast.
         # (2) DEFAULT: shard-shaped GEMM kernels, makespan-optimal attention items and split-K change fp32 summation
         # orders; the bound is rel_l2 2e-3, a tenth of the engine-vs-oracle tolerance.
-        canon = {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "-1"}
+        canon = {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "0"}
         v, a = b.modalities(5, b.lat_d, alat)
 
         def fwd(env=None):
@@ -654,7 +655,7 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
                      "max_abs": float(t[2]), "rel_l2": float(t[3]),
                      "what": f"x0 of the full {c['layers']}-block model: context-parallel forward over {world} ranks vs "
                              f"the un-sharded forward of the same model, max over ranks.  pinned kernels (standard GEMM "
-                             f"tiles, all-pairs attention items, split-K off): must be bit-exact; default kernel choice "
+                             f"tiles, split-KV attention items only, split-K off): must be bit-exact; default kernel choice "
                              f"(shard-shaped GEMMs, split-K): rel_l2 <= 2e-3",
                      "ok": bool(float(t[0]) == 0.0 and float(t[3]) <= 2e-3)}
 

@@ -258,6 +258,51 @@ int ltx2_tile_accumulate(float* out, float* wsum, const float* tile, int32_t BC,
 int ltx2_tile_normalize(float* out, const float* wsum, int32_t BC, int64_t plane, void* stream);
 
 /* =====================================================================================
+ * Video-VAE ENCODER and 2x latent SPATIAL UPSCALER building blocks.  Both are 3x3x3 conv stacks:
+ * the convs run on the same tcgen05 implicit-GEMM kernel as the decoder (ltx2_conv3d_packed); the ops below are what
+ * differs.  The host mirrors (ltx-2-mlx_b200/video_vae_encoder.py: SimpleVideoEncoder, upscaler.py: SpatialUpscaler)
+ * sequence them like model/video_vae/simple_encoder.py:306-405 and model/upscaler/spatial.py:376-412.
+ * Activations: channels-last bf16 [B,T,H,W,C].
+ * ===================================================================================== */
+
+/* x -> padded [B, TL+2, H+2, W+2, C] (TL = T, or T+1 with dup_first: the first frame duplicated in front,
+ * simple_encoder.py:237-240), with an optional activation applied on the way:
+ *   hw_mode 0 reflect (decoder) / 1 zero (encoder :62-74, upscaler :57-66);
+ *   t_mode  0 replicate 1+1 / 1 causal: first frame twice in front (simple_encoder.py:76-84) / 2 zero 1+1 (upscaler);
+ *   act     0 none / 1 pixel-norm + SiLU (simple_encoder.py:12-15,145-151) / 2 GroupNorm affine / 3 GroupNorm + SiLU
+ *           (spatial.py:160-181: `residual` is added after the norm, before the SiLU);
+ *   gn_stats [B,groups,2] = (mean, rstd) from ltx2_group_stats.  out_plain (optional) receives the un-padded result. */
+int ltx2_pad_act(const void* x, void* out_padded, void* out_plain, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C,
+                 int32_t hw_mode, int32_t t_mode, int32_t dup_first, int32_t act, const float* gn_stats,
+                 const float* gn_weight, const float* gn_bias, int32_t groups, float eps, const void* residual,
+                 void* stream);
+/* group_norm_5d statistics (spatial.py:91-128): over (C/groups, T, H, W) per (batch, group) */
+int ltx2_group_stats(const void* x, int32_t B, int64_t thw, int32_t C, int32_t groups, float eps, float* stats,
+                     void* stream);
+/* conv weight [Cout,Cin,3,3,3] + bias -> the kernel's packed form (bf16 [Cout_pad, 27*Cin], fp32 [Cout_pad]) */
+int ltx2_conv3d_pack(const void* weight, int32_t w_dtype, const void* bias, int32_t b_dtype, int32_t Cout,
+                     int32_t Cout_pad, int32_t Cin, void* w_packed, float* b_packed, void* stream);
+/* 3x3x3 conv on a padded input [B,T+2,H+2,W+2,Cin] -> out [B,T,H,W,Cout] (+ residual [B,T,H,W,Cout] if given) */
+int ltx2_conv3d_packed(const void* x_padded, const void* w_packed, const float* b_packed, void* out, const void* residual,
+                       int32_t B, int32_t T, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t Cout_pad,
+                       void* stream);
+/* patchify (ops.py:44-68): video fp32 [B,3,F,H,W] -> bf16 [B,F,H/4,W/4,Cp], channel (c*4 + r_w)*4 + r_h, zeros >= 48 */
+int ltx2_patchify_video(const float* video, void* out, int32_t B, int32_t F, int32_t H, int32_t W, int32_t Cp,
+                        void* stream);
+/* SpaceToDepthDownsample3d tail (simple_encoder.py:207-257): space_to_depth(conv output y) + group-mean of
+ * space_to_depth(x); y [B,TL,H,W,Cout/sp], x [B,T,H,W,Cx], out [B,TL/st,H/sh,W/sw,Cout] */
+int ltx2_space_to_depth_residual(const void* y, const void* x, void* out, int32_t B, int32_t T, int32_t H, int32_t W,
+                                 int32_t Cx, int32_t Cout, int32_t st, int32_t sh, int32_t sw, int32_t dup_first,
+                                 void* stream);
+/* PixelShuffle2d (spatial.py:184-218): y [BF,H,W,4C] -> out [BF,2H,2W,C], source channel c*4 + r_h*2 + r_w */
+int ltx2_pixel_shuffle2(const void* y, void* out, int64_t BF, int32_t H, int32_t W, int32_t C, void* stream);
+/* layout changes at the network boundaries: channels-last bf16 [B,thw,Cs] -> fp32 NCDHW (first C channels, optional
+ * (x - mean) / std: PerChannelStatistics.normalize, ops.py:173-186) and NCDHW (dtype code) -> channels-last bf16 */
+int ltx2_ndhwc_to_ncdhw(const void* x, float* out, int32_t B, int32_t C, int32_t Cs, int64_t thw, const float* mean,
+                        const float* stdv, void* stream);
+int ltx2_ncdhw_to_ndhwc(const void* x, int32_t dtype, void* out, int32_t B, int32_t C, int64_t thw, void* stream);
+
+/* =====================================================================================
  * Per-op entry points (unit parity against the oracle)
  * ===================================================================================== */
 

@@ -92,6 +92,15 @@ SIGNATURES = {
     "ltx2_vae_decode": (_I32, [_P, _P, _I32, _P, _F, _F, _P, _I32, _P, _P]),
     "ltx2_conv3d_workspace_bytes": (_I64, [_I32] * 6),
     "ltx2_conv3d": (_I32, [_P, _P, _I32, _P, _I32, _P] + [_I32] * 7 + [_P, _P]),
+    "ltx2_pad_act": (_I32, [_P, _P, _P] + [_I32] * 9 + [_P, _P, _P, _I32, _F, _P, _P]),
+    "ltx2_group_stats": (_I32, [_P, _I32, _I64, _I32, _I32, _F, _P, _P]),
+    "ltx2_conv3d_pack": (_I32, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "ltx2_conv3d_packed": (_I32, [_P, _P, _P, _P, _P] + [_I32] * 7 + [_P]),
+    "ltx2_patchify_video": (_I32, [_P, _P] + [_I32] * 5 + [_P]),
+    "ltx2_space_to_depth_residual": (_I32, [_P, _P, _P] + [_I32] * 10 + [_P]),
+    "ltx2_pixel_shuffle2": (_I32, [_P, _P, _I64, _I32, _I32, _I32, _P]),
+    "ltx2_ndhwc_to_ncdhw": (_I32, [_P, _P, _I32, _I32, _I32, _I64, _P, _P, _P]),
+    "ltx2_ncdhw_to_ndhwc": (_I32, [_P, _I32, _P, _I32, _I32, _I64, _P]),
     "ltx2_vae_set_profile": (_I32, [_P, _I32]),
     "ltx2_vae_profile_read": (_I32, [_P, _P, _P, _P]),
     "ltx2_vae_profile_launch": (_I32, [_P, _I32, _P, _P]),
