@@ -309,6 +309,22 @@ def iter_upscaler_weights(seed: int = 0, device="cpu", dtype=torch.float32, in_c
     yield from conv("final_conv", in_channels, mid_channels)
 
 
+def iter_connector_weights(heads: int = 30, head_dim: int = 128, layers: int = 2, registers: int = 128, gated: bool = True,
+                           seed: int = 0, device="cpu", dtype=torch.float32) -> Iterator[Tuple[str, torch.Tensor]]:
+    """Yield (module_key, tensor) for the text-embeddings connector (model/text_encoder/connector.py:104-176) under the
+    reference's module attribute names, i.e. the checkpoint keys `model.diffusion_model.video_embeddings_connector.*`
+    after loader/weight_converter.py:146-162,300-313."""
+    D = heads * head_dim
+    for i in range(layers):
+        P = f"transformer_1d_blocks.{i}"
+        for k, t in _attention(P + ".attn1", D, D, D, heads, gated, seed, device, dtype):
+            yield k.replace(".to_out.0.", ".to_out."), t
+        yield from _linear(P + ".ff.project_in.proj", 4 * D, D, seed, device, dtype)
+        yield from _linear(P + ".ff.project_out", D, 4 * D, seed, device, dtype)
+    if registers:
+        yield "learnable_registers", _uniform("learnable_registers", (registers, D), 1.0, seed, device, torch.float32)
+
+
 def dit_weights(cfg: DitConfig, seed: int = 0, device="cpu", dtype=torch.float32) -> Dict[str, torch.Tensor]:
     return dict(iter_dit_weights(cfg, seed, device, dtype))
 

@@ -257,7 +257,11 @@ def _key(s):
     return _wrap(np.array([0, int(s)], dtype=np.uint32))
 
 
-random = types.SimpleNamespace(seed=_seed, normal=_normal, key=_key)
+def _uniform(low=0.0, high=1.0, shape=(), dtype=float32, key=None):
+    return _wrap((_rng.uniform(low, high, size=shape)).astype(dtype))
+
+
+random = types.SimpleNamespace(seed=_seed, normal=_normal, key=_key, uniform=_uniform)
 
 
 # --- mx.fast ---------------------------------------------------------------------

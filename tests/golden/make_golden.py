@@ -330,6 +330,31 @@ def golden_upscaler():
     print("upscaler", out.shape)
 
 
+def golden_connector():
+    """Embeddings1DConnector (model/text_encoder/connector.py) -- the reference's own class, both RoPE layouts, gated
+    attention on, learnable registers (sequence extended to 1024).  The Metal interleaved-RoPE kernel cannot run here, so
+    the reference's own naive fallback (rope.py:76-89) is selected."""
+    _stub_package("LTX_2_MLX.model.text_encoder", f"{REF}/LTX_2_MLX/model/text_encoder")
+    ref_conn = importlib.import_module("LTX_2_MLX.model.text_encoder.connector")
+    ref_rope._HAS_FUSED_ROPE = False
+    heads, hd, layers, regs = 4, 64, 2, 128
+    w = dict(synthetic.iter_connector_weights(heads=heads, head_dim=hd, layers=layers, registers=regs, gated=True, seed=17))
+    x = rnd((2, 20, heads * hd), 700)
+    out = {}
+    for name, rt in (("interleaved", ref_rope.LTXRopeType.INTERLEAVED), ("split", ref_rope.LTXRopeType.SPLIT)):
+        conn = ref_conn.Embeddings1DConnector(attention_head_dim=hd, num_attention_heads=heads, num_layers=layers,
+                                              num_learnable_registers=regs, rope_type=rt, apply_gated_attention=True)
+        for k, v in w.items():
+            set_by_key(conn, k, v)
+        # SPLIT with B > 1 breaks inside the reference (apply_split_rotary_emb reshapes with the table's batch of 1)
+        y, mask = conn(mx.array(x if name == "interleaved" else x[:1]), None)
+        out[name] = A(y).astype(np.float32)
+        assert float(np.abs(A(mask)).max()) == 0.0
+    np.savez_compressed(os.path.join(HERE, "connector.npz"), x=x, weight_checksum=checksum(w),
+                        cfg=np.array([heads, hd, layers, regs]), **{"y_" + k: v for k, v in out.items()})
+    print("connector", {k: v.shape for k, v in out.items()})
+
+
 def _ref_function(path, name):
     """Compile ONE function of a reference file that cannot be imported as a module here (pipelines/common.py pulls
     in PIL, the encoder, ...): its source text is taken from the reference file at run time and executed as is."""
@@ -368,6 +393,9 @@ def golden_sampling():
 
 
 if __name__ == "__main__":
+    if "--connector-only" in sys.argv:
+        golden_connector()
+        sys.exit(0)
     if "--upscaler-only" in sys.argv:
         golden_upscaler()
         sys.exit(0)
@@ -384,3 +412,4 @@ if __name__ == "__main__":
     golden_dit_v1()
     golden_dit_v2_av()
     golden_vae()
+    golden_connector()
