@@ -302,7 +302,8 @@ def bench_vae(args, dev, rank, world=1):
     import torch
     import torch.distributed as dist
     from ltx2_b200 import _lib, synthetic
-    from ltx2_b200.video_vae import SimpleVideoDecoder, chunk_plan, decode_latent
+    from ltx2_b200.video_vae import (SimpleVideoDecoder, chunk_plan, decode_latent, decode_latent_video,
+                                     disable_temporal_shards, enable_temporal_shards)
     vcfg = synthetic.VaeConfig()
     dec = SimpleVideoDecoder(device=dev)
     w_cpu = {}
@@ -317,6 +318,23 @@ def bench_vae(args, dev, rank, world=1):
     dec.load_weights(tee())
     assert not dec.missing_weights()
     kw = dict(group=dist.group.WORLD, dst=0) if world > 1 else {}
+    shard_parity = None
+    if world > 1:
+        # bit-exactness of the sharded decode against this rank's own single-GPU decode of the same clip (noise off)
+        plat = synthetic.latents((1, 128, 7, 16, 24), seed=45).to(dev)
+        keep = dec.decode_noise_scale
+        dec.decode_noise_scale = 0.0
+        ref = decode_latent_video(plat, dec)
+        enable_temporal_shards(dec, (1, 128, 7, 16, 24), group=dist.group.WORLD)
+        got = decode_latent_video(plat, dec, group=dist.group.WORLD)
+        dec.decode_noise_scale = keep
+        t = torch.tensor([0.0 if torch.equal(got, ref) else 1.0, float((got - ref).abs().max())], device=dev,
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shard_parity = {"bit_exact": float(t[0]) == 0.0, "max_abs": float(t[1]),
+                        "what": f"49-frame chunk (latent 1x128x7x16x24) decoded in temporal shards over {world} ranks vs the "
+                                f"single-GPU decode of the same latent on every rank, noise off"}
+        del ref, got
 
     def sync():
         if world > 1:
@@ -409,17 +427,20 @@ def bench_vae(args, dev, rank, world=1):
                   "oracle_seconds": t_or,
                   "cpu_frames_per_s": 9.0 / t_or}
         parity["ok"] = bool(parity["rel_l2"] < 3e-2 and parity["pearson"] > 0.999)
+    if world > 1:
+        disable_temporal_shards(dec)
     return {
         "metric": "VAE decode frames/sec", "value": frames * 1000.0 / ms, "unit": "frames/s", "ms_per_decode": ms,
         "config": {"workload": "decode_latent, latent 1x128x9x16x24 -> 65 frames @ 512x768, V2.0 decoder stack "
                                "(base 128, 5 res blocks/group), reference chunking 7/2 -> chunks " + str(plan),
                    "parallelism": "single GPU" if world == 1 else
-                                  f"decode units spread over {world} ranks, collected on rank 0 (strong scaling)",
+                                  f"temporal shards: the frames of every chunk are split over {world} ranks (one halo frame "
+                                  f"per neighbour and conv through peer memory), collected on rank 0 (strong scaling)",
                    "noise": "decode_noise_scale 0.025 (reference default), timestep 0.05"},
         "gpu_launches": int(launches),
         "e2e": {"value": frames * 1000.0 / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(lat_h.numel() * 4),
                 "d2h_bytes_per_step": int(out_h.numel())},
-        "parity": parity, "sweep": sweep,
+        "parity": parity, "shard_parity": shard_parity, "sweep": sweep,
         "roofline": {"bound": "tensor", "kernel": "conv3d_kernel (tcgen05 implicit GEMM, all convs of one 7-frame chunk)",
                      "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
                      "traffic": profiled_traffic("prof_conv", "conv3d_kernel<128>"),

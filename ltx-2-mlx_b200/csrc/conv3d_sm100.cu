@@ -148,8 +148,8 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
       if (t == 0) { tps[nt_++] = 0; tps[nt_++] = 1; }
     } else {
       tps[nt_++] = t + 1;
-      if (t == 0) tps[nt_++] = 0;
-      if (t == p.T - 1) tps[nt_++] = p.T + 1;
+      if (t == 0 && !p.pad_skip_front) tps[nt_++] = 0;
+      if (t == p.T - 1 && !p.pad_skip_back) tps[nt_++] = p.T + 1;
     }
     hps[nh_++] = h + 1;
     if (h == 1) hps[nh_++] = 0;
@@ -250,7 +250,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
       const int Cf = p.Cout / sp;
       const int sub = col0 / Cf, c0 = col0 % Cf;
       const int a = sub / (p.fh * p.fw), bb2 = (sub / p.fw) % p.fh, d = sub % p.fw;
-      const int drop = (p.ft > 1) ? 1 : 0;
+      const int drop = (p.ft > 1 && !p.d2s_keep_first) ? 1 : 0;
       const int to = t * p.ft + a - drop;
       if (to < 0) continue;
       const int To = p.T * p.ft - drop, Ho = p.H * p.fh, Wo = p.W * p.fw;

@@ -248,6 +248,9 @@ struct ConvParams {
   int64_t pad_mod_stride = 0, pad_shift_off = 0, pad_scale_off = 0;
   float pad_eps = 1e-6f;
   int pad_causal = 0;
+  int pad_skip_front = 0, pad_skip_back = 0;   // temporal shards: that T pad slot belongs to the neighbour rank
+  int d2s_keep_first = 0;               // temporal shards: this rank's first input frame is not the clip's frame 0, so
+                                        // the depth-to-space keeps both of its output frames (no first-frame drop)
 };
 
 // x_padded: bf16 [B, T+2, H+2, W+2, Cin]; w_packed: bf16 [Cout_pad, 27*Cin] (tap-major, channel-minor)
@@ -263,13 +266,17 @@ int pack_conv_bias(const void* b, int dtype, float* packed, int Cout, int Cout_p
 // (x*std+mean, simple_decoder.py:492-493) and optional noise blend (:496-498): noise*s + (1-s)*x
 int latent_to_padded(const void* latent, int dtype, const float* std_, const float* mean, const float* noise,
                      float noise_scale, void* out, int B, int C, int T, int H, int W, int causal,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int t0 = 0, int Tn = -1 /* window [t0, t0+Tn) of the T frames; -1 = all */);
 
 // x [B,T,H,W,C] bf16 -> padded [B,T+2,H+2,W+2,C] bf16 applying (when act != 0)
 //   silu(pixel_norm(x) * (1 + scale[b]) + shift[b])   (simple_decoder.py:229-231, 339-342, 528-542)
 // mod: fp32 [B, mod_stride] with rows shift at shift_off and scale at scale_off; reflect pad H/W, replicate pad T.
 int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, int act, const float* mod,
-                 int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream);
+                 int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream,
+                 int skip_front = 0, int skip_back = 0 /* temporal shards: leave that pad slot to the neighbour rank */);
+// temporal shards: my first / last real frame -> the previous rank's back pad slot / the next rank's front pad slot
+int halo_push(const void* mine, void* prev, void* next, int B, int n, int n_prev, int n_next, int64_t frame_bytes,
+              cudaStream_t stream);
 
 // decode_latent post-processing (simple_decoder.py:749-798)
 //   blend: dst[:, :, t0+i] = dst*(1-r_i) + src[:, :, i]*r_i for i < overlap (r = linspace(0,1,overlap)), then copy tail

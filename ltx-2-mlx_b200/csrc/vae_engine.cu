@@ -13,7 +13,10 @@
 #include "../../include/ltx2_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include <string>
 #include <unordered_map>
@@ -78,7 +81,22 @@ struct VaeProfiler {                 // CUDA events around every conv launch (be
   size_t used = 0;
 };
 
+constexpr int kMaxVaeRanks = 8;
+// temporal shards: exchange region (two padded conv-input buffers + barrier flags) mapped into every rank by CUDA IPC
+struct VaeCp {
+  int rank = 0, world = 1;
+  char* region = nullptr;
+  size_t region_bytes = 0, pad_bytes = 0;
+  size_t off_xp[2] = {0, 0}, off_flags = 0;
+  char* peer_base[kMaxVaeRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool opened[kMaxVaeRanks] = {false, false, false, false, false, false, false, false};
+  uint32_t** peer_flags_dev = nullptr;
+  uint32_t epoch = 0;
+  bool connected = false;
+};
+
 struct LtxVae {
+  VaeCp cp;
   VaeProfiler prof;
   LtxVaeConfig cfg;
   std::unordered_map<std::string, VSlot> slots;
@@ -254,6 +272,12 @@ int ltx2_vae_create(const LtxVaeConfig* cfg, LtxVae** out) {
 
 void ltx2_vae_destroy(LtxVae* e) {
   if (!e) return;
+  if (e->cp.region) {
+    for (int r = 0; r < e->cp.world; ++r)
+      if (e->cp.opened[r]) cudaIpcCloseMemHandle(e->cp.peer_base[r]);
+    cudaFree(e->cp.region);
+    if (e->cp.peer_flags_dev) cudaFree(e->cp.peer_flags_dev);
+  }
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   for (auto ev : e->prof.events) cudaEventDestroy(ev);
@@ -333,8 +357,25 @@ int ltx2_vae_output_shape(LtxVae* e, const int64_t in_shape[5], int64_t out_shap
   return LTX2_OK;
 }
 
-int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
-                    float noise_scale, const float* noise, int32_t causal, float* out, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// contiguous, as-even-as-possible split of T frames over the first min(world, T) ranks; other ranks get an empty range
+void split_frames(int T, int world, int r, int* a, int* b) {
+  const int active = std::min(world, T);
+  if (r >= active) { *a = *b = T; return; }
+  const int base = T / active, rem = T % active;
+  *a = r * base + std::min(r, rem);
+  *b = *a + base + (r < rem ? 1 : 0);
+}
+
+// One decoder forward.  sharded == false: the whole clip on this GPU (ltx2_vae_decode).  sharded == true: this rank
+// computes the frames [a, b) of every activation (temporal shards, ltx2_vae_decode_sharded); `out` then receives only the
+// rank's own output frames and *out_t0 / *out_tn their position in the clip.
+int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
+                    float noise_scale, const float* noise, int32_t causal, float* out, void* stream, bool sharded,
+                    int64_t* out_t0, int64_t* out_tn) {
   LTX2_REQUIRE(e && latent && shape && out, "vae_decode: null argument");
   const int B = (int)shape[0], Cl = (int)shape[1];
   LTX2_REQUIRE(Cl == e->cfg.latent_channels, "vae_decode: latent has %d channels, decoder expects %d", Cl,
@@ -352,19 +393,34 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
       }
     }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VaeCp& cp = e->cp;
+  const int world = sharded ? cp.world : 1, rank = sharded ? cp.rank : 0;
+  if (sharded) {
+    LTX2_REQUIRE(cp.connected && cp.world > 1, "vae_decode_sharded: ltx2_vae_cp_connect has not been called");
+    LTX2_REQUIRE(!causal, "vae_decode_sharded: causal decoding is not sharded (its halo is two frames on one side)");
+  }
+  // frame ranges [ra[r], rb[r]) of every rank at the current stage; Tt = frames of the whole clip at that stage
+  int ra[kMaxVaeRanks], rb[kMaxVaeRanks];
+  int Tt = (int)shape[2];
+  for (int r = 0; r < world; ++r) split_frames(Tt, world, r, &ra[r], &rb[r]);
+  auto n_of = [&](int r) { return (r >= 0 && r < world) ? rb[r] - ra[r] : 0; };
 
-  // ---- workspace sizing: walk the stages ----
-  Dims d{(int)shape[2], (int)shape[3], (int)shape[4], e->conv_in.Cout};
-  size_t max_act = size_t(B) * d.T * d.H * d.W * d.C;
+  // ---- workspace sizing: walk the stages (local frame counts when sharded) ----
+  Dims d{n_of(rank), (int)shape[3], (int)shape[4], e->conv_in.Cout};
+  size_t max_act = size_t(B) * std::max(d.T, 1) * d.H * d.W * d.C;
   size_t max_pad = size_t(B) * (d.T + 2) * (d.H + 2) * (d.W + 2) * std::max(d.C, Cl);
   size_t max_mod = 0;
-  for (auto& s : e->stages) {
-    if (s.kind == 0) {
-      max_mod = std::max(max_mod, size_t(s.num_layers) * B * 4 * s.C);
-    } else {
-      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
-      max_act = std::max(max_act, size_t(B) * d.T * d.H * d.W * d.C);
-      max_pad = std::max(max_pad, size_t(B) * (d.T + 2) * (d.H + 2) * (d.W + 2) * d.C);
+  {
+    int a = ra[rank], b = rb[rank];
+    for (auto& s : e->stages) {
+      if (s.kind == 0) {
+        max_mod = std::max(max_mod, size_t(s.num_layers) * B * 4 * s.C);
+      } else {
+        if (s.ft > 1 && b > a) { a = std::max(0, 2 * a - 1); b = 2 * b - 1; }
+        d.T = b - a; d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
+        max_act = std::max(max_act, size_t(B) * std::max(d.T, 1) * d.H * d.W * d.C);
+        max_pad = std::max(max_pad, size_t(B) * (d.T + 2) * (d.H + 2) * (d.W + 2) * d.C);
+      }
     }
   }
   max_mod = std::max(max_mod, size_t(B) * 2 * e->Cf);
@@ -384,8 +440,16 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   ws.base = reinterpret_cast<uintptr_t>(e->ws);
   bf16* cur = reinterpret_cast<bf16*>(ws.take(max_act * 2));
   bf16* other = reinterpret_cast<bf16*>(ws.take(max_act * 2));
-  bf16* xp = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
-  bf16* xp2 = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
+  bf16* xps[2];
+  xps[0] = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
+  xps[1] = reinterpret_cast<bf16*>(ws.take(max_pad * 2));
+  if (sharded) {
+    // the padded conv inputs live in the exchange region: neighbours store their boundary frames into them
+    LTX2_REQUIRE(max_pad * 2 <= cp.pad_bytes, "vae_decode_sharded: padded input of %zu bytes exceeds the exchange buffers "
+                 "(%zu): call ltx2_vae_cp_init with the largest latent", max_pad * 2, cp.pad_bytes);
+    xps[0] = reinterpret_cast<bf16*>(cp.region + cp.off_xp[0]);
+    xps[1] = reinterpret_cast<bf16*>(cp.region + cp.off_xp[1]);
+  }
   float* mod = reinterpret_cast<float*>(ws.take(max_mod * 4));
   float* mod_final = reinterpret_cast<float*>(ws.take(size_t(B) * 2 * e->Cf * 4));
   float* tdev = reinterpret_cast<float*>(ws.take(size_t(B) * 4 + 16));
@@ -394,7 +458,27 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   float* temb = reinterpret_cast<float*>(ws.take(size_t(B) * 4 * maxC * 4));
   LTX2_REQUIRE(B <= 8, "vae_decode: batch %d > 8 unsupported", B);
 
-  if (use_t) {
+  // ---- temporal shards: halo exchange in front of every conv except conv_in ----
+  // A conv reads buffer xps[i]; the producer of the NEXT conv's input writes xps[1 - i], so a neighbour that is one conv
+  // ahead never stores into a buffer this rank is still reading.
+  int last_read = 1;
+  auto wbuf = [&]() { return 1 - last_read; };
+  auto has_prev = [&]() { return sharded && n_of(rank) > 0 && ra[rank] > 0; };
+  auto has_next = [&]() { return sharded && n_of(rank) > 0 && rb[rank] < Tt; };
+  auto sync_halo = [&](int buf, const Dims& dd) -> int {
+    if (!sharded) return LTX2_OK;
+    if (n_of(rank) > 0) {
+      const int64_t frame_bytes = int64_t(dd.H + 2) * (dd.W + 2) * dd.C * 2;
+      void* prev = has_prev() ? cp.peer_base[rank - 1] + cp.off_xp[buf] : nullptr;
+      void* next = has_next() ? cp.peer_base[rank + 1] + cp.off_xp[buf] : nullptr;
+      LTX2_PROPAGATE(halo_push(xps[buf], prev, next, B, n_of(rank), n_of(rank - 1), n_of(rank + 1), frame_bytes, st));
+    }
+    return cp_barrier(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, cp.world,
+                      ++cp.epoch, st);
+  };
+  const bool idle = sharded && n_of(rank) == 0;      // more ranks than latent frames: only keeps the barriers in step
+
+  if (use_t && !idle) {
     std::vector<float> tv(B, timestep);
     LTX2_CUDA_CHECK(cudaMemcpyAsync(tdev, tv.data(), size_t(B) * 4, cudaMemcpyHostToDevice, st));
     LTX2_CUDA_CHECK(cudaStreamSynchronize(st));     // tv is a stack-owned staging buffer
@@ -410,12 +494,17 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
     const float* mod = nullptr;
     int64_t stride = 0, shift_off = 0, scale_off = 0;
   };
-  auto conv = [&](const ConvW& w, const bf16* xin_padded, const Dims& dd, int mode, bf16* o, const bf16* residual,
-                  float* o32, const StageW* up, const PadOut* po = nullptr) -> int {
+  // conv that reads xps[buf]; in sharded mode it is preceded by the halo exchange of that buffer (except conv_in)
+  auto conv = [&](const ConvW& w, int buf, bool halo, const Dims& dd, int mode, bf16* o, const bf16* residual, float* o32,
+                  const StageW* up, const PadOut* po = nullptr) -> int {
+    if (halo) LTX2_PROPAGATE(sync_halo(buf, Dims{dd.T, dd.H, dd.W, w.Cin}));
+    last_read = buf;
+    if (idle) return LTX2_OK;
     ConvParams p;
     if (po != nullptr && po->dst != nullptr) {
       p.pad_out = po->dst; p.pad_act = po->act; p.pad_mod = po->mod; p.pad_mod_stride = po->stride;
       p.pad_shift_off = po->shift_off; p.pad_scale_off = po->scale_off; p.pad_eps = 1e-6f; p.pad_causal = causal;
+      p.pad_skip_front = has_prev(); p.pad_skip_back = has_next();
     }
     p.B = B; p.T = dd.T; p.H = dd.H; p.W = dd.W;
     p.Cin = w.Cin; p.Cout = w.Cout; p.Cout_pad = w.Cout_pad;
@@ -423,6 +512,7 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
     if (up) {
       p.ft = up->ft; p.fh = up->fh; p.fw = up->fw;
       p.c_d2s = up->residual ? w.Cin / (up->ft * up->fh * up->fw) : 0;
+      p.d2s_keep_first = has_prev();
     }
     VaeProfiler& pf = e->prof;
     if (pf.on) {
@@ -434,76 +524,89 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
       pf.flops.push_back(2.0 * w.Cin * double(w.Cout) * 27.0 * B * dd.T * double(dd.H) * dd.W);
       cudaEventRecord(pf.events[pf.used], st);
     }
-    const int r = conv3d_bf16(xin_padded, w.w, p, st);
+    const int r = conv3d_bf16(xps[buf], w.w, p, st);
     if (pf.on) {
       cudaEventRecord(pf.events[pf.used + 1], st);
       pf.used += 2;
     }
     return r;
   };
+  // separate normalise / activate / pad pass into the write buffer
+  auto pad_pass = [&](const bf16* src, const Dims& dd, int C, int act, const float* m, int64_t stride, int64_t sh,
+                      int64_t sc) -> int {
+    if (idle) return LTX2_OK;
+    return norm_act_pad(src, xps[wbuf()], B, dd.T, dd.H, dd.W, C, act, m, stride, sh, sc, 1e-6f, causal, st, has_prev(),
+                        has_next());
+  };
   e->prof.used = 0;
   e->prof.flops.clear();
 
-  d = Dims{(int)shape[2], (int)shape[3], (int)shape[4], Cl};
+  d = Dims{n_of(rank), (int)shape[3], (int)shape[4], Cl};
   const bool inject = use_t && noise != nullptr && noise_scale != 0.f;
-  LTX2_PROPAGATE(latent_to_padded(latent, dtype, e->stdv, e->mean, inject ? noise : nullptr, noise_scale, xp, B, Cl,
-                                  d.T, d.H, d.W, causal, st));
-  LTX2_PROPAGATE(conv(e->conv_in, xp, d, CONV_EPI_PLAIN, cur, nullptr, nullptr, nullptr));
+  if (!idle)
+    LTX2_PROPAGATE(latent_to_padded(latent, dtype, e->stdv, e->mean, inject ? noise : nullptr, noise_scale, xps[0], B, Cl,
+                                    Tt, d.H, d.W, causal, st, ra[rank], d.T));
+  LTX2_PROPAGATE(conv(e->conv_in, 0, false, d, CONV_EPI_PLAIN, cur, nullptr, nullptr, nullptr));
   d.C = e->conv_in.Cout;
 
   // Final norm / scale-shift rows (simple_decoder.py:528-542), computed up front: the last conv of the last group
   // produces the activated, padded input of conv_out in its epilogue.
   const int Cf = e->Cf;
-  if (use_t && e->last_temb.present) {
-    LTX2_PROPAGATE(run_mlp(e->last_temb));
-  } else {
-    LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 2 * Cf * 4, st));
+  if (!idle) {
+    if (use_t && e->last_temb.present) {
+      LTX2_PROPAGATE(run_mlp(e->last_temb));
+    } else {
+      LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 2 * Cf * 4, st));
+    }
+    LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod_final, 0, int64_t(2) * Cf, 1, B,
+                                       2, Cf, st));
   }
-  LTX2_PROPAGATE(build_modulation_ex(e->last_table, 0, temb, int64_t(2) * Cf, Cf, mod_final, 0, int64_t(2) * Cf, 1, B, 2,
-                                     Cf, st));
   // Stages with 128 or 256 channels (83 % of the conv FLOPs, all of the large activations) run FUSED: every conv's
   // epilogue writes the next conv's input already pixel-normalised, modulated, SiLU-activated and padded, so the
   // separate norm_act_pad pass (one read + one write of the activation per conv) only runs once per group.
   // LTX2_VAE_FUSE=0 restores the unfused sequence (A/B and debugging).
   const char* fuse_env = getenv("LTX2_VAE_FUSE");
   const bool fuse_on = !(fuse_env && fuse_env[0] == '0');
-  bool xp_ready = false;           // xp already holds the padded input of the next consumer
+  bool xp_ready = false;           // xps[wbuf()] already holds the padded input of the next consumer
   const size_t n_stages = e->stages.size();
   for (size_t si = 0; si < n_stages; ++si) {
     StageW& s = e->stages[si];
     if (s.kind == 0) {
       const int C = s.C;
-      if (use_t && s.temb.present) {
-        LTX2_PROPAGATE(run_mlp(s.temb));
-      } else {
-        LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 4 * C * 4, st));
+      if (!idle) {
+        if (use_t && s.temb.present) {
+          LTX2_PROPAGATE(run_mlp(s.temb));
+        } else {
+          LTX2_CUDA_CHECK(cudaMemsetAsync(temb, 0, size_t(B) * 4 * C * 4, st));
+        }
+        LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod, int64_t(B) * 4 * C,
+                                           int64_t(4) * C, s.num_layers, B, 4, C, st));
       }
-      LTX2_PROPAGATE(build_modulation_ex(s.tables, int64_t(4) * C, temb, int64_t(4) * C, C, mod, int64_t(B) * 4 * C,
-                                         int64_t(4) * C, s.num_layers, B, 4, C, st));
       const bool fuse = fuse_on && (C == 128 || C == 256);
       if (!fuse) {
         for (int j = 0; j < s.num_layers; ++j) {
           const float* mj = mod + size_t(j) * B * 4 * C;
-          LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, 0, C, 1e-6f, causal, st));
-          LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, other, nullptr, nullptr, nullptr));
-          LTX2_PROPAGATE(norm_act_pad(other, xp, B, d.T, d.H, d.W, C, 1, mj, int64_t(4) * C, int64_t(2) * C,
-                                      int64_t(3) * C, 1e-6f, causal, st));
-          LTX2_PROPAGATE(conv(s.conv2[j], xp, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr));
+          LTX2_PROPAGATE(pad_pass(cur, d, C, 1, mj, int64_t(4) * C, 0, C));
+          LTX2_PROPAGATE(conv(s.conv1[j], wbuf(), true, d, CONV_EPI_PLAIN, other, nullptr, nullptr, nullptr));
+          LTX2_PROPAGATE(pad_pass(other, d, C, 1, mj, int64_t(4) * C, int64_t(2) * C, int64_t(3) * C));
+          LTX2_PROPAGATE(conv(s.conv2[j], wbuf(), true, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr));
         }
         xp_ready = false;
         continue;
       }
-      LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, C, 1, mod, int64_t(4) * C, 0, C, 1e-6f, causal, st));
+      LTX2_PROPAGATE(pad_pass(cur, d, C, 1, mod, int64_t(4) * C, 0, C));
       for (int j = 0; j < s.num_layers; ++j) {
         const float* mj = mod + size_t(j) * B * 4 * C;
-        // conv1: xp -> xp2 = act(norm2_j(.)); its raw output has no other reader
+        // conv1: reads xps[i] -> xps[1 - i] = act(norm2_j(.)); its raw output has no other reader
+        int rb_ = wbuf();
         PadOut p1;
-        p1.dst = xp2; p1.act = 1; p1.mod = mj; p1.stride = int64_t(4) * C; p1.shift_off = int64_t(2) * C;
+        p1.dst = xps[1 - rb_]; p1.act = 1; p1.mod = mj; p1.stride = int64_t(4) * C; p1.shift_off = int64_t(2) * C;
         p1.scale_off = int64_t(3) * C;
-        LTX2_PROPAGATE(conv(s.conv1[j], xp, d, CONV_EPI_PLAIN, nullptr, nullptr, nullptr, nullptr, &p1));
-        // conv2: xp2 -> cur = residual + conv (raw, the next residual) and xp = padded input of the next consumer
+        LTX2_PROPAGATE(conv(s.conv1[j], rb_, true, d, CONV_EPI_PLAIN, nullptr, nullptr, nullptr, nullptr, &p1));
+        // conv2: -> cur = residual + conv (raw, the next residual) and the padded input of the next consumer
+        rb_ = wbuf();
         PadOut p2;
-        p2.dst = xp;
+        p2.dst = xps[1 - rb_];
         if (j + 1 < s.num_layers) {
           p2.act = 1; p2.mod = mod + size_t(j + 1) * B * 4 * C; p2.stride = int64_t(4) * C; p2.shift_off = 0;
           p2.scale_off = C;
@@ -518,21 +621,143 @@ int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
           p2.dst = nullptr;                 // another res group follows: its rows are not built yet
           xp_ready = false;
         }
-        LTX2_PROPAGATE(conv(s.conv2[j], xp2, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr, &p2));
+        LTX2_PROPAGATE(conv(s.conv2[j], rb_, true, d, CONV_EPI_RESIDUAL, cur, cur, nullptr, nullptr, &p2));
       }
     } else {
-      if (!xp_ready)
-        LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, s.C, 0, nullptr, 0, 0, 0, 1e-6f, causal, st));
+      if (!xp_ready) LTX2_PROPAGATE(pad_pass(cur, d, s.C, 0, nullptr, 0, 0, 0));
       xp_ready = false;
-      LTX2_PROPAGATE(conv(s.up, xp, d, CONV_EPI_D2S, other, cur, nullptr, &s));
+      LTX2_PROPAGATE(conv(s.up, wbuf(), true, d, CONV_EPI_D2S, other, cur, nullptr, &s));
       std::swap(cur, other);
-      d.T = d.T * s.ft - (s.ft > 1 ? 1 : 0); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
+      if (s.ft > 1) {
+        for (int r = 0; r < world; ++r)
+          if (rb[r] > ra[r]) { ra[r] = std::max(0, 2 * ra[r] - 1); rb[r] = 2 * rb[r] - 1; }
+        Tt = 2 * Tt - 1;
+        for (int r = 0; r < world; ++r)
+          if (rb[r] <= ra[r]) ra[r] = rb[r] = Tt;
+      }
+      d.T = n_of(rank); d.H *= s.fh; d.W *= s.fw; d.C = s.C / s.multiplier;
     }
   }
   // final norm + scale/shift + SiLU (unless the last conv already produced it), conv_out, unpatchify (:528-552)
-  if (!xp_ready)
-    LTX2_PROPAGATE(norm_act_pad(cur, xp, B, d.T, d.H, d.W, Cf, 1, mod_final, int64_t(2) * Cf, 0, Cf, 1e-6f, causal, st));
-  return conv(e->conv_out, xp, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+  if (!xp_ready) LTX2_PROPAGATE(pad_pass(cur, d, Cf, 1, mod_final, int64_t(2) * Cf, 0, Cf));
+  if (out_t0) *out_t0 = idle ? 0 : ra[rank];
+  if (out_tn) *out_tn = n_of(rank);
+  return conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
+                    float noise_scale, const float* noise, int32_t causal, float* out, void* stream) {
+  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, causal, out, stream, false, nullptr,
+                         nullptr);
+}
+
+// ---- temporal shards over the GPUs of one NVLink box ---------------------------------------------
+// Every rank holds the whole latent and the decoder weights and computes a contiguous range of frames of every activation.
+// A 3x3x3 conv needs one frame from each neighbour: the padded conv inputs live in a CUDA-IPC exchange region, and after a
+// rank has produced its padded input it stores its first / last frame into the neighbours' pad slots (halo_push) and all
+// ranks pass a flag barrier -- one small kernel pair per conv, no collective library on the data path.  Frame t of a
+// stage becomes frames 2t-1, 2t of the next (frame 0 -> 0), so ownership follows the depth-to-space without any
+// re-distribution, and every rank ends with a contiguous range of output frames.  Bit-identical to the single-GPU decode.
+int ltx2_vae_shard_frames(LtxVae* e, int64_t latent_frames, int32_t rank, int32_t world, int64_t* t0, int64_t* tn) {
+  LTX2_REQUIRE(e && t0 && tn && world >= 1 && world <= kMaxVaeRanks && rank >= 0 && rank < world && latent_frames >= 1,
+               "vae_shard_frames: bad argument");
+  int a, b;
+  split_frames((int)latent_frames, world, rank, &a, &b);
+  for (auto& s : e->stages)
+    if (s.kind == 1 && s.ft > 1 && b > a) { a = std::max(0, 2 * a - 1); b = 2 * b - 1; }
+  *t0 = b > a ? a : 0;
+  *tn = b - a;
+  return LTX2_OK;
+}
+
+int ltx2_vae_cp_init(LtxVae* e, int32_t rank, int32_t world, const int64_t max_latent_shape[5], char* handle_out) {
+  LTX2_REQUIRE(e && handle_out && max_latent_shape, "vae_cp_init: null argument");
+  LTX2_REQUIRE(world >= 2 && world <= kMaxVaeRanks && rank >= 0 && rank < world, "vae_cp_init: bad rank %d / world %d", rank,
+               world);
+  VaeCp& cp = e->cp;
+  LTX2_REQUIRE(cp.region == nullptr, "vae_cp_init: already initialised (call ltx2_vae_cp_shutdown first)");
+  // largest padded conv input of ANY rank for this latent shape (the region layout must be the same on every rank)
+  const int B = (int)max_latent_shape[0], T = (int)max_latent_shape[2];
+  size_t max_pad = 0;
+  for (int r = 0; r < world; ++r) {
+    int a, b;
+    split_frames(T, world, r, &a, &b);
+    int H = (int)max_latent_shape[3], W = (int)max_latent_shape[4], C = std::max(e->conv_in.Cout, e->cfg.latent_channels);
+    max_pad = std::max(max_pad, size_t(B) * (b - a + 2) * (H + 2) * (W + 2) * C);
+    for (auto& s : e->stages)
+      if (s.kind == 1) {
+        if (s.ft > 1 && b > a) { a = std::max(0, 2 * a - 1); b = 2 * b - 1; }
+        H *= s.fh; W *= s.fw; C = s.C / s.multiplier;
+        max_pad = std::max(max_pad, size_t(B) * (b - a + 2) * (H + 2) * (W + 2) * C);
+      }
+  }
+  cp.rank = rank; cp.world = world;
+  cp.pad_bytes = align256(max_pad * 2);
+  cp.off_xp[0] = 0; cp.off_xp[1] = cp.pad_bytes; cp.off_flags = 2 * cp.pad_bytes;
+  cp.region_bytes = cp.off_flags + 256;
+  LTX2_CUDA_CHECK(cudaMalloc(&cp.region, cp.region_bytes));
+  LTX2_CUDA_CHECK(cudaMemset(cp.region, 0, cp.region_bytes));
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  LTX2_CUDA_CHECK(cudaIpcGetMemHandle(&h, cp.region));
+  memcpy(handle_out, &h, 64);
+  return LTX2_OK;
+}
+
+int ltx2_vae_cp_connect(LtxVae* e, const char* handles) {
+  LTX2_REQUIRE(e && handles && e->cp.region, "vae_cp_connect: call ltx2_vae_cp_init first");
+  VaeCp& cp = e->cp;
+  std::vector<uint32_t*> flags(cp.world);
+  for (int r = 0; r < cp.world; ++r) {
+    if (r == cp.rank) {
+      cp.peer_base[r] = cp.region;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + size_t(r) * 64, 64);
+      void* p = nullptr;
+      LTX2_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      cp.peer_base[r] = reinterpret_cast<char*>(p);
+      cp.opened[r] = true;
+    }
+    flags[r] = reinterpret_cast<uint32_t*>(cp.peer_base[r] + cp.off_flags);
+  }
+  LTX2_CUDA_CHECK(cudaMalloc(&cp.peer_flags_dev, sizeof(uint32_t*) * kMaxVaeRanks));
+  LTX2_CUDA_CHECK(cudaMemcpy(cp.peer_flags_dev, flags.data(), sizeof(uint32_t*) * cp.world, cudaMemcpyHostToDevice));
+  cp.epoch = 0;
+  cp.connected = true;
+  return LTX2_OK;
+}
+
+// phase 0 on every rank (close the imported mappings), host barrier, phase 1 (free the own region)
+int ltx2_vae_cp_shutdown(LtxVae* e, int32_t phase) {
+  LTX2_REQUIRE(e != nullptr && (phase == 0 || phase == 1), "vae_cp_shutdown: bad argument");
+  VaeCp& cp = e->cp;
+  if (!cp.region) return LTX2_OK;
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  if (phase == 0) {
+    for (int r = 0; r < cp.world; ++r)
+      if (cp.opened[r]) {
+        cudaIpcCloseMemHandle(cp.peer_base[r]);
+        cp.opened[r] = false;
+        cp.peer_base[r] = nullptr;
+      }
+    cp.connected = false;
+    return LTX2_OK;
+  }
+  cudaFree(cp.region);
+  if (cp.peer_flags_dev) cudaFree(cp.peer_flags_dev);
+  cp = VaeCp();
+  return LTX2_OK;
+}
+
+int ltx2_vae_decode_sharded(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
+                            float noise_scale, const float* noise, float* out_local, int64_t* out_t0, int64_t* out_tn,
+                            void* stream) {
+  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, 0, out_local, stream, true, out_t0, out_tn);
 }
 
 // Conv3dSimple.__call__ (simple_decoder.py:90-180) as ONE op, for unit parity of the conv kernel at production shapes:

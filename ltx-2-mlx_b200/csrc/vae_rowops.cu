@@ -33,17 +33,20 @@ template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { retu
 template <typename Tin>
 __global__ void latent_to_padded_kernel(const Tin* __restrict__ lat, const float* __restrict__ std_,
                                         const float* __restrict__ mean, const float* __restrict__ noise, float ns,
-                                        __nv_bfloat16* __restrict__ out, int B, int C, int T, int H, int W, int causal) {
-  const int64_t total = static_cast<int64_t>(B) * (T + 2) * (H + 2) * (W + 2) * C;
+                                        __nv_bfloat16* __restrict__ out, int B, int C, int T, int H, int W, int causal,
+                                        int t0, int Tn) {
+  // T = frames of the latent; the output holds the window [t0, t0 + Tn) plus one pad slot on each side, which is the
+  // true neighbour frame when the window is a shard of a longer clip (replication only at the clip's own ends)
+  const int64_t total = static_cast<int64_t>(B) * (Tn + 2) * (H + 2) * (W + 2) * C;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = i % C;
     int64_t r = i / C;
     const int wp = r % (W + 2); r /= (W + 2);
     const int hp = r % (H + 2); r /= (H + 2);
-    const int tp = r % (T + 2);
-    const int b = r / (T + 2);
-    const int t = src_t(tp, T, causal), h = reflect1(hp - 1, H), w = reflect1(wp - 1, W);
+    const int tp = r % (Tn + 2);
+    const int b = r / (Tn + 2);
+    const int t = src_t(tp + t0, T, causal), h = reflect1(hp - 1, H), w = reflect1(wp - 1, W);
     const int64_t src = (((static_cast<int64_t>(b) * C + c) * T + t) * H + h) * W + w;
     float v = ldf<Tin>(lat + src) * std_[c] + mean[c];
     if (noise != nullptr) v = noise[src] * ns + (1.0f - ns) * v;
@@ -60,12 +63,14 @@ template <int U>
 __global__ void __launch_bounds__(256)
 norm_act_pad_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int T, int H, int W, int C,
                     int P, int act, const float* __restrict__ mod, int mod_stride, int shift_off, int scale_off,
-                    float eps, int causal) {
+                    float eps, int causal, int skip_front, int skip_back) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;                       // (b*(T+2) + tp)*(H+2) + hp
   const int hp = row % (H + 2);
   const int tp = (row / (H + 2)) % (T + 2);
+  // temporal shards: a pad slot that holds a NEIGHBOUR rank's frame is filled by that rank (halo_push), not replicated
+  if ((skip_front && tp == 0) || (skip_back && tp == T + 1)) return;
   const int b = row / ((H + 2) * (T + 2));
   const int t = src_t(tp, T, causal), h = reflect1(hp - 1, H);
   const __nv_bfloat16* src_row = x + (static_cast<int64_t>(b) * T + t) * H * static_cast<int64_t>(W) * C +
@@ -241,23 +246,25 @@ inline int grid_for(int64_t n, int threads) {
 
 int latent_to_padded(const void* latent, int dtype, const float* std_, const float* mean, const float* noise,
                      float noise_scale, void* out, int B, int C, int T, int H, int W, int causal,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int t0, int Tn) {
   LTX2_REQUIRE(H >= 2 && W >= 2, "reflect padding needs H, W >= 2 (got %d x %d)", H, W);
-  const int64_t total = static_cast<int64_t>(B) * (T + 2) * (H + 2) * (W + 2) * C;
+  if (Tn < 0) { t0 = 0; Tn = T; }
+  LTX2_REQUIRE(t0 >= 0 && Tn >= 1 && t0 + Tn <= T && (!causal || (t0 == 0 && Tn == T)), "latent_to_padded: bad window");
+  const int64_t total = static_cast<int64_t>(B) * (Tn + 2) * (H + 2) * (W + 2) * C;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   const int g = grid_for(total, 256);
   switch (dtype) {
     case LTX2_F32:
       latent_to_padded_kernel<<<g, 256, 0, stream>>>(reinterpret_cast<const float*>(latent), std_, mean, noise,
-                                                     noise_scale, o, B, C, T, H, W, causal);
+                                                     noise_scale, o, B, C, T, H, W, causal, t0, Tn);
       break;
     case LTX2_BF16:
       latent_to_padded_kernel<<<g, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(latent), std_, mean, noise,
-                                                     noise_scale, o, B, C, T, H, W, causal);
+                                                     noise_scale, o, B, C, T, H, W, causal, t0, Tn);
       break;
     case LTX2_F16:
       latent_to_padded_kernel<<<g, 256, 0, stream>>>(reinterpret_cast<const __half*>(latent), std_, mean, noise,
-                                                     noise_scale, o, B, C, T, H, W, causal);
+                                                     noise_scale, o, B, C, T, H, W, causal, t0, Tn);
       break;
     default: set_error("latent_to_padded: bad dtype %d", dtype); return LTX2_ERR_INVALID;
   }
@@ -267,7 +274,8 @@ int latent_to_padded(const void* latent, int dtype, const float* std_, const flo
 }
 
 int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, int act, const float* mod,
-                 int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream) {
+                 int64_t mod_stride, int64_t shift_off, int64_t scale_off, float eps, int causal, cudaStream_t stream,
+                 int skip_front, int skip_back) {
   LTX2_REQUIRE(C % 64 == 0 && C <= 32 * 8 * kPadMaxU && (C / 8 >= 32 ? (C / 8) % 32 == 0 : (32 % (C / 8)) == 0),
                "norm_act_pad: C=%d unsupported (64, 128, 256, 512, 768 or 1024)", C);
   LTX2_REQUIRE(H >= 2 && W >= 2, "reflect padding needs H, W >= 2 (got %d x %d)", H, W);
@@ -280,12 +288,46 @@ int norm_act_pad(const void* x, void* out, int B, int T, int H, int W, int C, in
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
   const int ms = static_cast<int>(mod_stride), so = static_cast<int>(shift_off), sc = static_cast<int>(scale_off);
   switch (U) {
-    case 1: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<1>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
-    case 2: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<2>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
-    case 3: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<3>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
-    case 4: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<4>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal)); break;
+    case 1: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<1>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal, skip_front, skip_back)); break;
+    case 2: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<2>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal, skip_front, skip_back)); break;
+    case 3: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<3>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal, skip_front, skip_back)); break;
+    case 4: LTX2_CUDA_CHECK(launch_pdl(norm_act_pad_kernel<4>, dim3(rows), dim3(256), 0, stream, xi, xo, T, H, W, C, P, act, mod, ms, so, sc, eps, causal, skip_front, skip_back)); break;
     default: set_error("norm_act_pad: C=%d unsupported", C); return LTX2_ERR_INVALID;
   }
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+// Temporal shards of the decoder (vae_engine.cu): after a rank has produced its padded conv input [B, n+2, Hp*Wp*C], its
+// first real frame (slot 1) goes into the PREVIOUS rank's back pad slot (n_prev + 1) and its last real frame (slot n)
+// into the NEXT rank's front pad slot (0) -- stores to peer memory over NVLink, 16 bytes per thread.
+__global__ void halo_push_kernel(const uint4* __restrict__ mine, uint4* __restrict__ prev, uint4* __restrict__ next, int B,
+                                 int n, int n_prev, int n_next, int64_t frame16) {
+  const int64_t per = static_cast<int64_t>(B) * frame16;
+  const int64_t total = per * ((prev != nullptr ? 1 : 0) + (next != nullptr ? 1 : 0));
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool to_prev = prev != nullptr && i < per;
+    const int64_t j = to_prev ? i : i - (prev != nullptr ? per : 0);
+    const int b = j / frame16;
+    const int64_t e = j % frame16;
+    if (to_prev)
+      prev[(static_cast<int64_t>(b) * (n_prev + 2) + n_prev + 1) * frame16 + e] =
+          mine[(static_cast<int64_t>(b) * (n + 2) + 1) * frame16 + e];
+    else
+      next[(static_cast<int64_t>(b) * (n_next + 2)) * frame16 + e] = mine[(static_cast<int64_t>(b) * (n + 2) + n) * frame16 + e];
+  }
+}
+
+int halo_push(const void* mine, void* prev, void* next, int B, int n, int n_prev, int n_next, int64_t frame_bytes,
+              cudaStream_t stream) {
+  if (prev == nullptr && next == nullptr) return LTX2_OK;
+  LTX2_REQUIRE(frame_bytes % 16 == 0 && n >= 1, "halo_push: bad frame size");
+  const int64_t total = static_cast<int64_t>(B) * (frame_bytes / 16) * 2;
+  halo_push_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(mine),
+                                                            reinterpret_cast<uint4*>(prev), reinterpret_cast<uint4*>(next),
+                                                            B, n, n_prev, n_next, frame_bytes / 16);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

@@ -39,6 +39,7 @@ class SimpleVideoDecoder:
         self.mean_of_means = torch.zeros(128)
         self.std_of_means = torch.zeros(128)
         self._noise_generator: Optional[torch.Generator] = None
+        self._shards = None            # (rank, world, group) once enable_temporal_shards() ran
 
         cfg = LtxVaeConfig()
         cfg.base_channels, cfg.latent_channels = base_channels, 128
@@ -137,6 +138,108 @@ class SimpleVideoDecoder:
         return out
 
 
+def shard_frames(decoder: SimpleVideoDecoder, latent_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first output frame, output frame count) of `rank` when a `latent_frames`-frame latent is decoded in temporal
+    shards over `world` ranks (host logic of the C ABI, no GPU work)."""
+    t0, tn = C.c_int64(), C.c_int64()
+    check(lib().ltx2_vae_shard_frames(decoder._h, latent_frames, rank, world, C.byref(t0), C.byref(tn)),
+          "ltx2_vae_shard_frames")
+    return int(t0.value), int(tn.value)
+
+
+def enable_temporal_shards(decoder: SimpleVideoDecoder, max_latent_shape, group=None) -> None:
+    """Collective: set up the exchange region for decoding ONE clip over the ranks of `group` in temporal shards
+    (include/ltx2_b200.h, ltx2_vae_cp_*).  `max_latent_shape` = the largest (B, 128, T, H, W) latent (or chunk) that will
+    be decoded; every rank must pass the same latents and hold the same weights afterwards."""
+    import torch.distributed as dist
+    from .context_parallel import exchange_handles
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return
+    buf = C.create_string_buffer(64)
+    shp = (C.c_int64 * 5)(*[int(v) for v in max_latent_shape])
+    with torch.cuda.device(decoder.device):
+        check(lib().ltx2_vae_cp_init(decoder._h, rank, world, shp, buf), "ltx2_vae_cp_init")
+        handles = exchange_handles(buf.raw, group)
+        check(lib().ltx2_vae_cp_connect(decoder._h, handles), "ltx2_vae_cp_connect")
+        torch.cuda.synchronize()
+    dist.barrier(group=group)
+    decoder._shards = (rank, world, group)
+
+
+def disable_temporal_shards(decoder: SimpleVideoDecoder) -> None:
+    """Collective teardown: close the imported mappings, barrier, free the own region."""
+    import torch.distributed as dist
+    if decoder._shards is None:
+        return
+    group = decoder._shards[2]
+    with torch.cuda.device(decoder.device):
+        check(lib().ltx2_vae_cp_shutdown(decoder._h, 0), "ltx2_vae_cp_shutdown")
+        dist.barrier(group=group)
+        check(lib().ltx2_vae_cp_shutdown(decoder._h, 1), "ltx2_vae_cp_shutdown")
+    dist.barrier(group=group)
+    decoder._shards = None
+
+
+def decode_sharded(decoder: SimpleVideoDecoder, latent, timestep: Optional[float] = 0.05,
+                   dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """SimpleVideoDecoder.__call__ over the ranks enabled by enable_temporal_shards(): every rank passes the same
+    latent, computes its frame range, and the ranges are collected on rank `dst` (others return None) or on every rank
+    (dst=None).  Bit-identical to the single-GPU decode (noise injection off or the same noise on every rank)."""
+    import torch.distributed as dist
+    rank, world, group = decoder._shards
+    with torch.cuda.device(decoder.device):
+        x = to_device(latent, decoder.device)
+        if x.ndim != 5:
+            raise ValueError(f"latent must be (B, C, T, H, W); got {tuple(x.shape)}")
+        B, _, T, H, W = decoder.output_shape(x.shape)
+        t0, tn = shard_frames(decoder, x.shape[2], rank, world)
+        local = torch.empty(B, 3, max(tn, 1), H, W, device=decoder.device, dtype=torch.float32)
+        noise = None
+        s = float(decoder.decode_noise_scale)
+        if decoder.timestep_conditioning and timestep is not None and s != 0.0:
+            # every rank must blend the SAME noise into the latent (each also builds its neighbours' boundary frames of
+            # the first conv input): rank 0 of the group draws it
+            noise = torch.randn(x.shape, device=decoder.device, dtype=torch.float32, generator=decoder._noise_generator)
+            dist.broadcast(noise, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        shape = (C.c_int64 * 5)(*x.shape)
+        o0, on = C.c_int64(), C.c_int64()
+        check(lib().ltx2_vae_decode_sharded(decoder._h, ptr(x), dtype_code(x), shape,
+                                            -1.0 if timestep is None else float(timestep), s, ptr(noise), ptr(local),
+                                            C.byref(o0), C.byref(on), stream_ptr()), "ltx2_vae_decode_sharded")
+        assert (int(o0.value), int(on.value)) == (t0, tn)
+        g = lambda r: dist.get_global_rank(group, r) if group is not None else r  # noqa: E731
+        spans = [shard_frames(decoder, x.shape[2], r, world) for r in range(world)]
+        if dst is None:
+            # every rank needs the clip: all-gather frame ranges padded to the longest one
+            nmax = max(n for _, n in spans)
+            padded = torch.zeros(B, 3, nmax, H, W, device=decoder.device, dtype=torch.float32)
+            if tn:
+                padded[:, :, :tn] = local[:, :, :tn]
+            parts = [torch.empty_like(padded) for _ in range(world)]
+            dist.all_gather(parts, padded, group=group)
+            video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32)
+            for (a, n), part in zip(spans, parts):
+                if n:
+                    video[:, :, a:a + n] = part[:, :, :n]
+            return video
+        if rank != dst:
+            if tn:
+                dist.send(local[:, :, :tn].contiguous(), dst=g(dst), group=group)
+            return None
+        video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32)
+        for r, (a, n) in enumerate(spans):
+            if n == 0:
+                continue
+            if r == rank:
+                video[:, :, a:a + n] = local[:, :, :n]
+            else:
+                tmp = torch.empty(B, 3, n, H, W, device=decoder.device, dtype=torch.float32)
+                dist.recv(tmp, src=g(r), group=group)
+                video[:, :, a:a + n] = tmp
+        return video
+
+
 def load_vae_decoder_weights(decoder: SimpleVideoDecoder, weights_path: str) -> None:
     """Drop-in for simple_decoder.load_vae_decoder_weights: safetensors file -> engine."""
     from safetensors import safe_open
@@ -207,7 +310,10 @@ def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[
     if group is not None:              # e.g. torch.distributed.group.WORLD
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sharded = decoder._shards is not None and world > 1
     if T <= temporal_chunk_size:
+        if sharded:
+            return decode_sharded(decoder, x, timestep, dst)
         if world > 1 and dst is not None and rank != dst:
             return None
         return decoder(x, timestep=timestep, show_progress=False)
@@ -219,7 +325,10 @@ def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[
     pieces = []
     length = 0
     for i, (a, b) in enumerate(plan):
-        if unit_owner(i, world) == rank:
+        if sharded:
+            # temporal shards: ALL ranks work on every chunk (its frames are split over them); collected on dst / all
+            v = decode_sharded(decoder, x[:, :, a:b].contiguous(), timestep, dst)
+        elif unit_owner(i, world) == rank:
             v = decoder(x[:, :, a:b].contiguous(), timestep=timestep, show_progress=False)
         elif dst is None or rank == dst:
             v = torch.empty(decoder.output_shape((x.shape[0], x.shape[1], b - a, x.shape[3], x.shape[4])),
@@ -233,9 +342,10 @@ def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[
         pieces.append((v, length - ov, ov, n_t))
         length = length - ov + n_t
     if world > 1:
-        for i, (v, _, _, _) in enumerate(pieces):
-            if v is not None:
-                _exchange_unit(v, unit_owner(i, world), group, dst)
+        if not sharded:
+            for i, (v, _, _, _) in enumerate(pieces):
+                if v is not None:
+                    _exchange_unit(v, unit_owner(i, world), group, dst)
         if dst is not None and rank != dst:
             return None
     video = torch.empty(B, 3, length, H, W, device=decoder.device, dtype=torch.float32)

@@ -11,7 +11,8 @@ import torch.distributed as dist  # noqa: E402
 
 from ltx2_b200 import synthetic  # noqa: E402
 from ltx2_b200.tiling import SpatialTilingConfig, TemporalTilingConfig, TilingConfig, decode_tiled  # noqa: E402
-from ltx2_b200.video_vae import SimpleVideoDecoder, decode_latent, decode_latent_video  # noqa: E402
+from ltx2_b200.video_vae import (SimpleVideoDecoder, decode_latent, decode_latent_video, decode_sharded,  # noqa: E402
+                                 disable_temporal_shards, enable_temporal_shards, shard_frames)
 
 BLOCKS = [["res_x", {"num_layers": 2}], ["compress_all", {"multiplier": 2, "residual": True}],
           ["res_x", {"num_layers": 1}], ["compress_all", {"multiplier": 2, "residual": True}],
@@ -51,6 +52,42 @@ def main():
         good = out.shape == ref.shape and d <= 1e-5
         ok = ok and good
         print(f"rank {rank} tiles {name}: max|diff| {d:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+    # ---- temporal shards: ONE clip's frames split over the ranks, halo frames exchanged through peer memory ----
+    # must be BIT-IDENTICAL to the single-GPU decode (same kernels per frame; only who computes which frame changes)
+    single = {}
+    cases = [(1, 7, 2, 3), (2, 5, 3, 2), (1, 1, 2, 2), (1, 2, 4, 4), (1, 16, 2, 2)]
+    for (B, T, H, W) in cases:
+        lat = synthetic.latents((B, 128, T, H, W), seed=500 + T)
+        single[(B, T, H, W)] = (lat, dec(lat, timestep=0.05))
+    long_lat = synthetic.latents((1, 128, 16, 2, 3), seed=520)
+    long_ref_u8 = decode_latent(long_lat, dec)
+    long_ref = decode_latent_video(long_lat, dec)
+    enable_temporal_shards(dec, (2, 128, 16, 4, 4), group=G)
+    for key, (lat, ref) in single.items():
+        for dst in (None, 0):
+            out = decode_sharded(dec, lat, 0.05, dst=dst)
+            good = (out is None) if (dst is not None and rank != dst) else torch.equal(out, ref)
+            ok = ok and good
+            spans = [shard_frames(dec, key[1], r, world) for r in range(world)]
+            print(f"rank {rank} temporal shards B,T,H,W={key} dst={dst} spans={spans}: {'OK' if good else 'MISMATCH'}",
+                  flush=True)
+    # the reference's chunked decode_latent on top of the shards (every chunk split over all ranks), uint8 frames
+    out = decode_latent_video(long_lat, dec, group=G)
+    good = torch.equal(out, long_ref)
+    u8 = decode_latent(long_lat, dec, group=G, dst=0)
+    good = good and ((u8 is None) if rank != 0 else torch.equal(u8, long_ref_u8))
+    ok = ok and good
+    print(f"rank {rank} decode_latent over temporal shards: {'OK' if good else 'MISMATCH'}", flush=True)
+    # noise injection: the same noise on every rank (broadcast from rank 0) -> shards agree with each other
+    dec.decode_noise_scale = 0.025
+    a = decode_sharded(dec, single[(1, 7, 2, 3)][0], 0.05, dst=None)
+    parts = [torch.empty_like(a) for _ in range(world)]
+    dist.all_gather(parts, a)
+    good = all(torch.equal(p, parts[0]) for p in parts) and bool(torch.isfinite(a).all())
+    ok = ok and good
+    print(f"rank {rank} temporal shards with noise injection, same clip on all ranks: {'OK' if good else 'MISMATCH'}", flush=True)
+    dec.decode_noise_scale = 0.0
+    disable_temporal_shards(dec)
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
