@@ -72,7 +72,7 @@ CONFIGS = {
                         "768x512x65 (N=3456 video + N_a=65 audio tokens, S=1024, B=1, 48 blocks)"),
     # BASELINE.json configs[3]
     "dev-cfg": dict(heads=32, head_dim=128, layers=48, caption=3840, F=16, H=24, W=32, S=1024, B=2, av=False,
-                    cfg_scale=5.0,
+                    cfg_scale=5.0, parity_blocks=1,
                     name="LTX-2 19B dev DiT denoise step, 1024x768x121 (N=12288 video tokens, S=1024), cond+uncond as "
                          "a batch of 2, CFG 5.0, 25-step LTX2Scheduler sigmas, 48 blocks"),
     # CPU-sized debug configuration (not a bench line)
@@ -628,7 +628,7 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
     # ---- parity against the oracle (un-sharded model, rank 0) ----
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = b.parity(args.parity_blocks)
+        parity = b.parity(min(args.parity_blocks, c.get("parity_blocks", args.parity_blocks)))
     barrier()
 
     # ---- context parallel: sharded forward vs the un-sharded forward of the same model, on every rank ----
@@ -704,7 +704,7 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
 
     # ---- a longer region at N > 1 (the K-step region is a fraction of a second there): >= 100 steps, clocks sampled ----
     long_run = None
-    if world > 1 and args.steps < 100 and not args.no_long:
+    if world > 1 and args.steps < 100 and not args.no_long and name == args.config:
         n_long = 100
         barrier()
         sampler = ClockSampler(local_rank)
