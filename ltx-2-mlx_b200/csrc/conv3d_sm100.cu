@@ -276,7 +276,10 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
       for (int j = 0; j < 32; j += 16) {
         const int ch = (col0 + j) / 16;
         if (ch >= p.Cout / 16) break;
-        float* o = p.out_f32 + ((static_cast<int64_t>(b) * (p.Cout / 16) + ch) * p.T + t) * Hp * static_cast<int64_t>(Wp);
+        // out_t_total > 0: this launch produces frames [out_t0, out_t0 + T) of a longer clip (temporal shards)
+        const int Tall = p.out_t_total > 0 ? p.out_t_total : p.T;
+        float* o = p.out_f32 +
+                   ((static_cast<int64_t>(b) * (p.Cout / 16) + ch) * Tall + p.out_t0 + t) * Hp * static_cast<int64_t>(Wp);
 #pragma unroll
         for (int rh = 0; rh < 4; ++rh)
           *reinterpret_cast<float4*>(o + static_cast<int64_t>(h * 4 + rh) * Wp + w * 4) =

@@ -249,6 +249,7 @@ struct ConvParams {
   float pad_eps = 1e-6f;
   int pad_causal = 0;
   int pad_skip_front = 0, pad_skip_back = 0;   // temporal shards: that T pad slot belongs to the neighbour rank
+  int out_t_total = 0, out_t0 = 0;      // UNPATCHIFY into frames [out_t0, out_t0 + T) of a clip of out_t_total frames
   int d2s_keep_first = 0;               // temporal shards: this rank's first input frame is not the clip's frame 0, so
                                         // the depth-to-space keeps both of its output frames (no first-frame drop)
 };

@@ -88,6 +88,7 @@ struct VaeCp {
   char* region = nullptr;
   size_t region_bytes = 0, pad_bytes = 0;
   size_t off_xp[2] = {0, 0}, off_flags = 0;
+  size_t off_out = 0, out_bytes = 0;      // the clip being assembled: every rank stores its frames into the receivers' copy
   char* peer_base[kMaxVaeRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool opened[kMaxVaeRanks] = {false, false, false, false, false, false, false, false};
   uint32_t** peer_flags_dev = nullptr;
@@ -375,8 +376,8 @@ void split_frames(int T, int world, int r, int* a, int* b) {
 // rank's own output frames and *out_t0 / *out_tn their position in the clip.
 int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream, bool sharded,
-                    int64_t* out_t0, int64_t* out_tn) {
-  LTX2_REQUIRE(e && latent && shape && out, "vae_decode: null argument");
+                    int dst) {
+  LTX2_REQUIRE(e && latent && shape && (out || sharded), "vae_decode: null argument");
   const int B = (int)shape[0], Cl = (int)shape[1];
   LTX2_REQUIRE(Cl == e->cfg.latent_channels, "vae_decode: latent has %d channels, decoder expects %d", Cl,
                e->cfg.latent_channels);
@@ -394,6 +395,7 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
     }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VaeCp& cp = e->cp;
+  int out_T_total = 0, out_T0 = 0;          // set for the sharded conv_out
   const int world = sharded ? cp.world : 1, rank = sharded ? cp.rank : 0;
   if (sharded) {
     LTX2_REQUIRE(cp.connected && cp.world > 1, "vae_decode_sharded: ltx2_vae_cp_connect has not been called");
@@ -514,6 +516,7 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
       p.c_d2s = up->residual ? w.Cin / (up->ft * up->fh * up->fw) : 0;
       p.d2s_keep_first = has_prev();
     }
+    p.out_t_total = out_T_total; p.out_t0 = out_T0;
     VaeProfiler& pf = e->prof;
     if (pf.on) {
       if (pf.used + 2 > pf.events.size()) {
@@ -640,9 +643,38 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   }
   // final norm + scale/shift + SiLU (unless the last conv already produced it), conv_out, unpatchify (:528-552)
   if (!xp_ready) LTX2_PROPAGATE(pad_pass(cur, d, Cf, 1, mod_final, int64_t(2) * Cf, 0, Cf));
-  if (out_t0) *out_t0 = idle ? 0 : ra[rank];
-  if (out_tn) *out_tn = n_of(rank);
-  return conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+  if (!sharded) return conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
+  // Temporal shards: conv_out writes this rank's frames at their place in ITS copy of the clip (exchange region), the
+  // spans are then stored into the receiving ranks' copies over NVLink, and after one more barrier every receiver copies
+  // the assembled clip out of the region -- no collective library call anywhere in the decode.
+  const int64_t HW = int64_t(d.H) * 4 * d.W * 4;
+  const size_t clip_bytes = size_t(B) * 3 * Tt * HW * 4;
+  LTX2_REQUIRE(clip_bytes <= cp.out_bytes, "vae_decode_sharded: clip of %zu bytes exceeds the exchange buffer (%zu)",
+               clip_bytes, cp.out_bytes);
+  float* my_clip = reinterpret_cast<float*>(cp.region + cp.off_out);
+  out_T_total = Tt;
+  out_T0 = idle ? 0 : ra[rank];
+  LTX2_PROPAGATE(conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, my_clip, nullptr));
+  if (!idle) {
+    void* peers[kMaxVaeRanks];
+    int np = 0;
+    for (int r = 0; r < world; ++r)
+      if (r != rank && (dst < 0 || r == dst)) peers[np++] = cp.peer_base[r] + cp.off_out;
+    if (np > 0)
+      for (int bc = 0; bc < B * 3; ++bc) {
+        const size_t off = (size_t(bc) * Tt + ra[rank]) * HW * 4;
+        void* pp[kMaxVaeRanks];
+        for (int i = 0; i < np; ++i) pp[i] = static_cast<char*>(peers[i]) + off;
+        LTX2_PROPAGATE(peer_broadcast(reinterpret_cast<char*>(my_clip) + off, pp, np, int64_t(n_of(rank)) * HW * 4, st));
+      }
+  }
+  LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, cp.world,
+                            ++cp.epoch, st));
+  if (dst < 0 || dst == rank) {
+    LTX2_REQUIRE(out != nullptr, "vae_decode_sharded: the receiving rank needs an output buffer");
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(out, my_clip, clip_bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return LTX2_OK;
 }
 
 }  // namespace
@@ -651,8 +683,7 @@ extern "C" {
 
 int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream) {
-  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, causal, out, stream, false, nullptr,
-                         nullptr);
+  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, causal, out, stream, false, 0);
 }
 
 // ---- temporal shards over the GPUs of one NVLink box ---------------------------------------------
@@ -697,7 +728,12 @@ int ltx2_vae_cp_init(LtxVae* e, int32_t rank, int32_t world, const int64_t max_l
   }
   cp.rank = rank; cp.world = world;
   cp.pad_bytes = align256(max_pad * 2);
-  cp.off_xp[0] = 0; cp.off_xp[1] = cp.pad_bytes; cp.off_flags = 2 * cp.pad_bytes;
+  {
+    int64_t os[5];
+    ltx2_vae_output_shape(e, max_latent_shape, os);
+    cp.out_bytes = align256(size_t(os[0]) * os[1] * os[2] * os[3] * os[4] * 4);
+  }
+  cp.off_xp[0] = 0; cp.off_xp[1] = cp.pad_bytes; cp.off_out = 2 * cp.pad_bytes; cp.off_flags = cp.off_out + cp.out_bytes;
   cp.region_bytes = cp.off_flags + 256;
   LTX2_CUDA_CHECK(cudaMalloc(&cp.region, cp.region_bytes));
   LTX2_CUDA_CHECK(cudaMemset(cp.region, 0, cp.region_bytes));
@@ -755,9 +791,9 @@ int ltx2_vae_cp_shutdown(LtxVae* e, int32_t phase) {
 }
 
 int ltx2_vae_decode_sharded(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
-                            float noise_scale, const float* noise, float* out_local, int64_t* out_t0, int64_t* out_tn,
-                            void* stream) {
-  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, 0, out_local, stream, true, out_t0, out_tn);
+                            float noise_scale, const float* noise, int32_t dst, float* out, void* stream) {
+  LTX2_REQUIRE(e && dst >= -1 && dst < e->cp.world, "vae_decode_sharded: bad destination rank %d", dst);
+  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, 0, out, stream, true, dst);
 }
 
 // Conv3dSimple.__call__ (simple_decoder.py:90-180) as ONE op, for unit parity of the conv kernel at production shapes:

@@ -165,6 +165,9 @@ def enable_temporal_shards(decoder: SimpleVideoDecoder, max_latent_shape, group=
         torch.cuda.synchronize()
     dist.barrier(group=group)
     decoder._shards = (rank, world, group)
+    # the decode-noise draws (simple_decoder.py:496-498) must be identical on every rank: same seed, same call sequence
+    decoder._shard_noise = torch.Generator(device=decoder.device)
+    decoder._shard_noise.manual_seed(0x5EED)
 
 
 def disable_temporal_shards(decoder: SimpleVideoDecoder) -> None:
@@ -184,8 +187,8 @@ def disable_temporal_shards(decoder: SimpleVideoDecoder) -> None:
 def decode_sharded(decoder: SimpleVideoDecoder, latent, timestep: Optional[float] = 0.05,
                    dst: Optional[int] = None) -> Optional[torch.Tensor]:
     """SimpleVideoDecoder.__call__ over the ranks enabled by enable_temporal_shards(): every rank passes the same
-    latent, computes its frame range, and the ranges are collected on rank `dst` (others return None) or on every rank
-    (dst=None).  Bit-identical to the single-GPU decode (noise injection off or the same noise on every rank)."""
+    latent, computes its frame range, and stores it into the clip on rank `dst` (others return None) or on every rank
+    (dst=None) through peer memory -- no torch.distributed call on the data path.  Bit-identical to the single-GPU decode (noise injection off or the same noise on every rank)."""
     import torch.distributed as dist
     rank, world, group = decoder._shards
     with torch.cuda.device(decoder.device):
@@ -193,50 +196,19 @@ def decode_sharded(decoder: SimpleVideoDecoder, latent, timestep: Optional[float
         if x.ndim != 5:
             raise ValueError(f"latent must be (B, C, T, H, W); got {tuple(x.shape)}")
         B, _, T, H, W = decoder.output_shape(x.shape)
-        t0, tn = shard_frames(decoder, x.shape[2], rank, world)
-        local = torch.empty(B, 3, max(tn, 1), H, W, device=decoder.device, dtype=torch.float32)
         noise = None
         s = float(decoder.decode_noise_scale)
         if decoder.timestep_conditioning and timestep is not None and s != 0.0:
             # every rank must blend the SAME noise into the latent (each also builds its neighbours' boundary frames of
-            # the first conv input): rank 0 of the group draws it
-            noise = torch.randn(x.shape, device=decoder.device, dtype=torch.float32, generator=decoder._noise_generator)
-            dist.broadcast(noise, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            # the first conv input): enable_temporal_shards() seeded one generator identically on all ranks
+            noise = torch.randn(x.shape, device=decoder.device, dtype=torch.float32, generator=decoder._shard_noise)
+        receive = dst is None or rank == dst
+        video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32) if receive else None
         shape = (C.c_int64 * 5)(*x.shape)
-        o0, on = C.c_int64(), C.c_int64()
         check(lib().ltx2_vae_decode_sharded(decoder._h, ptr(x), dtype_code(x), shape,
-                                            -1.0 if timestep is None else float(timestep), s, ptr(noise), ptr(local),
-                                            C.byref(o0), C.byref(on), stream_ptr()), "ltx2_vae_decode_sharded")
-        assert (int(o0.value), int(on.value)) == (t0, tn)
-        g = lambda r: dist.get_global_rank(group, r) if group is not None else r  # noqa: E731
-        spans = [shard_frames(decoder, x.shape[2], r, world) for r in range(world)]
-        if dst is None:
-            # every rank needs the clip: all-gather frame ranges padded to the longest one
-            nmax = max(n for _, n in spans)
-            padded = torch.zeros(B, 3, nmax, H, W, device=decoder.device, dtype=torch.float32)
-            if tn:
-                padded[:, :, :tn] = local[:, :, :tn]
-            parts = [torch.empty_like(padded) for _ in range(world)]
-            dist.all_gather(parts, padded, group=group)
-            video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32)
-            for (a, n), part in zip(spans, parts):
-                if n:
-                    video[:, :, a:a + n] = part[:, :, :n]
-            return video
-        if rank != dst:
-            if tn:
-                dist.send(local[:, :, :tn].contiguous(), dst=g(dst), group=group)
-            return None
-        video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32)
-        for r, (a, n) in enumerate(spans):
-            if n == 0:
-                continue
-            if r == rank:
-                video[:, :, a:a + n] = local[:, :, :n]
-            else:
-                tmp = torch.empty(B, 3, n, H, W, device=decoder.device, dtype=torch.float32)
-                dist.recv(tmp, src=g(r), group=group)
-                video[:, :, a:a + n] = tmp
+                                            -1.0 if timestep is None else float(timestep), s, ptr(noise),
+                                            -1 if dst is None else int(dst), ptr(video), stream_ptr()),
+              "ltx2_vae_decode_sharded")
         return video
 
 
