@@ -839,6 +839,15 @@ def run_ours(args, c):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.vae_only:
+        vae = bench_vae(args, dev, rank, world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            vae["n_gpus"] = world
+            print(json.dumps(vae))
+        return 0
     out = run_dit(args, c, dev, rank, local_rank, world, args.config)
 
     # ---- the other BASELINE.json configurations, attached as `configs` (each a full line of its own) ----
@@ -922,6 +931,7 @@ def main():
                     help="N = 1: also time the FP8 linear path of the same configuration (`fp8` key)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
+    ap.add_argument("--vae-only", action="store_true", help="only the VAE decode leg (prints its object as the line)")
     ap.add_argument("--no-sweep", action="store_true", help="VAE: only the 65-frame point")
     ap.add_argument("--no-long", action="store_true", help="N > 1: skip the extra 100-step region")
     ap.add_argument("--parallel", default="cp", choices=["cp", "replicas"],
