@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (torch fp32) of the reference's 2x latent SPATIAL UPSCALER.
 
-Groundwork for SURVEY.md 8(f) rank 3 (stage 2 of the distilled / two-stage pipelines): no CUDA path exists yet.
-Imported only by tests/.  Pinned by tests/golden/upscaler.npz, produced by the reference's own `SpatialUpscaler` (weights
+SURVEY.md 8(f) rank 3 (stage 2 of the distilled / two-stage pipelines): the checker of the CUDA path
+ltx-2-mlx_b200/upscaler.py (tests/test_encoder_upscaler_gpu.py).  Imported only by tests/.  Pinned by tests/golden/upscaler.npz, produced by the reference's own `SpatialUpscaler` (weights
 through its own `load_spatial_upscaler_weights`) over the restated mlx primitives of oracle/_mlx_shim.
 
 Reference map (/root/reference/LTX_2_MLX/model/upscaler/spatial.py):

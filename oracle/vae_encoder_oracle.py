@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (torch fp32) of the reference video-VAE ENCODER.
 
-Groundwork for SURVEY.md 8(f) rank 3 (image conditioning / stage 2 need the encoder): no CUDA path exists yet; this
-oracle and its golden vectors are what that path will be built against.  Imported only by tests/.  Pinned by
+SURVEY.md 8(f) rank 3 (image conditioning / stage 2 need the encoder): the checker of the CUDA path
+ltx-2-mlx_b200/video_vae_encoder.py (tests/test_encoder_upscaler_gpu.py).  Imported only by tests/.  Pinned by
 tests/golden/vae_encoder.npz, produced by the reference's own `SimpleVideoEncoder` (weights through its own
 `load_vae_encoder_weights`) over the restated mlx primitives of oracle/_mlx_shim (tests/golden/make_golden.py).
 

@@ -1,5 +1,5 @@
-"""Latent spatial upscaler oracle vs a golden vector from the reference's own SpatialUpscaler (SURVEY.md 8(f) rank 3:
-groundwork -- no CUDA path yet; this pins the oracle it will be built against)."""
+"""Latent spatial upscaler oracle vs a golden vector from the reference's own SpatialUpscaler (SURVEY.md 8(f) rank 3;
+pins the oracle the CUDA upscaler path is tested against in tests/test_encoder_upscaler_gpu.py)."""
 import os
 
 import numpy as np

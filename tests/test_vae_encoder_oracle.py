@@ -1,5 +1,5 @@
-"""Video-VAE encoder oracle vs golden vectors from the reference's own SimpleVideoEncoder (SURVEY.md 8(f) rank 3:
-groundwork -- the CUDA path for the encoder is not built yet; this pins the oracle it will be built against)."""
+"""Video-VAE encoder oracle vs golden vectors from the reference's own SimpleVideoEncoder (SURVEY.md 8(f) rank 3;
+pins the oracle the CUDA encoder path is tested against in tests/test_encoder_upscaler_gpu.py)."""
 import os
 
 import numpy as np
