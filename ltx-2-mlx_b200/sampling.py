@@ -97,7 +97,8 @@ def timestep_classes_from_mask(mask: torch.Tensor):
 
 
 def euler_denoising_loop(x0_model, latent, context, positions, sigmas: Sequence[float], *, denoise_mask=None,
-                         clean_latent=None, negative_context=None, cfg_scale: float = 1.0) -> torch.Tensor:
+                         clean_latent=None, negative_context=None, cfg_scale: float = 1.0,
+                         timestep_classes=None) -> torch.Tensor:
     """pipelines/distilled.py:214-253 (video only) with optional CFG (pipelines/one_stage.py:267-326): for every sigma,
     x0 = model(Modality(latent, timesteps = mask * sigma, ...)), then the fused update.  Returns the final latent.
 
@@ -119,7 +120,9 @@ def euler_denoising_loop(x0_model, latent, context, positions, sigmas: Sequence[
         ctx = torch.cat([ctx, to_device(negative_context, dev)], dim=0).contiguous()      # (2B, S, C): cond | uncond
         pos = torch.cat([pos, pos], dim=0).contiguous()
     rep = 2 if cfg else 1
-    classes = timestep_classes_from_mask(mask.repeat(rep, 1)) if use_mask else None
+    classes = None
+    if use_mask:      # pre-computed by a caller that must not synchronise here (GraphedDenoiser captures this loop)
+        classes = timestep_classes if timestep_classes is not None else timestep_classes_from_mask(mask.repeat(rep, 1))
     for i in range(len(sigmas) - 1):
         sigma = float(sigmas[i])
         sig = torch.full((B * rep,), sigma, device=dev)
@@ -157,7 +160,8 @@ class GraphedDenoiser:
 
     def _loop(self):
         return euler_denoising_loop(self.x0_model, self._lat, self._ctx, self._pos, self.sigmas, denoise_mask=self._mask,
-                                    clean_latent=self._clean, negative_context=self._nctx, cfg_scale=self.cfg_scale)
+                                    clean_latent=self._clean, negative_context=self._nctx, cfg_scale=self.cfg_scale,
+                                    timestep_classes=self._classes)
 
     def __call__(self, latent, context, positions, *, denoise_mask=None, clean_latent=None, negative_context=None):
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -168,9 +172,23 @@ class GraphedDenoiser:
                    mask=_f32(denoise_mask, dev) if denoise_mask is not None else None,
                    clean=_f32(clean_latent, dev) if clean_latent is not None else None,
                    nctx=to_device(negative_context, dev) if negative_context is not None else None)
-        key = tuple((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in ins.items())
+        # the (batch, mask value) classes are found OUTSIDE the graph (torch.unique synchronises); the graph sees them as
+        # static buffers, and a different class count means a different graph
+        classes = None
+        if ins["mask"] is not None:
+            rep = 2 if (ins["nctx"] is not None and self.cfg_scale != 1.0) else 1
+            B, T, _ = ins["lat"].shape
+            classes = timestep_classes_from_mask(ins["mask"].reshape(B, T).repeat(rep, 1))
+            if classes is None:
+                raise NotImplementedError("GraphedDenoiser: more than 64 distinct mask values")
+        key = tuple((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in ins.items()) + \
+            (None if classes is None else int(classes[0].numel()),)
+        if self._graph is not None and key == self._key and classes is not None:
+            self._classes[0].copy_(classes[0])
+            self._classes[1].copy_(classes[1])
         if self._graph is None or key != self._key:
             self._key = key
+            self._classes = None if classes is None else (classes[0].clone(), classes[1].clone())
             for k, v in ins.items():
                 setattr(self, "_" + k, None if v is None else v.clone())
             model.reset_context_cache()
