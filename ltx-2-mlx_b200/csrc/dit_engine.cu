@@ -243,6 +243,10 @@ struct LtxDit {
   bool ctx_cache_on = false, ctx_cache_hit = false;   // state of the forward in flight
   int layer_limit = 0;              // diagnostics: run only the first n blocks (0 = all)
   bool coef_dirty = true;           // FP8 mode: a weight changed -> recompute the FFN bound coefficients
+  // audio+video models: the audio stream's self/text attention and FFN (65 tokens: ~30 latency-bound launches per
+  // block) run on a side stream next to the video stream's kernels and join it around the cross-modal attention
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bf16* kvc_kv(int layer, int B, int S) const {
     return reinterpret_cast<bf16*>(kvc) + size_t(layer) * 3 * size_t(B) * S * D;
   }
@@ -752,6 +756,9 @@ void ltx2_dit_destroy(LtxDit* e) {
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
   if (e->kvc) cudaFree(e->kvc);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->scale1) cudaFree(e->scale1);
   if (e->fg_video) cudaFree(e->fg_video);
   if (e->fg_audio) cudaFree(e->fg_audio);
@@ -1377,6 +1384,32 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
   }
 
   const int D = e->D, Da = e->Da, B = sh.B, N = sh.N, Na = sh.Na;
+  // fork / join of the audio side stream (LTX2_AUDIO_SIDE_STREAM=0: everything on the caller's stream)
+  cudaStream_t sa = st;
+  if (has_audio) {
+    const char* env = getenv("LTX2_AUDIO_SIDE_STREAM");
+    if (!(env && env[0] == '0')) {
+      if (e->side == nullptr) {
+        LTX2_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+        LTX2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        LTX2_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+      }
+      sa = e->side;
+    }
+  }
+  auto fork_audio = [&]() -> int {          // the side stream may start once the main stream got here
+    if (sa == st) return LTX2_OK;
+    LTX2_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
+    LTX2_CUDA_CHECK(cudaStreamWaitEvent(sa, e->ev_fork, 0));
+    return LTX2_OK;
+  };
+  auto join_audio = [&]() -> int {          // the main stream continues once the side stream got here
+    if (sa == st) return LTX2_OK;
+    LTX2_CUDA_CHECK(cudaEventRecord(e->ev_join, sa));
+    LTX2_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join, 0));
+    return LTX2_OK;
+  };
+  if (has_audio) LTX2_PROPAGATE(fork_audio());
   for (int l = 0; l < n_layers; ++l) {
     const BlockW& w = e->blocks[l];
     const uint64_t bit = uint64_t(1) << l;
@@ -1388,7 +1421,8 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     LTX2_PROPAGATE(run_self_and_text(e, vb, w.v, l, (sk.video_self_attn & bit) != 0, cas, st));
     if (has_audio) {
       g_split_k = 1;
-      LTX2_PROPAGATE(run_self_and_text(e, ab, w.a, l, (sk.audio_self_attn & bit) != 0, 1.0f, st));
+      LTX2_PROPAGATE(run_self_and_text(e, ab, w.a, l, (sk.audio_self_attn & bit) != 0, 1.0f, sa));
+      LTX2_PROPAGATE(join_audio());            // the cross-modal attentions read and write both residual streams
       const bool do_a2v = (sk.a2v_cross_attn & bit) == 0, do_v2a = (sk.v2a_cross_attn & bit) == 0;
       const float* cmv = vb.ca_mod + size_t(l) * B * 5 * D;     // rows: scale_a2v, shift_a2v, scale_v2a, shift_v2a, gate
       const float* cma = ab.ca_mod + size_t(l) * B * 5 * Da;
@@ -1441,13 +1475,17 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
                                        ab.row_batch, 1.0f, st));
       }
     }
+    if (has_audio) LTX2_PROPAGATE(fork_audio());
     g_split_k = split_v;
     LTX2_PROPAGATE(run_ffn(e, vb, w.v, l, st));
     g_split_k = 1;
-    if (has_audio) LTX2_PROPAGATE(run_ffn(e, ab, w.a, l, st));
+    if (has_audio) LTX2_PROPAGATE(run_ffn(e, ab, w.a, l, sa));
   }
   LTX2_PROPAGATE(run_head(e, vb, e->vw, *video, x0, out_video, st));
-  if (has_audio) LTX2_PROPAGATE(run_head(e, ab, e->aw, *audio, x0, out_audio, st));
+  if (has_audio) {
+    LTX2_PROPAGATE(run_head(e, ab, e->aw, *audio, x0, out_audio, sa));
+    LTX2_PROPAGATE(join_audio());
+  }
   if (e->ctx_cache_on) {
     e->cached_tag = e->ctx_tag;
     e->cached_B = sh.B;

@@ -15,7 +15,11 @@ timeout -s KILL 600 $NCU --set full --import-source on -k regex:gemm_bf16_kernel
 echo "gemm capture rc=$?"
 timeout -s KILL 600 $NCU --set full -k regex:"norm_modulate|qkv_head_scatter|headnorm_rope" -s 6 -c 4 -f -o gpurun_out/prof_rows_${tag} python tools/profile_step.py --layers 3 > gpurun_out/cap_rows.log 2>&1
 echo "row kernels capture rc=$?"
-timeout -s KILL 600 $NCU --set full --import-source on -k regex:conv3d_kernel -s 40 -c 3 -f -o gpurun_out/prof_conv_${tag} python tools/profile_vae.py > gpurun_out/cap_conv.log 2>&1
+timeout -s KILL 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_${tag}_dit_fp8.csv python tools/profile_step.py --fp8 > gpurun_out/cap_dit8.log 2>&1
+echo "dit fp8 launch list rc=$?"
+timeout -s KILL 600 $NCU --set full --import-source on -k regex:gemm_bf16_kernel -s 8 -c 6 -f -o gpurun_out/prof_gemm8_${tag} python tools/profile_step.py --layers 3 --fp8 > gpurun_out/cap_gemm8.log 2>&1
+echo "fp8 gemm capture rc=$?"
+timeout -s KILL 600 $NCU --set full --import-source on -k regex:conv3d -s 36 -c 8 -f -o gpurun_out/prof_conv_${tag} python tools/profile_vae.py > gpurun_out/cap_conv.log 2>&1
 echo "conv capture rc=$?"
 timeout -s KILL 600 $NCU --set full -k regex:norm_act_pad -s 30 -c 2 -f -o gpurun_out/prof_vaerow_${tag} python tools/profile_vae.py > gpurun_out/cap_vaerow.log 2>&1
 echo "vae row capture rc=$?"

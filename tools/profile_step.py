@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None, help="override block count (ncu --set full replays are slow)")
     ap.add_argument("--grid", type=int, nargs=3, default=None, metavar=("F", "H", "W"),
                     help="override the latent grid, e.g. 1 18 24 = the 432 tokens of an 8-way context-parallel shard")
+    ap.add_argument("--fp8", action="store_true", help="the FP8 linear path (LTXModel(fp8_linear=True))")
     args = ap.parse_args()
     c = dict(bench.CONFIGS[args.config])
     if args.layers:
@@ -38,7 +39,8 @@ def main():
     cfg = synthetic.DitConfig(num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], num_layers=c["layers"],
                               cross_attention_dim=D, caption_channels=c["caption"])
     model = LTXModel(model_type=LTXModelType.VideoOnly, num_attention_heads=c["heads"], attention_head_dim=c["head_dim"],
-                     num_layers=c["layers"], cross_attention_dim=D, caption_channels=c["caption"], device=dev)
+                     num_layers=c["layers"], cross_attention_dim=D, caption_channels=c["caption"], device=dev,
+                     fp8_linear=args.fp8)
     model.load_weights(iter_engine_weights(synthetic.iter_dit_weights(cfg, seed=0, device=dev, dtype=torch.bfloat16), False))
     N, S = c["F"] * c["H"] * c["W"], c["S"]
     lat = synthetic.latents((1, N, 128), seed=42).to(dev)

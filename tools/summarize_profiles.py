@@ -80,6 +80,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     md = [f"# ncu launch lists ({tag})\n"]
     for f, title in ((f"launches_{tag}_dit.csv", "one DiT denoising step (19B, N=3456) -- tools/profile_step.py"),
+                     (f"launches_{tag}_dit_fp8.csv", "the same step with the FP8 linear path (fp8_linear) -- tools/profile_step.py --fp8"),
                      (f"launches_{tag}_vae.csv", "one VAE chunk decode (7 latent frames -> 49 frames @ 512x768) -- tools/profile_vae.py")):
         p = os.path.join(SRC, f)
         if os.path.exists(p):
