@@ -57,7 +57,10 @@ def launch_list(path, title):
 
 
 def full_capture(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):         # exported on the GPU box by tools/capture_profiles.sh (`ncu -i ... --page raw --csv`)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
@@ -90,7 +93,7 @@ def main():
     open(os.path.join(OUT, f"{tag}_launches.md"), "w").write("\n".join(md))
     caps = {}
     for f in sorted(os.listdir(SRC)):
-        if f.endswith(f"_{tag}.ncu-rep"):
+        if f.startswith("prof_") and (f.endswith(f"_{tag}.ncu-rep") or f.endswith(f"_{tag}.csv")):
             caps[f] = full_capture(os.path.join(SRC, f))
     json.dump(caps, open(os.path.join(OUT, f"{tag}_kernels.json"), "w"), indent=1)
     print(open(os.path.join(OUT, f"{tag}_launches.md")).read())
