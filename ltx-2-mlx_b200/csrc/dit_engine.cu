@@ -1104,16 +1104,24 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
       LTX2_PROPAGATE(gate_scatter(sb.gate_logits, peers, B, N, H, Hl, Nt, cp.rank * cp.n_local, st));
       gl = reinterpret_cast<const float*>(cp.region + cp.off_gate);
     }
-    if (cp.ctx_tokens == S && !v2 && !(e->ctx_cache_on && e->ctx_cache_hit)) {
+    if (cp.ctx_tokens == S && !(e->ctx_cache_on && e->ctx_cache_hit)) {
       // text-context K/V for this block: each rank projects S/P context rows and stores the result into EVERY rank's
-      // buffer (GEMM epilogue with peer destinations) instead of all ranks repeating the full projection
+      // buffer (peer-memory broadcast) instead of all ranks repeating the full projection.  V2 models project the
+      // sigma-modulated context (transformer.py:449-452), which is formed here, before the projection.
       const int Sl = S / cp.world;
       const AttnW& cw = w.attn2;
+      const bf16* ctx_src = sb.ctx;
+      if (v2) {
+        const float* pm = sb.prompt_mod + size_t(layer) * B * 2 * dim;
+        LTX2_PROPAGATE(norm_modulate(sb.ctx, 1, dim, sb.ctx_mod, dim, B * S, dim, NORM_NONE, c.norm_eps, pm,
+                                     int64_t(2) * dim, 0, dim, sb.ctx_batch, st));
+        ctx_src = sb.ctx_mod;
+      }
       for (int b = 0; b < B; ++b) {
         const size_t row0 = size_t(b) * S + size_t(cp.rank) * Sl;
         const size_t byte0 = cp.off_ckv[layer & 1] + row0 * 2 * cw.inner * sizeof(bf16);
         bf16* mine = reinterpret_cast<bf16*>(cp.region + byte0);
-        LTX2_PROPAGATE(linear_bf16(sb.ctx + row0 * dim, dim, cw.kv, Sl, mine, 2 * cw.inner, false, st));
+        LTX2_PROPAGATE(linear_bf16(ctx_src + row0 * dim, dim, cw.kv, Sl, mine, 2 * cw.inner, false, st));
         void* peers[kMaxCpRanks];
         int np = 0;
         for (int r = 0; r < cp.world; ++r)
@@ -1161,9 +1169,12 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
   if (v2) {
     if (tq8) LTX2_PROPAGATE(rms_mod_q8(e, sb, txn, mod, ms, 6, 7, sb.row_cls, st));
     else LTX2_PROPAGATE(rms_mod(e, sb, sb.xn, mod, ms, 6, 7, sb.row_cls, st));
-    const float* pm = sb.prompt_mod + size_t(layer) * B * 2 * dim;
-    LTX2_PROPAGATE(norm_modulate(sb.ctx, 1, dim, sb.ctx_mod, dim, B * S, dim, NORM_NONE, c.norm_eps, pm,
-                                 int64_t(2) * dim, 0, dim, sb.ctx_batch, st));
+    const bool kv_from_peers = e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !skip_self;
+    if (!kv_from_peers) {       // (context-parallel ranks already formed and projected their share of it above)
+      const float* pm = sb.prompt_mod + size_t(layer) * B * 2 * dim;
+      LTX2_PROPAGATE(norm_modulate(sb.ctx, 1, dim, sb.ctx_mod, dim, B * S, dim, NORM_NONE, c.norm_eps, pm,
+                                   int64_t(2) * dim, 0, dim, sb.ctx_batch, st));
+    }
     ctx = sb.ctx_mod;
   } else {
     if (tq8) LTX2_PROPAGATE(rms_mod_q8(e, sb, txn, nullptr, 0, 0, 0, nullptr, st));
@@ -1174,7 +1185,7 @@ int run_self_and_text(LtxDit* e, StreamBuf& sb, const BlockStreamW& w, int layer
     a.xq8 = sb.xq;
     a.xq8_scale = sb.xs;
   }
-  const bool region_kv = e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !v2 && !skip_self;
+  const bool region_kv = e->cp.world > 1 && &sb == &e->vb && e->cp.ctx_tokens == S && !skip_self;
   if (&sb == &e->vb && e->ctx_cache_on) {
     // V1: the context K/V of this block do not depend on sigma -- computed by the first forward of a sample, reused after
     bf16* kvl = e->kvc_kv(layer, B, S);

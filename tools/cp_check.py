@@ -33,7 +33,7 @@ def av_cases(rank, world, dev):
               out_channels=32, num_layers=3, cross_attention_dim=heads * 128, caption_channels=None,
               cross_attention_adaln=True, apply_gated_attention=True, av_ca_timestep_scale_multiplier=1000, device=dev)
     ok = True
-    for (B, F, H, W, S, Na, per_token), split_k in [(c, k) for c in [(2, 2, 4, 8, 40, 9, False), (1, 4, 8, 8, 24, 17, True)]
+    for (B, F, H, W, S, Na, per_token), split_k in [(c, k) for c in [(2, 2, 4, 8, 64, 9, False), (1, 4, 8, 8, 24, 17, True)]
                                                     for k in (1, 0)]:
         N = F * H * W
         if split_k:
@@ -44,7 +44,8 @@ def av_cases(rank, world, dev):
         load_transformer_state_dict(single, w)
         load_transformer_state_dict(sharded, w)
         assert sharded.missing_weights() == []
-        context_parallel.enable(sharded, batch=B, n_total=N)
+        # S = 64 also exercises the sharded projection of the sigma-modulated text K/V (V2)
+        context_parallel.enable(sharded, batch=B, n_total=N, context_tokens=S if S % (8 * world) == 0 else 0)
         lat = synthetic.latents((B, N, 32), seed=310)
         ctx = synthetic.latents((B, S, heads * 128), seed=311, std=0.5)
         pos = synthetic.video_positions(B, F, H, W)
