@@ -435,20 +435,27 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
 //   warp 1, CTA 0       MMA issuer: waits full + peer_full, commits multicast to `empty` / `acc_full` of both CTAs
 //   warps 2-5           epilogue of the CTA's own 128 positions; `acc_empty` lives in CTA 0, counts all 8 epilogue warps
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN>
+// KH3: one pipeline stage carries the THREE kernel rows kh = 0, 1, 2 of a (kt, kw, channel chunk): the activation box is
+// 18 rows high instead of 16 (18 KB instead of 3 x 16 KB), and tap kh reads it at row offset kh -- 8 positions x 128 B =
+// 1024 B, exactly one swizzle atom, so the shifted operand needs nothing but a start address.  The implicit GEMM
+// otherwise re-reads every activation 27 times from L2 (9.9 TB/s on the 128-channel stage: the measured bound behind
+// the 66 % tensor-pipe activity, profiles/r2_kernels.json); this cuts the L2 -> SM activation traffic by 2.67x.
+template <int BN, bool KH3 = true>
 struct ConvPairCfg {
-  static constexpr int kStages = 6;
-  static constexpr int kABytes = CBM * CBK * 2;
-  static constexpr int kBBytes = (BN / 2) * CBK * 2;
+  static constexpr int kTaps = KH3 ? 3 : 1;
+  static constexpr int kABytes = KH3 ? (CTH + 2) * CTW * CBK * 2 : CBM * CBK * 2;     // 18 KB / 16 KB
+  static constexpr int kBTap = (BN / 2) * CBK * 2;                                      // one tap's weight half
+  static constexpr int kBBytes = kTaps * kBTap;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = KH3 ? (BN >= 256 ? 3 : 5) : 6;
   static constexpr int kTmemCols = 2 * BN;                  // 256 or 512
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512 + 3 * BN * 4;
 };
 
-template <int BN>
+template <int BN, bool KH3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, ConvParams p) {
-  using Cfg = ConvPairCfg<BN>;
+  using Cfg = ConvPairCfg<BN, KH3>;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -472,7 +479,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const int num_m = p.B * p.T * tiles_h * tiles_w;
   const int num_pairs = (num_m + 1) / 2;              // pair pt = position tiles 2 pt (CTA 0) and 2 pt + 1 (CTA 1)
   const int cchunks = p.Cin / CBK;
-  const int num_kb = 27 * cchunks;
+  const int num_kb = (KH3 ? 9 : 27) * cchunks;        // KH3: a K block = (kt, kw, channel chunk) with all three kh
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -512,14 +519,26 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const int plane0 = b * (p.T + 2) + t;
       int tap = 0, cc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw, hy * CTH + kh,
-                      plane0 + kt);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * CBK,
-                      static_cast<int>(rank) * (BN / 2));
+          if (KH3) {
+            // tap = kt*3 + kw; the 18-row box covers kh = 0..2; the weights of the three taps (kt, kh, kw) sit 3*C_in
+            // apart in the packed [C_out, 27*C_in] matrix
+            const int kt = tap / 3, kw = tap % 3;
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw, hy * CTH,
+                        plane0 + kt);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_2d(smem_b + stage * Cfg::kBBytes + kh * Cfg::kBTap, &tmap_w, &full_bar[stage],
+                          ((kt * 3 + kh) * 3 + kw) * p.Cin + cc * CBK, static_cast<int>(rank) * (BN / 2));
+          } else {
+            const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_x, &full_bar[stage], cc * CBK, wx * CTW + kw, hy * CTH + kh,
+                        plane0 + kt);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage], kb * CBK,
+                        static_cast<int>(rank) * (BN / 2));
+          }
         }
         if (++cc == cchunks) { cc = 0; ++tap; }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -558,7 +577,12 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < CBK / 16; ++k) umma2_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int kh = 0; kh < Cfg::kTaps; ++kh)
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k)
+              // tap kh: activation rows shifted by kh * 8 positions (one 1024-byte swizzle atom), its own weight tile
+              umma2_bf16_ss(d_tmem, adesc + kh * (1024 >> 4) + 2 * k, bdesc + kh * (Cfg::kBTap >> 4) + 2 * k, idesc,
+                            (kb | kh | k) != 0);
           umma2_commit_both(&empty_bar[stage]);
         }
         __syncwarp();
@@ -602,18 +626,19 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int BN>
+template <int BN, bool KH3>
 int launch_conv_pair(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvPairCfg<BN>;
+  using Cfg = ConvPairCfg<BN, KH3>;
   static PerDeviceOnce configured;
   if (configured.first()) {
-    LTX2_CUDA_CHECK(cudaFuncSetAttribute(conv3d_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(conv3d_pair_kernel<BN, KH3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
   }
   const int num_m = p.B * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW);
   const int pairs = (num_m + 1) / 2, clusters = num_sms() / 2;
   const int grid = 2 * (pairs < clusters ? pairs : clusters);
-  LTX2_CUDA_CHECK(launch_pdl(conv3d_pair_kernel<BN>, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, stream, tx, tw, p));
+  LTX2_CUDA_CHECK(launch_pdl(conv3d_pair_kernel<BN, KH3>, dim3(grid), dim3(kConvThreads), Cfg::kSmemBytes, stream, tx, tw,
+                             p));
   count_launch();
   return LTX2_OK;
 }
@@ -692,7 +717,20 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
       CUtensorMap twp;
       LTX2_PROPAGATE(get_tensor_map_2d(&twp, w_packed, p.Cout_pad, static_cast<uint64_t>(27) * p.Cin,
                                        static_cast<uint64_t>(27) * p.Cin, bn / 2));
-      return bn == 128 ? launch_conv_pair<128>(tx, twp, p, stream) : launch_conv_pair<256>(tx, twp, p, stream);
+      // LTX2_CONV_KH3=0: one tap per pipeline stage (the round-2a kernel) for A/B runs
+      const char* e3 = getenv("LTX2_CONV_KH3");
+      if (e3 && e3[0] == '0')
+        return bn == 128 ? launch_conv_pair<128, false>(tx, twp, p, stream) : launch_conv_pair<256, false>(tx, twp, p, stream);
+      CUtensorMap tx18;     // the same padded input with an 18-row box: kh = 0..2 of a tile in one load
+      {
+        uint64_t dims[4] = {static_cast<uint64_t>(p.Cin), static_cast<uint64_t>(p.W + 2), static_cast<uint64_t>(p.H + 2),
+                            static_cast<uint64_t>(p.B) * (p.T + 2)};
+        uint64_t str[3] = {static_cast<uint64_t>(p.Cin) * 2, static_cast<uint64_t>(p.W + 2) * p.Cin * 2,
+                           static_cast<uint64_t>(p.H + 2) * (p.W + 2) * p.Cin * 2};
+        uint32_t box[4] = {CBK, CTW, CTH + 2, 1};
+        LTX2_PROPAGATE(make_tensor_map_bf16(&tx18, x_padded, 4, dims, str, box));
+      }
+      return bn == 128 ? launch_conv_pair<128, true>(tx18, twp, p, stream) : launch_conv_pair<256, true>(tx18, twp, p, stream);
     }
   }
   CUtensorMap tw_map;

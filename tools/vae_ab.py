@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the VAE decode variants on one GPU: fused conv producer (LTX2_VAE_FUSE) x SM-pair conv kernel
-(LTX2_CONV_PAIR), same decoder, same latent.  Prints frames/s of decode_latent (65 frames @ 512x768), the conv class
+(LTX2_CONV_PAIR) x three kernel rows per pipeline stage (LTX2_CONV_KH3), same decoder, same latent.  Prints frames/s of decode_latent (65 frames @ 512x768), the conv class
 time of one profiled 7-frame chunk, and the relative difference of each variant's video to the unfused 1-CTA one."""
 import ctypes as C
 import itertools
@@ -22,8 +22,10 @@ def main():
     lat = synthetic.latents((1, 128, 9, 16, 24), seed=43).to(dev)
     L = _lib.lib()
     base = None
-    for fuse, pair in itertools.product(("0", "1"), ("0", "1", "2")):
-        os.environ["LTX2_VAE_FUSE"], os.environ["LTX2_CONV_PAIR"] = fuse, pair
+    combos = [("0", "0", "0"), ("0", "2", "0"), ("1", "0", "0"), ("1", "2", "0"), ("1", "2", "1"), ("0", "2", "1"),
+              ("1", "2", "0"), ("1", "2", "1")]          # (the last two repeat: clocks drift over the run)
+    for fuse, pair, kh3 in combos:
+        os.environ["LTX2_VAE_FUSE"], os.environ["LTX2_CONV_PAIR"], os.environ["LTX2_CONV_KH3"] = fuse, pair, kh3
         dec.decode_noise_scale = 0.0
         vid = dec(lat[:, :, :3].contiguous(), timestep=0.05)
         if base is None:
@@ -53,7 +55,7 @@ def main():
         _lib.check(L.ltx2_vae_set_profile(dec._h, 0))
         if os.environ.get("VAE_AB_DETAIL"):
             print("   per launch ms (TF/s): " + " ".join(f"{a * 1e3:.0f}us({b / a / 1e9:.0f})" for a, b in per))
-        print(f"fuse={fuse} pair={pair}: {65e3 / ms:7.1f} frames/s ({ms:.2f} ms)  conv class {pm.value:.2f} ms "
+        print(f"fuse={fuse} pair={pair} kh3={kh3}: {65e3 / ms:7.1f} frames/s ({ms:.2f} ms)  conv class {pm.value:.2f} ms "
               f"({pf.value / pm.value / 1e9:.0f} TF/s, {pl.value} launches)  rel diff to unfused/1-CTA {diff:.2e}", flush=True)
 
 
