@@ -688,8 +688,9 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
   if (p.Cout_pad % 64 != 0) bn = 32;
   if (p.pad_out == nullptr && bn > 64) {
     // Few position tiles (the 1024- / 512-channel stages of a temporal shard: 3-24 tiles): a tile's K loop is serial, so
-    // narrower weight tiles put more SMs on the conv.  Cost model in MMA clocks per K step (measured, tools/probe:
-    // N 256 -> 128, N 128 -> 64, N 64 -> 48 shared-memory bound), times the number of waves.
+    // narrower weight tiles put more SMs on the conv.  Cost model in clocks per K step of the 1-CTA kernel as MEASURED
+    // on whole convs (N 256 -> 128; N 128 -> 86 and N 64 -> 56: shared-memory / L2 bound, profiles/r2_vae_ab_kh3.txt),
+    // times the number of waves -- a conv with many tiles keeps the 256-wide tile.
     const long m_tiles = static_cast<long>(p.B) * p.T * ((p.H + CTH - 1) / CTH) * ((p.W + CTW - 1) / CTW);
     const int nsm = num_sms();
     long best = -1;
@@ -697,7 +698,7 @@ int conv3d_bf16(const void* x_padded, const void* w_packed, const ConvParams& p,
     for (int cand = bn; cand >= 64; cand >>= 1) {
       if (p.Cout_pad % cand != 0) continue;
       const long tiles = m_tiles * (p.Cout_pad / cand);
-      const long cost = ((tiles + nsm - 1) / nsm) * (cand == 256 ? 128 : cand == 128 ? 64 : 48);
+      const long cost = ((tiles + nsm - 1) / nsm) * (cand == 256 ? 128 : cand == 128 ? 86 : 56);
       if (best < 0 || cost < best) { best = cost; best_bn = cand; }
     }
     bn = best_bn;
