@@ -336,6 +336,26 @@ def bench_vae(args, dev, rank, world=1):
                                 f"single-GPU decode of the same latent on every rank, noise off"}
         del ref, got
 
+        def time_chunk(t_lat):
+            from ltx2_b200.video_vae import decode_sharded
+            cl = synthetic.latents((1, 128, t_lat, 16, 24), seed=46).to(dev)
+            for _ in range(2):
+                decode_sharded(dec, cl, 0.05, dst=0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(6):
+                decode_sharded(dec, cl, 0.05, dst=0)
+            b.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([a.elapsed_time(b) / 6], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0])
+
+        shard_parity["chunk_ms"] = {"7_latent_frames": time_chunk(7), "4_latent_frames": time_chunk(4),
+                                    "note": "one sharded SimpleVideoDecoder call incl. assembling the clip on rank 0"}
+
     def sync():
         if world > 1:
             dist.barrier()

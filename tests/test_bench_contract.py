@@ -7,7 +7,8 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r1c_*.json")))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "bench_r1c_*.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "bench_r2_n*.json")))
 
 
 @pytest.mark.parametrize("path", LINES, ids=[os.path.basename(p) for p in LINES])
@@ -28,6 +29,24 @@ def test_committed_bench_line_has_the_contract_keys(path):
     if d["n_gpus"] == 1 and "cpu_baseline" in d:
         c = d["cpu_baseline"]
         assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    if "bench_r2_" in path:
+        # round 2: the line proves what it timed -- the benched model against the oracle, the sharded forward against
+        # the un-sharded one, the hoisted fractions
+        p = d["parity"]
+        assert p["ok"] and p["rel_l2"] < p["tolerance"]["rel_l2"] and p["pearson"] > p["tolerance"]["pearson"]
+        for k in ("gemm_frac", "attention_frac", "step_frac"):
+            assert 0 < d[k] < 1.0, k
+        assert d["flops_per_step"]["executed"] <= d["flops_per_step"]["as_reference"]
+        if d["n_gpus"] > 1:
+            assert d["cp_parity"]["ok"] and d["cp_parity"]["bit_exact_pinned_kernels"] is True
+        if "vae" in d:
+            assert d["vae_frames_per_s"] == d["vae"]["value"]
+            if d["n_gpus"] > 1:
+                assert d["vae"]["shard_parity"]["bit_exact"] is True
+            else:
+                assert d["vae"]["parity"]["ok"]
+        if "fp8" in d:
+            assert d["fp8"]["parity"]["ok"] and d["fp8"]["value"] > d["value"] and "fp8" in d["fp8"]["dtype"]
 
 
 def test_there_are_committed_bench_lines():
