@@ -238,17 +238,22 @@ int ltx2_vae_decode(LtxVae* vae, const void* latent, int32_t dtype, const int64_
  * ltx2_vae_decode.  Non-causal decode only.
  *   1. every rank: ltx2_vae_cp_init(rank, world, largest latent shape) -> 64-byte CUDA IPC handle;
  *   2. the host layer all-gathers the handles, calls ltx2_vae_cp_connect on every rank, then a host barrier;
- *   3. ltx2_vae_decode_sharded, collectively, with the SAME latent on every rank: conv_out's epilogue writes each rank's
- *      frames at their place in the clip, the spans are stored into the copy of rank `dst` (or of every rank, dst = -1)
- *      over NVLink, and `out` [B,3,T',32H,32W] fp32 receives the assembled clip there (may be NULL elsewhere);
- *      ltx2_vae_shard_frames tells which output frames a rank computes;
- *   4. teardown: ltx2_vae_cp_shutdown(0) on every rank, host barrier, ltx2_vae_cp_shutdown(1). */
+ *   3. ltx2_vae_decode_sharded, collectively on the ranks of a GROUP [group_first, group_first + group_size) (the whole
+ *      world, or an aligned equal-size part of it: e.g. the two halves of 8 ranks decode two temporal chunks of
+ *      decode_latent at the same time), with the SAME latent on every rank of the group: conv_out's epilogue writes each
+ *      rank's frames at their place in the clip and the spans are stored into clip slot `slot` of rank `dst` (or of every
+ *      rank, dst = -1) over NVLink; ltx2_vae_shard_frames tells which output frames a rank computes;
+ *   4. ltx2_vae_cp_collect, on ALL ranks: a barrier over the whole world, then the receiving ranks copy the assembled
+ *      clip [B,3,T',32H,32W] fp32 of that slot into `out`;
+ *   5. teardown: ltx2_vae_cp_shutdown(0) on every rank, host barrier, ltx2_vae_cp_shutdown(1). */
 int ltx2_vae_cp_init(LtxVae* vae, int32_t rank, int32_t world, const int64_t max_latent_shape[5], char* handle_out);
 int ltx2_vae_cp_connect(LtxVae* vae, const char* handles);
 int ltx2_vae_cp_shutdown(LtxVae* vae, int32_t phase);
 int ltx2_vae_shard_frames(LtxVae* vae, int64_t latent_frames, int32_t rank, int32_t world, int64_t* t0, int64_t* tn);
 int ltx2_vae_decode_sharded(LtxVae* vae, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
-                            float noise_scale, const float* noise, int32_t dst, float* out, void* stream);
+                            float noise_scale, const float* noise, int32_t group_first, int32_t group_size, int32_t slot,
+                            int32_t dst, void* stream);
+int ltx2_vae_cp_collect(LtxVae* vae, int32_t slot, const int64_t clip_shape[5], int32_t dst, float* out, void* stream);
 
 /* Conv3dSimple.__call__ (simple_decoder.py:90-180) as one op, for unit parity of the implicit-GEMM conv kernel at
  * production shapes: x [B,T,H,W,Cin] bf16 channels-last, weight in PyTorch layout [Cout,Cin,3,3,3] and bias [Cout]

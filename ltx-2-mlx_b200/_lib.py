@@ -94,7 +94,8 @@ SIGNATURES = {
     "ltx2_vae_cp_connect": (_I32, [_P, _P]),
     "ltx2_vae_cp_shutdown": (_I32, [_P, _I32]),
     "ltx2_vae_shard_frames": (_I32, [_P, _I64, _I32, _I32, _P, _P]),
-    "ltx2_vae_decode_sharded": (_I32, [_P, _P, _I32, _P, _F, _F, _P, _I32, _P, _P]),
+    "ltx2_vae_decode_sharded": (_I32, [_P, _P, _I32, _P, _F, _F, _P, _I32, _I32, _I32, _I32, _P]),
+    "ltx2_vae_cp_collect": (_I32, [_P, _I32, _P, _I32, _P, _P]),
     "ltx2_conv3d_workspace_bytes": (_I64, [_I32] * 6),
     "ltx2_conv3d": (_I32, [_P, _P, _I32, _P, _I32, _P] + [_I32] * 7 + [_P, _P]),
     "ltx2_pad_act": (_I32, [_P, _P, _P] + [_I32] * 9 + [_P, _P, _P, _I32, _F, _P, _P]),

@@ -126,6 +126,9 @@ int peer_broadcast(const void* src, void* const* dst_peers, int n_peers, int64_t
 // cross-GPU barrier on flag words in peer memory: signal epoch to every rank's flags[rank], wait for all of mine
 int cp_barrier(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int world, uint32_t epoch,
                cudaStream_t stream);
+// barrier among the ranks [first, first + count) only; slot0 = first flag word of the barrier domain (8 words each)
+int cp_barrier_group(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int first, int count, int slot0,
+                     uint32_t epoch, cudaStream_t stream);
 int attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int Tq, int Tk, int Tkp,
                    int Dh, float scale, const float* gate_logits, float* lse_out, cudaStream_t stream,
                    long long* trace = nullptr);

@@ -332,6 +332,28 @@ __global__ void cp_barrier_kernel(uint32_t* const* __restrict__ peer_flags, uint
   }
 }
 
+// the same among the ranks [first, first + count) of a larger world; `slot0` = first flag word of this barrier domain
+// (every group size has its own words and epoch, so groups of different sizes never see each other's counts)
+__global__ void cp_barrier_group_kernel(uint32_t* const* __restrict__ peer_flags, uint32_t* my_flags, int rank, int first,
+                                        int count, int slot0, uint32_t epoch) {
+  const int i = threadIdx.x;
+  if (i < count) {
+    const int peer = first + i;
+    __threadfence_system();
+    volatile uint32_t* f = peer_flags[peer] + slot0 + rank;
+    *f = epoch;
+    volatile uint32_t* m = my_flags + slot0 + peer;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(*m - epoch) < 0) {
+      if (clock64() - t0 > 40000000000LL) {
+        printf("ltx2: group barrier timeout (rank %d waiting for rank %d, epoch %u, have %u)\n", rank, peer, epoch, *m);
+        __trap();
+      }
+    }
+    __threadfence_system();
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // v_transpose: [B*T, inner] -> [B,H,Dh,Tp], 64x64 tiles through shared memory
 // ---------------------------------------------------------------------------------
@@ -600,6 +622,14 @@ int gate_scatter(const float* logits, float* const* dst_peers, int B, int n_loca
 int cp_barrier(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int world, uint32_t epoch,
                cudaStream_t stream) {
   cp_barrier_kernel<<<1, 32, 0, stream>>>(peer_flags_dev, my_flags, rank, world, epoch);
+  LTX2_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return LTX2_OK;
+}
+
+int cp_barrier_group(uint32_t* const* peer_flags_dev, uint32_t* my_flags, int rank, int first, int count, int slot0,
+                     uint32_t epoch, cudaStream_t stream) {
+  cp_barrier_group_kernel<<<1, 32, 0, stream>>>(peer_flags_dev, my_flags, rank, first, count, slot0, epoch);
   LTX2_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return LTX2_OK;

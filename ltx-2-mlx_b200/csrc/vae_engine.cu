@@ -92,9 +92,12 @@ struct VaeCp {
   char* peer_base[kMaxVaeRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool opened[kMaxVaeRanks] = {false, false, false, false, false, false, false, false};
   uint32_t** peer_flags_dev = nullptr;
-  uint32_t epoch = 0;
+  uint32_t epoch[4] = {0, 0, 0, 0};       // one barrier domain per group size: world, world/2, world/4, world/8
   bool connected = false;
 };
+constexpr int kVaeClipSlots = 4;           // clips in flight: two concurrent rank groups x two alternating rounds (a group
+                                           // outside the receiver's group has no barrier with it inside a decode, so a
+                                           // slot is only reused after one full-world collect in between)
 
 struct LtxVae {
   VaeCp cp;
@@ -376,7 +379,7 @@ void split_frames(int T, int world, int r, int* a, int* b) {
 // rank's own output frames and *out_t0 / *out_tn their position in the clip.
 int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream, bool sharded,
-                    int dst) {
+                    int dst, int grp_first = 0, int grp_size = 0, int slot = 0) {
   LTX2_REQUIRE(e && latent && shape && (out || sharded), "vae_decode: null argument");
   const int B = (int)shape[0], Cl = (int)shape[1];
   LTX2_REQUIRE(Cl == e->cfg.latent_channels, "vae_decode: latent has %d channels, decoder expects %d", Cl,
@@ -396,10 +399,18 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VaeCp& cp = e->cp;
   int out_T_total = 0, out_T0 = 0;          // set for the sharded conv_out
-  const int world = sharded ? cp.world : 1, rank = sharded ? cp.rank : 0;
+  // the shard world is the rank GROUP [grp_first, grp_first + grp_size) of the connected ranks (the whole world by
+  // default); `rank` is this rank's index inside it
+  if (sharded && grp_size <= 0) { grp_first = 0; grp_size = cp.world; }
+  const int world = sharded ? grp_size : 1, rank = sharded ? cp.rank - grp_first : 0;
+  int dom = 0;                                       // barrier domain: log2(world / group size)
   if (sharded) {
     LTX2_REQUIRE(cp.connected && cp.world > 1, "vae_decode_sharded: ltx2_vae_cp_connect has not been called");
     LTX2_REQUIRE(!causal, "vae_decode_sharded: causal decoding is not sharded (its halo is two frames on one side)");
+    LTX2_REQUIRE(grp_size >= 1 && cp.world % grp_size == 0 && grp_first % grp_size == 0 && rank >= 0 && rank < grp_size,
+                 "vae_decode_sharded: rank %d is not in the group [%d, %d)", cp.rank, grp_first, grp_first + grp_size);
+    for (int g = cp.world / grp_size; g > 1; g >>= 1) ++dom;
+    LTX2_REQUIRE(dom < 4 && slot >= 0 && slot < kVaeClipSlots, "vae_decode_sharded: bad group size or clip slot");
   }
   // frame ranges [ra[r], rb[r]) of every rank at the current stage; Tt = frames of the whole clip at that stage
   int ra[kMaxVaeRanks], rb[kMaxVaeRanks];
@@ -471,12 +482,13 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
     if (!sharded) return LTX2_OK;
     if (n_of(rank) > 0) {
       const int64_t frame_bytes = int64_t(dd.H + 2) * (dd.W + 2) * dd.C * 2;
-      void* prev = has_prev() ? cp.peer_base[rank - 1] + cp.off_xp[buf] : nullptr;
-      void* next = has_next() ? cp.peer_base[rank + 1] + cp.off_xp[buf] : nullptr;
+      void* prev = has_prev() ? cp.peer_base[cp.rank - 1] + cp.off_xp[buf] : nullptr;
+      void* next = has_next() ? cp.peer_base[cp.rank + 1] + cp.off_xp[buf] : nullptr;
       LTX2_PROPAGATE(halo_push(xps[buf], prev, next, B, n_of(rank), n_of(rank - 1), n_of(rank + 1), frame_bytes, st));
     }
-    return cp_barrier(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, cp.world,
-                      ++cp.epoch, st);
+    if (grp_size == 1) return LTX2_OK;               // a group of one rank: nothing to wait for
+    return cp_barrier_group(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, grp_first,
+                            grp_size, dom * 8, ++cp.epoch[dom], st);
   };
   const bool idle = sharded && n_of(rank) == 0;      // more ranks than latent frames: only keeps the barriers in step
 
@@ -644,22 +656,23 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
   // final norm + scale/shift + SiLU (unless the last conv already produced it), conv_out, unpatchify (:528-552)
   if (!xp_ready) LTX2_PROPAGATE(pad_pass(cur, d, Cf, 1, mod_final, int64_t(2) * Cf, 0, Cf));
   if (!sharded) return conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, out, nullptr);
-  // Temporal shards: conv_out writes this rank's frames at their place in ITS copy of the clip (exchange region), the
-  // spans are then stored into the receiving ranks' copies over NVLink, and after one more barrier every receiver copies
-  // the assembled clip out of the region -- no collective library call anywhere in the decode.
+  // Temporal shards: conv_out writes this rank's frames at their place in ITS copy of the clip (exchange region, clip
+  // slot `slot`), and the spans are then stored into the receiving ranks' copies over NVLink.  ltx2_vae_cp_collect (a
+  // barrier over ALL ranks, then a copy out of the region) completes the clip -- no collective library call anywhere.
   const int64_t HW = int64_t(d.H) * 4 * d.W * 4;
   const size_t clip_bytes = size_t(B) * 3 * Tt * HW * 4;
   LTX2_REQUIRE(clip_bytes <= cp.out_bytes, "vae_decode_sharded: clip of %zu bytes exceeds the exchange buffer (%zu)",
                clip_bytes, cp.out_bytes);
-  float* my_clip = reinterpret_cast<float*>(cp.region + cp.off_out);
+  const size_t clip_off = cp.off_out + size_t(slot) * cp.out_bytes;
+  float* my_clip = reinterpret_cast<float*>(cp.region + clip_off);
   out_T_total = Tt;
   out_T0 = idle ? 0 : ra[rank];
   LTX2_PROPAGATE(conv(e->conv_out, wbuf(), true, d, CONV_EPI_UNPATCHIFY, nullptr, nullptr, my_clip, nullptr));
   if (!idle) {
     void* peers[kMaxVaeRanks];
     int np = 0;
-    for (int r = 0; r < world; ++r)
-      if (r != rank && (dst < 0 || r == dst)) peers[np++] = cp.peer_base[r] + cp.off_out;
+    for (int r = 0; r < cp.world; ++r)
+      if (r != cp.rank && (dst < 0 || r == dst)) peers[np++] = cp.peer_base[r] + clip_off;
     if (np > 0)
       for (int bc = 0; bc < B * 3; ++bc) {
         const size_t off = (size_t(bc) * Tt + ra[rank]) * HW * 4;
@@ -668,12 +681,7 @@ int vae_decode_impl(LtxVae* e, const void* latent, int32_t dtype, const int64_t 
         LTX2_PROPAGATE(peer_broadcast(reinterpret_cast<char*>(my_clip) + off, pp, np, int64_t(n_of(rank)) * HW * 4, st));
       }
   }
-  LTX2_PROPAGATE(cp_barrier(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, cp.world,
-                            ++cp.epoch, st));
-  if (dst < 0 || dst == rank) {
-    LTX2_REQUIRE(out != nullptr, "vae_decode_sharded: the receiving rank needs an output buffer");
-    LTX2_CUDA_CHECK(cudaMemcpyAsync(out, my_clip, clip_bytes, cudaMemcpyDeviceToDevice, st));
-  }
+  (void)out;
   return LTX2_OK;
 }
 
@@ -683,6 +691,7 @@ extern "C" {
 
 int ltx2_vae_decode(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
                     float noise_scale, const float* noise, int32_t causal, float* out, void* stream) {
+  LTX2_REQUIRE(out != nullptr, "vae_decode: null output");
   return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, causal, out, stream, false, 0);
 }
 
@@ -714,9 +723,11 @@ int ltx2_vae_cp_init(LtxVae* e, int32_t rank, int32_t world, const int64_t max_l
   // largest padded conv input of ANY rank for this latent shape (the region layout must be the same on every rank)
   const int B = (int)max_latent_shape[0], T = (int)max_latent_shape[2];
   size_t max_pad = 0;
-  for (int r = 0; r < world; ++r) {
+  // ... for every group size a decode may run with (the world, its halves, ..., one rank)
+  for (int gs = world; gs >= 1; gs >>= 1)
+  for (int r = 0; r < gs; ++r) {
     int a, b;
-    split_frames(T, world, r, &a, &b);
+    split_frames(T, gs, r, &a, &b);
     int H = (int)max_latent_shape[3], W = (int)max_latent_shape[4], C = std::max(e->conv_in.Cout, e->cfg.latent_channels);
     max_pad = std::max(max_pad, size_t(B) * (b - a + 2) * (H + 2) * (W + 2) * C);
     for (auto& s : e->stages)
@@ -733,7 +744,8 @@ int ltx2_vae_cp_init(LtxVae* e, int32_t rank, int32_t world, const int64_t max_l
     ltx2_vae_output_shape(e, max_latent_shape, os);
     cp.out_bytes = align256(size_t(os[0]) * os[1] * os[2] * os[3] * os[4] * 4);
   }
-  cp.off_xp[0] = 0; cp.off_xp[1] = cp.pad_bytes; cp.off_out = 2 * cp.pad_bytes; cp.off_flags = cp.off_out + cp.out_bytes;
+  cp.off_xp[0] = 0; cp.off_xp[1] = cp.pad_bytes; cp.off_out = 2 * cp.pad_bytes;
+  cp.off_flags = cp.off_out + kVaeClipSlots * cp.out_bytes;
   cp.region_bytes = cp.off_flags + 256;
   LTX2_CUDA_CHECK(cudaMalloc(&cp.region, cp.region_bytes));
   LTX2_CUDA_CHECK(cudaMemset(cp.region, 0, cp.region_bytes));
@@ -763,7 +775,7 @@ int ltx2_vae_cp_connect(LtxVae* e, const char* handles) {
   }
   LTX2_CUDA_CHECK(cudaMalloc(&cp.peer_flags_dev, sizeof(uint32_t*) * kMaxVaeRanks));
   LTX2_CUDA_CHECK(cudaMemcpy(cp.peer_flags_dev, flags.data(), sizeof(uint32_t*) * cp.world, cudaMemcpyHostToDevice));
-  cp.epoch = 0;
+  for (int i = 0; i < 4; ++i) cp.epoch[i] = 0;
   cp.connected = true;
   return LTX2_OK;
 }
@@ -791,9 +803,30 @@ int ltx2_vae_cp_shutdown(LtxVae* e, int32_t phase) {
 }
 
 int ltx2_vae_decode_sharded(LtxVae* e, const void* latent, int32_t dtype, const int64_t shape[5], float timestep,
-                            float noise_scale, const float* noise, int32_t dst, float* out, void* stream) {
+                            float noise_scale, const float* noise, int32_t group_first, int32_t group_size, int32_t slot,
+                            int32_t dst, void* stream) {
   LTX2_REQUIRE(e && dst >= -1 && dst < e->cp.world, "vae_decode_sharded: bad destination rank %d", dst);
-  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, 0, out, stream, true, dst);
+  return vae_decode_impl(e, latent, dtype, shape, timestep, noise_scale, noise, 0, nullptr, stream, true, dst, group_first,
+                         group_size, slot);
+}
+
+// Completes clip slot `slot`: a barrier over ALL connected ranks (every group that stored into the slot has finished),
+// then the receiving ranks (dst, or all with dst = -1) copy the clip [B,3,T',32H,32W] fp32 out of the exchange region.
+int ltx2_vae_cp_collect(LtxVae* e, int32_t slot, const int64_t clip_shape[5], int32_t dst, float* out, void* stream) {
+  LTX2_REQUIRE(e && clip_shape && e->cp.connected && slot >= 0 && slot < kVaeClipSlots && dst >= -1 && dst < e->cp.world,
+               "vae_cp_collect: bad argument");
+  VaeCp& cp = e->cp;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LTX2_PROPAGATE(cp_barrier_group(cp.peer_flags_dev, reinterpret_cast<uint32_t*>(cp.region + cp.off_flags), cp.rank, 0,
+                                  cp.world, 0, ++cp.epoch[0], st));
+  if (dst < 0 || dst == cp.rank) {
+    LTX2_REQUIRE(out != nullptr, "vae_cp_collect: the receiving rank needs an output buffer");
+    const size_t bytes = size_t(clip_shape[0]) * clip_shape[1] * clip_shape[2] * clip_shape[3] * clip_shape[4] * 4;
+    LTX2_REQUIRE(bytes <= cp.out_bytes, "vae_cp_collect: clip larger than the exchange buffer");
+    LTX2_CUDA_CHECK(cudaMemcpyAsync(out, cp.region + cp.off_out + size_t(slot) * cp.out_bytes, bytes,
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+  return LTX2_OK;
 }
 
 // Conv3dSimple.__call__ (simple_decoder.py:90-180) as ONE op, for unit parity of the conv kernel at production shapes:

@@ -184,31 +184,48 @@ def disable_temporal_shards(decoder: SimpleVideoDecoder) -> None:
     decoder._shards = None
 
 
-def decode_sharded(decoder: SimpleVideoDecoder, latent, timestep: Optional[float] = 0.05,
-                   dst: Optional[int] = None) -> Optional[torch.Tensor]:
-    """SimpleVideoDecoder.__call__ over the ranks enabled by enable_temporal_shards(): every rank passes the same
-    latent, computes its frame range, and stores it into the clip on rank `dst` (others return None) or on every rank
-    (dst=None) through peer memory -- no torch.distributed call on the data path.  Bit-identical to the single-GPU decode (noise injection off or the same noise on every rank)."""
-    import torch.distributed as dist
+def decode_sharded(decoder: SimpleVideoDecoder, latent, timestep: Optional[float] = 0.05, dst: Optional[int] = None,
+                   group_ranks: Optional[Tuple[int, int]] = None, slot: int = 0,
+                   collect: bool = True) -> Optional[torch.Tensor]:
+    """SimpleVideoDecoder.__call__ over the ranks enabled by enable_temporal_shards(): every rank of the rank group
+    `group_ranks` = (first, size) (default: all ranks) passes the same latent, computes its frame range and stores it into
+    clip slot `slot` on rank `dst` (or on every rank, dst=None) through peer memory -- no torch.distributed call on the
+    data path.  collect=True finishes with collect_clip() (a barrier over ALL ranks: every rank must get there); with
+    collect=False the caller does that itself, e.g. after two groups have decoded two chunks side by side.
+    Bit-identical to the single-GPU decode (noise injection off, or the same noise on every rank)."""
     rank, world, group = decoder._shards
+    first, size = group_ranks if group_ranks is not None else (0, world)
     with torch.cuda.device(decoder.device):
         x = to_device(latent, decoder.device)
         if x.ndim != 5:
             raise ValueError(f"latent must be (B, C, T, H, W); got {tuple(x.shape)}")
-        B, _, T, H, W = decoder.output_shape(x.shape)
         noise = None
         s = float(decoder.decode_noise_scale)
         if decoder.timestep_conditioning and timestep is not None and s != 0.0:
             # every rank must blend the SAME noise into the latent (each also builds its neighbours' boundary frames of
             # the first conv input): enable_temporal_shards() seeded one generator identically on all ranks
             noise = torch.randn(x.shape, device=decoder.device, dtype=torch.float32, generator=decoder._shard_noise)
+        if first <= rank < first + size:
+            shape = (C.c_int64 * 5)(*x.shape)
+            check(lib().ltx2_vae_decode_sharded(decoder._h, ptr(x), dtype_code(x), shape,
+                                                -1.0 if timestep is None else float(timestep), s, ptr(noise), first, size,
+                                                slot, -1 if dst is None else int(dst), stream_ptr()),
+                  "ltx2_vae_decode_sharded")
+        if not collect:
+            return None
+        return collect_clip(decoder, x.shape, dst, slot)
+
+
+def collect_clip(decoder: SimpleVideoDecoder, latent_shape, dst: Optional[int] = None, slot: int = 0):
+    """Collective over ALL ranks: wait until every rank group has stored its frames of clip slot `slot`, then return the
+    clip (B, 3, T', 32H, 32W) on rank `dst` (None elsewhere) or on every rank (dst=None)."""
+    rank, world, group = decoder._shards
+    with torch.cuda.device(decoder.device):
+        oshape = decoder.output_shape(tuple(latent_shape))
         receive = dst is None or rank == dst
-        video = torch.empty(B, 3, T, H, W, device=decoder.device, dtype=torch.float32) if receive else None
-        shape = (C.c_int64 * 5)(*x.shape)
-        check(lib().ltx2_vae_decode_sharded(decoder._h, ptr(x), dtype_code(x), shape,
-                                            -1.0 if timestep is None else float(timestep), s, ptr(noise),
-                                            -1 if dst is None else int(dst), ptr(video), stream_ptr()),
-              "ltx2_vae_decode_sharded")
+        video = torch.empty(oshape, device=decoder.device, dtype=torch.float32) if receive else None
+        check(lib().ltx2_vae_cp_collect(decoder._h, slot, (C.c_int64 * 5)(*oshape), -1 if dst is None else int(dst),
+                                        ptr(video), stream_ptr()), "ltx2_vae_cp_collect")
         return video
 
 
@@ -296,8 +313,28 @@ def decode_latent_video(latent, decoder: SimpleVideoDecoder, timestep: Optional[
     # chunks land at frame (len_so_far - overlap); the reference concatenates, we blend into one buffer
     pieces = []
     length = 0
+    # temporal shards with >= 4 ranks and >= 2 chunks: the two halves of the ranks decode two chunks side by side (a chunk
+    # of 7 latent frames cannot use more than 7 ranks, and the small early stages do not speed up below one frame per
+    # rank, so two 4-rank groups finish two chunks sooner than 8 ranks finish them one after the other)
+    halves = sharded and world >= 4 and world % 2 == 0 and len(plan) >= 2
+    shard_out = {}
+    if halves:
+        hw = world // 2
+        for i0 in range(0, len(plan), 2):
+            pair = plan[i0:i0 + 2]
+            s0 = 2 * ((i0 // 2) % 2)          # clip slots alternate between rounds (see kVaeClipSlots, vae_engine.cu)
+            for j, (a, b) in enumerate(pair):
+                # (every rank calls this for every chunk, so the shared noise generator advances identically everywhere;
+                #  only the ranks of the chunk's group launch kernels)
+                decode_sharded(decoder, x[:, :, a:b].contiguous(), timestep, dst, group_ranks=(j * hw, hw), slot=s0 + j,
+                               collect=False)
+            for j, (a, b) in enumerate(pair):
+                shard_out[i0 + j] = collect_clip(decoder, (x.shape[0], x.shape[1], b - a, x.shape[3], x.shape[4]), dst,
+                                                 s0 + j)
     for i, (a, b) in enumerate(plan):
-        if sharded:
+        if halves:
+            v = shard_out[i]
+        elif sharded:
             # temporal shards: ALL ranks work on every chunk (its frames are split over them); collected on dst / all
             v = decode_sharded(decoder, x[:, :, a:b].contiguous(), timestep, dst)
         elif unit_owner(i, world) == rank:

@@ -71,6 +71,23 @@ def main():
             spans = [shard_frames(dec, key[1], r, world) for r in range(world)]
             print(f"rank {rank} temporal shards B,T,H,W={key} dst={dst} spans={spans}: {'OK' if good else 'MISMATCH'}",
                   flush=True)
+    # rank groups: each half of the ranks decodes its own clip at the same time, both collected on rank 0 / everywhere
+    if world >= 2 and world % 2 == 0:
+        from ltx2_b200.video_vae import collect_clip
+        hw = world // 2
+        keys = [(1, 7, 2, 3), (2, 5, 3, 2)]
+        for dst in (None, 0):
+            for rnd in range(3):                      # three rounds: the clip slots alternate and are reused
+                s0 = 2 * (rnd % 2)
+                for j, key in enumerate(keys):
+                    decode_sharded(dec, single[key][0], 0.05, dst=dst, group_ranks=(j * hw, hw), slot=s0 + j, collect=False)
+                good = True
+                for j, key in enumerate(keys):
+                    out = collect_clip(dec, single[key][0].shape, dst, s0 + j)
+                    good = good and ((out is None) if (dst is not None and rank != dst) else torch.equal(out, single[key][1]))
+                ok = ok and good
+                print(f"rank {rank} two rank groups side by side, round {rnd}, dst={dst}: {'OK' if good else 'MISMATCH'}",
+                      flush=True)
     # the reference's chunked decode_latent on top of the shards (every chunk split over all ranks), uint8 frames
     out = decode_latent_video(long_lat, dec, group=G)
     good = torch.equal(out, long_ref)
