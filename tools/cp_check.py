@@ -139,6 +139,31 @@ def main():
         context_parallel.disable(sharded)
         del single, sharded
     ok = av_cases(rank, world, dev) and ok
+    # the FP8 linear path under context parallelism: row-local quantisation, so with split-K off it is bit-exact too
+    for split_k in (1, 0):
+        if split_k:
+            os.environ["LTX2_CP_SPLIT_K"] = str(split_k)
+        else:
+            os.environ.pop("LTX2_CP_SPLIT_K", None)
+        B, F, H, W, S = 2, 2, 4, 8, 64
+        N = F * H * W
+        single, sharded = LTXModel(**kw, fp8_linear=True), LTXModel(**kw, fp8_linear=True)
+        load_transformer_state_dict(single, w)
+        load_transformer_state_dict(sharded, w)
+        context_parallel.enable(sharded, batch=B, n_total=N, context_tokens=S if S % (8 * world) == 0 else 0)
+        lat = synthetic.latents((B, N, 32), seed=320)
+        ctx = synthetic.latents((B, S, 64), seed=321, std=0.5)
+        pos = synthetic.video_positions(B, F, H, W)
+        mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.9, 0.4]), positions=pos)
+        ref, out = single(mod), sharded(mod)
+        torch.cuda.synchronize()
+        rl2 = float((out - ref).norm() / ref.norm())
+        good = torch.equal(out, ref) if split_k == 1 else rl2 <= 2e-3
+        ok = ok and good
+        print(f"rank {rank} FP8 linears, split_k={split_k or 'default'}: rel L2 {rl2:.2e} {'OK' if good else 'MISMATCH'}",
+              flush=True)
+        context_parallel.disable(sharded)
+        del single, sharded
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
