@@ -406,6 +406,14 @@ int ltx2_small_linear(const float* x, int32_t R, int32_t K, const void* W_bf16, 
 int ltx2_x0_from_velocity(const float* latent, const float* velocity, const float* t_row, float* x0, int32_t M,
                           int32_t C, void* stream);
 
+/* Diagnostics: ltx2_attention_vrows plus a clock64 timeline of CTA 0.  SM-pair kernel (head_dim 128, Tq > 128): trace
+ * must hold 16 * ceil(Tk / 128) words; per key block k, trace[16k + e]: e = 0 P(k) seen by the MMA thread, 1 P(k)V and
+ * S(k+2) issued, 2 / 3 / 4 S(k) seen / exponentials done / P(k) published by the softmax warp of keys [0,64), 5 / 6 / 7
+ * the same for keys [64,128) (tools/attn2_check.py prints it). */
+int ltx2_attention_vrows_trace(const void* q, const void* k, const void* v, int64_t v_stride_t, int64_t v_stride_h,
+                               int64_t v_stride_b, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t Dh,
+                               float scale, long long* trace, void* stream);
+
 /* Host-side planners (no GPU needed; 148 SMs are assumed when no device is visible).  They expose which kernel and
  * tiling a launch will take, so the scheduling logic is testable on a CPU-only machine.
  *   ltx2_gemm_plan: out6 = {kernel (0 standard 128-token-row tiles, 1 transposed 128-weight-row tiles, 2 SM-pair tiles),

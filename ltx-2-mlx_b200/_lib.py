@@ -122,6 +122,7 @@ SIGNATURES = {
     "ltx2_gemm_bf16_splitk": (_I32, [_P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P, _I64, _P, _F, _I32, _P]),
     "ltx2_attention": (_I32, [_P, _P, _P, _P] + [_I32] * 6 + [_F, _P, _P, _P]),
     "ltx2_attention_vrows": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P] + [_I32] * 5 + [_F, _P, _P, _P]),
+    "ltx2_attention_vrows_trace": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P] + [_I32] * 5 + [_F, _P, _P]),
     "ltx2_attention_trace": (_I32, [_P, _P, _P, _P] + [_I32] * 6 + [_F, _P, _P]),
     "ltx2_norm_modulate": (_I32, [_P, _I32, _I64, _P, _I64, _I32, _I32, _I32, _F, _P, _I64, _I64, _I64, _P, _P]),
     "ltx2_headnorm_rope": (_I32, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),

@@ -97,6 +97,19 @@ int ltx2_attention_vrows(const void* q, const void* k, const void* v, int64_t v_
   return attention_bf16_v(q, k, av, out, B, H, Tq, Tk, Dh, scale, gate_logits, lse_out, S(stream));
 }
 
+// diagnostics: ltx2_attention_vrows plus the clock64 timeline of CTA 0 (SM-pair kernel: trace[16 * key_blocks])
+int ltx2_attention_vrows_trace(const void* q, const void* k, const void* v, int64_t v_stride_t, int64_t v_stride_h,
+                               int64_t v_stride_b, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t Dh,
+                               float scale, long long* trace, void* stream) {
+  AttnV av;
+  av.ptr = v;
+  av.rows = 1;
+  av.stride_t = v_stride_t;
+  av.stride_h = v_stride_h;
+  av.stride_b = v_stride_b;
+  return attention_bf16_v(q, k, av, out, B, H, Tq, Tk, Dh, scale, nullptr, nullptr, S(stream), trace);
+}
+
 // diagnostics: same as ltx2_attention, and CTA (0,0) writes clock64 stamps of its pipeline events to trace[nkv*8]
 int ltx2_attention_trace(const void* q, const void* k, const void* vt, void* out, int32_t B, int32_t H, int32_t Tq,
                          int32_t Tk, int32_t Tkp, int32_t Dh, float scale, long long* trace, void* stream) {

@@ -394,6 +394,16 @@ __device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory: each CTA of the pair reads ITS 128 rows of A from its own tensor memory at `tmem_a`
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the barrier at this shared-memory offset in BOTH CTAs when all MMAs issued so far have retired
 __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
   asm volatile(

@@ -102,6 +102,14 @@ int attention_pair_bf16(const void* q, const void* k, const AttnV& v, void* out,
                         float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
                         const AttnOutScatter& sc);
 
+// head_dim 128, V in row form, more than one query tile: SM-pair kernel (attention_2cta_sm100.cu, cta_group::2; two
+// adjacent query tiles of a head per cluster).  attention_bf16_v dispatches to it unless LTX2_ATTN_2CTA=0.
+// trace (diagnostics): cluster 0 / CTA 0 writes clock64 stamps to trace[16 * key_blocks].
+bool attention_2cta_applies(const AttnV& v, int Tq, int Dh);
+int attention_2cta_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
+                        float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
+                        const AttnOutScatter& sc);
+
 // Self-attention head preparation in ONE pass over a token row of the fused QKV projection (pitch ld):
 //   q,k: RMSNorm over the full row (learned weight) + split RoPE;  v: copy (skipped when dst.v[0] == null);
 // each head h is written to dst.{q,k,v}[h / heads_per_rank] at [(b*heads_per_rank + h % heads_per_rank) * n_total +
