@@ -422,6 +422,10 @@ int ltx2_attention_vrows_trace(const void* q, const void* k, const void* v, int6
  *                           128-query tiles run as split-KV items) and the resulting CTA count. */
 int ltx2_gemm_plan(int32_t M, int32_t N, int32_t K, int32_t mode, int32_t max_splits, int32_t* out6);
 int ltx2_attention_plan(int32_t Tq, int32_t BH, int32_t* pairs_per_slice, int32_t* n_ctas);
+/*   ltx2_attention_sm_pair_plan: the SM-pair attention kernel's persistent grid -- clusters (SM pairs) launched and
+ *                           whether the (work item, key block) space is cut into equal ranges per cluster whose partial
+ *                           results are merged (split = 1, stream-K) or whole items go round-robin (split = 0). */
+int ltx2_attention_sm_pair_plan(int32_t Tq, int32_t Tk, int32_t BH, int32_t* n_clusters, int32_t* split);
 
 /* The elementwise tail of one denoising step of the reference's host loops (pipelines/distilled.py:243-251,
  * pipelines/one_stage.py:284-320), fused into one pass over fp32 [M, C] tensors:

@@ -133,6 +133,7 @@ SIGNATURES = {
     "ltx2_x0_from_velocity": (_I32, [_P, _P, _P, _P, _I32, _I32, _P]),
     "ltx2_gemm_plan": (_I32, [_I32] * 5 + [_P]),
     "ltx2_attention_plan": (_I32, [_I32, _I32, _P, _P]),
+    "ltx2_attention_sm_pair_plan": (_I32, [_I32, _I32, _I32, _P, _P]),
     "ltx2_denoise_update": (_I32, [_P, _P, _P, _F, _P, _P, _F, _F, _P, _P, _I32, _I32, _P]),
     "ltx2_silu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),
     "ltx2_gelu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),

@@ -437,7 +437,7 @@ int attention_bf16_v(const void* q, const void* k, const AttnV& v, void* out, in
   // LTX2_ATTN_KERNEL=single keeps the one-tile kernel below for A/B measurements.
   const char* env_kernel = getenv("LTX2_ATTN_KERNEL");
   const bool use_pair = !(env_kernel && strcmp(env_kernel, "single") == 0);
-  if (Dh == 128 && use_pair && attention_2cta_applies(v, Tq, Dh))
+  if (Dh == 128 && use_pair && attention_2cta_applies(v, Tq, Tk, Dh))
     return attention_2cta_bf16(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, stream, trace, sc);
   if (Dh == 128 && use_pair)
     return attention_pair_bf16(q, k, v, out, B, H, Tq, Tk, scale, gate_logits, lse_out, stream, trace, sc);

@@ -197,6 +197,18 @@ int ltx2_attention_plan(int32_t Tq, int32_t BH, int32_t* pairs_per_slice, int32_
   return LTX2_OK;
 }
 
+int ltx2_attention_sm_pair_plan(int32_t Tq, int32_t Tk, int32_t BH, int32_t* n_clusters, int32_t* split) {
+  if (Tq <= 0 || Tk <= 0 || BH <= 0 || n_clusters == nullptr || split == nullptr) {
+    set_error("attention_sm_pair_plan: bad argument");
+    return LTX2_ERR_INVALID;
+  }
+  int c = 0, s = 0;
+  attention_2cta_plan(Tq, Tk, BH, &c, &s);
+  *n_clusters = c;
+  *split = s;
+  return LTX2_OK;
+}
+
 int ltx2_denoise_update(const float* sample, const float* cond_x0, const float* uncond_x0, float cfg_scale,
                         const float* denoise_mask, const float* clean_latent, float sigma, float sigma_next, float* out,
                         float* denoised_out, int32_t M, int32_t C, void* stream) {

@@ -413,6 +413,12 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
       : "memory");
 }
 
+// arrive on a barrier of THIS CTA only when all cta_group::2 MMAs issued so far have retired
+__device__ __forceinline__ void umma2_commit_local(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

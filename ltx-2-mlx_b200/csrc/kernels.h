@@ -103,9 +103,13 @@ int attention_pair_bf16(const void* q, const void* k, const AttnV& v, void* out,
                         const AttnOutScatter& sc);
 
 // head_dim 128, V in row form, more than one query tile: SM-pair kernel (attention_2cta_sm100.cu, cta_group::2; two
-// adjacent query tiles of a head per cluster).  attention_bf16_v dispatches to it unless LTX2_ATTN_2CTA=0.
+// adjacent query tiles of a head per cluster; persistent, stream-K over the key blocks).  attention_bf16_v dispatches
+// to it for very long sequences (>= 8192 queries and keys); LTX2_ATTN_2CTA=1 forces it, =0 removes it.
 // trace (diagnostics): cluster 0 / CTA 0 writes clock64 stamps to trace[16 * key_blocks].
-bool attention_2cta_applies(const AttnV& v, int Tq, int Dh);
+bool attention_2cta_applies(const AttnV& v, int Tq, int Tk, int Dh);
+// the pair kernel's work decomposition (pure host logic): clusters in the grid and whether (item, key block) ranges are
+// split across clusters (stream-K) or whole items go round-robin
+void attention_2cta_plan(int Tq, int Tk, int BH, int* n_clusters, int* split);
 int attention_2cta_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
                         float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
                         const AttnOutScatter& sc);

@@ -62,18 +62,20 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, tk: int, *, ga
     return (out, lse) if want_lse else out
 
 
-def attention_vrows(q: torch.Tensor, k: torch.Tensor, v_rows: torch.Tensor, H: int, Dh: int, *, gate_logits=None):
+def attention_vrows(q: torch.Tensor, k: torch.Tensor, v_rows: torch.Tensor, H: int, Dh: int, *, gate_logits=None,
+                    want_lse: bool = False):
     """V straight from a token-major buffer: v_rows [B, Tk, >= H*Dh] view (last dim contiguous), e.g. qkv[..., 2*inner:]."""
     _cuda(q, k, gate_logits)
     B, _, Tq, _ = q.shape
     Tk = k.shape[2]
     assert v_rows.is_cuda and v_rows.stride(2) == 1
     out = torch.empty(B, Tq, H * Dh, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Tq, device=q.device, dtype=torch.float32) if want_lse else None
     check(lib().ltx2_attention_vrows(ptr(q), ptr(k), ptr(v_rows), C.c_int64(v_rows.stride(1)), C.c_int64(Dh),
                                      C.c_int64(v_rows.stride(0)), ptr(out), B, H, Tq, Tk, Dh,
-                                     C.c_float(1.0 / math.sqrt(Dh)), ptr(gate_logits), None, stream_ptr()),
+                                     C.c_float(1.0 / math.sqrt(Dh)), ptr(gate_logits), ptr(lse), stream_ptr()),
           "ltx2_attention_vrows")
-    return out
+    return (out, lse) if want_lse else out
 
 
 def norm_modulate(x: torch.Tensor, *, kind: int, eps: float = 1e-6, mod: Optional[torch.Tensor] = None,

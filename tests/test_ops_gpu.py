@@ -140,6 +140,62 @@ def test_attention_two_stream_modes(monkeypatch, pairs, B, H, Tq, Tk):
     assert float((lse - ref_lse).abs().max()) < 2e-3
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("B,H,Tq,Tk,std", [(1, 2, 256, 128, 1.0), (1, 1, 256, 40, 1.0), (2, 3, 300, 333, 2.0),
+                                           (1, 2, 384, 1000, 4.0), (1, 3, 640, 1024, 1.0), (1, 2, 130, 2000, 2.0),
+                                           (2, 4, 1000, 700, 1.0)])
+def test_attention_sm_pair_kernel(monkeypatch, split, B, H, Tq, Tk, std):
+    """head_dim 128 SM-pair kernel (cta_group::2, attention_2cta_sm100.cu), forced on shapes the dispatcher would give to
+    the one-SM kernel: odd query-tile counts (the second CTA of the last pair runs on an out-of-range tile), ragged key
+    tails inside the first / second 64 keys of a block, a single key block, batch > 1, sharp logits (running maximum moves,
+    lazy rescale), with whole items per cluster (split 0) and with (item, key block) ranges cut across clusters and
+    merged by the last finisher (split 1)."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_ATTN_2CTA", "1")
+    monkeypatch.setenv("LTX2_ATTN_SPLIT", split)
+    Dh = 128
+    q = rnd(B, H, Tq, Dh, seed=31, std=std, dtype=torch.bfloat16)
+    k = rnd(B, H, Tk, Dh, seed=32, std=2.0, dtype=torch.bfloat16)
+    qkv = rnd(B, Tk, 3 * H * Dh, seed=33, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * H * Dh:]
+    gate = rnd(B * Tq, H, seed=34)
+    v = v_rows.reshape(B, Tk, H, Dh).permute(0, 2, 1, 3)
+    out = ops.attention_vrows(q, k, v_rows, H, Dh, gate_logits=gate)
+    ref, ref_lse = _attn_ref(q, k, v, gate)
+    assert rel_err(out.float(), ref) < 1.5e-2
+    out2, lse = ops.attention_vrows(q, k, v_rows, H, Dh, want_lse=True)
+    ref2, _ = _attn_ref(q, k, v)
+    assert rel_err(out2.float(), ref2) < 1.5e-2
+    assert float((lse - ref_lse).abs().max()) < 2e-3
+    # the same launch again: the merge counters of the split schedule were reset by the mergers
+    out3 = ops.attention_vrows(q, k, v_rows, H, Dh)
+    assert torch.equal(out2, out3)
+
+
+@pytest.mark.parametrize("H,Tq,Tk", [(4, 3456, 3456), (32, 3456, 1024)])
+def test_attention_sm_pair_kernel_production_shapes(monkeypatch, H, Tq, Tk):
+    """The SM-pair kernel at the 19B shapes (4 heads = one rank of 8 under context parallelism: 56 items over 74 SM
+    pairs, every item cut in two or three parts), against torch on two heads and bit-for-bit between its two schedules'
+    own repeat runs (the merge order is fixed, so a schedule is deterministic)."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_ATTN_2CTA", "1")
+    Dh = 128
+    q = rnd(1, H, Tq, Dh, seed=35, dtype=torch.bfloat16)
+    k = rnd(1, H, Tk, Dh, seed=36, dtype=torch.bfloat16)
+    qkv = rnd(1, Tk, 3 * H * Dh, seed=37, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * H * Dh:]
+    v = v_rows.reshape(1, Tk, H, Dh).permute(0, 2, 1, 3)
+    ref, _ = _attn_ref(q[:, :2], k[:, :2], v[:, :2])
+    outs = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("LTX2_ATTN_SPLIT", split)
+        out = ops.attention_vrows(q, k, v_rows, H, Dh)
+        assert rel_err(out[:, :, :2 * Dh].float(), ref) < 1.2e-2
+        assert torch.equal(out, ops.attention_vrows(q, k, v_rows, H, Dh))
+        outs[split] = out
+    assert rel_err(outs["0"].float(), outs["1"].float()) < 5e-3
+
+
 def test_attention_single_tile_kernel_still_matches(monkeypatch):
     """LTX2_ATTN_KERNEL=single keeps the one-tile kernel (the head_dim 64 path) reachable at head_dim 128 for A/B runs."""
     from ltx2_b200 import ops

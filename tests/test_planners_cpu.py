@@ -2,6 +2,7 @@
 The planners are pure host logic behind the C ABI (ltx2_gemm_plan, ltx2_attention_plan); with no device visible they
 assume the B200's 148 SMs."""
 import ctypes as C
+import os
 import random
 
 import pytest
@@ -87,6 +88,36 @@ def test_attention_work_items():
         pairs, ctas = attention_plan(Tq, BH)
         n_q = (Tq + 127) // 128
         assert 0 <= pairs <= n_q // 2 and ctas == BH * (n_q - pairs)
+
+
+def sm_pair_plan(Tq, Tk, BH):
+    from ltx2_b200._lib import check, lib
+    c, s = C.c_int32(), C.c_int32()
+    check(lib().ltx2_attention_sm_pair_plan(Tq, Tk, BH, C.byref(c), C.byref(s)), "ltx2_attention_sm_pair_plan")
+    return c.value, s.value
+
+
+def test_sm_pair_attention_schedule():
+    """The persistent SM-pair attention kernel: 32 heads x 14 query-tile pairs = 448 items do not fit 74 SM pairs in six
+    rounds, so the (item, key block) space is cut into 74 equal ranges (stream-K); a rank of 8 (4 heads, 56 items) spreads
+    its 1512 key blocks over all 74 pairs; few short items stay whole."""
+    os.environ.pop("LTX2_ATTN_SPLIT", None)
+    assert sm_pair_plan(3456, 3456, 32) == (74, 1)
+    assert sm_pair_plan(3456, 3456, 4) == (74, 1)
+    assert sm_pair_plan(432, 1024, 32) == (64, 0)          # 64 items of 8 blocks: one each
+    assert sm_pair_plan(256, 128, 2) == (2, 0)
+    rng = random.Random(2)
+    for _ in range(300):
+        Tq, Tk, BH = rng.randint(129, 20000), rng.randint(1, 20000), rng.randint(1, 64)
+        clusters, split = sm_pair_plan(Tq, Tk, BH)
+        n_items = BH * (((Tq + 127) // 128 + 1) // 2)
+        nblk = (Tk + 127) // 128
+        assert 1 <= clusters <= 74
+        if split:
+            # a range is at least four key blocks and a third of an item: at most four parts per item
+            assert n_items * nblk // clusters >= max(4, nblk // 3)
+        else:
+            assert clusters <= n_items
 
 
 def test_planners_reject_bad_arguments():

@@ -17,10 +17,13 @@ def case(Tq, Tk, heads, B=1, iters=20, check_heads=2, gate=False):
     ref = (torch.softmax(s, -1) @ v[:, hs].float()).permute(0, 2, 1, 3).reshape(B, Tq, check_heads * Dh)
     flops = 4.0 * B * heads * Tq * Tk * Dh
     res = {}
-    for name, env in (("2cta", {"LTX2_ATTN_2CTA": "1"}), ("2cta-p0", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_POLY": "0"}), ("2cta-p1", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_POLY": "1"}), ("2cta-p2", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_POLY": "2"}), ("pair", {"LTX2_ATTN_2CTA": "0"})):
+    for name, env in (("2cta", {"LTX2_ATTN_2CTA": "1"}), ("2cta-ns", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_SPLIT": "0"}), ("2cta-fs", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_SPLIT": "1"}), ("2cta-p2", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_POLY": "2"}), ("2cta-p4", {"LTX2_ATTN_2CTA": "1", "LTX2_ATTN_POLY": "4"}), ("pair", {"LTX2_ATTN_2CTA": "0"})):
         os.environ.pop("LTX2_ATTN_2CTA", None)
         os.environ.pop("LTX2_ATTN_POLY", None)
+        os.environ.pop("LTX2_ATTN_SPLIT", None)
+        os.environ.pop("LTX2_ATTN_DBG", None)
         os.environ.update(env)
+        print(f"   .. {name}", flush=True)
         out = ops.attention_vrows(q, k, v_rows, heads, Dh)
         torch.cuda.synchronize()
         err = float((out[:, :, :check_heads * Dh].float() - ref).norm() / ref.norm())
@@ -37,7 +40,7 @@ def case(Tq, Tk, heads, B=1, iters=20, check_heads=2, gate=False):
         print(f"Tq={Tq} Tk={Tk} H={heads} B={B} {name:8s} {ms*1e3:8.1f} us {flops/ms/1e9:7.1f} TF/s rel.err {err:.2e} finite {bool(torch.isfinite(out).all())}", flush=True)
     d = float((res["2cta"].float() - res["pair"].float()).abs().max())
     print(f"   max |2cta - pair| = {d:.3e}", flush=True)
-for shape in [(256, 128, 2)]:
+for shape in [(384, 1000, 2), (3456, 3456, 4), (3456, 3456, 16), (3456, 3456, 32), (3456, 1024, 32), (12288, 12288, 8), (6144, 6144, 8)]:
     case(*shape)
 case(640, 333, 4, B=2)
 
@@ -65,16 +68,16 @@ def timeline(Tq, Tk, heads):
     print("block " + " ".join(f"{n:>13s}" for n in names))
     for kb in range(min(nblk, 6)):
         print(f"{kb:5d} " + " ".join(f"{int(t[kb, e]) - t0:13d}" for e in range(8)))
-    print("MMA warp, relative to 'P seen': V acquired, PV issued, empty(V) committed, K acquired, S issued, empty(K) committed, s_full committed")
+    print("MMA warp, relative to 'P seen': entry acquired, PV issued, S issued, empty committed, s_full committed")
     for kb in range(2, min(nblk, 6)):
-        print(f"{kb:5d} " + " ".join(f"{int(t[kb, e]) - int(t[kb, 0]):8d}" for e in (8, 9, 10, 11, 12, 13, 1)))
+        print(f"{kb:5d} " + " ".join(f"{int(t[kb, e]) - int(t[kb, 0]):8d}" for e in (8, 9, 10, 11, 1)))
     if nblk > 6:
         per = (int(t[nblk - 2, 4]) - int(t[2, 4])) / (nblk - 4)
         print(f"period per 128-key block: {per:.0f} clk (tensor floor 1024)")
 
 
 if os.environ.get("ATTN2_TIMELINE", "1") != "0":
-    for dbg in ("0", "3"):
+    for dbg in ("0",):
         os.environ["LTX2_ATTN_DBG"] = dbg
         print("== LTX2_ATTN_DBG =", dbg, "(1: no S MMAs in the loop, 2: no P*V MMAs)")
-        timeline(3456, 3456, 4)
+        timeline(3456, 3456, 32)
