@@ -389,11 +389,12 @@ attention_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       float m_used = -INFINITY;                         // maximum the current scale of P, l and O refers to
       float l = 0.f;
 
+      bool s_ready = false;                             // the next S block was already complete when probed
       for (int j = 0; j < n; ++j) {
         const int b = j & 1;
         const int kv_valid = Tk - (sg.kb0 + j) * BK2 - g * GRP;   // valid keys of this group's 64 columns (may be <= 0)
         const uint32_t t_s = t_lane + b * BK2 + g * GRP;
-        wait_lean(&s_full[b], (b ? ns1 : ns0) & 1);
+        if (!s_ready) wait_lean(&s_full[b], (b ? ns1 : ns0) & 1);
         if (b) ++ns1; else ++ns0;
         if (trs) trace[j * kTrace + 2 + 3 * g] = clock64();
         tc_fence_after();
@@ -489,6 +490,8 @@ attention_2cta_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
         }
         if (trs) trace[j * kTrace + 3 + 3 * g] = clock64();
+        // probe the next block's barrier now: the round trip (~100 clocks) overlaps the publication below
+        s_ready = j + 1 < n && mbar_test_wait(&s_full[b ^ 1], (b ? ns0 : ns1) & 1);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

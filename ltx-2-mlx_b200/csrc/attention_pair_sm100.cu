@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kPairThreads, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int H, int Tq, int Tk,
                       float scale_log2, float scale, const float* __restrict__ gate_logits,
-                      float* __restrict__ lse_out, long long* __restrict__ trace, AttnOutScatter sc, PairGrid pg) {
+                      float* __restrict__ lse_out, long long* __restrict__ trace,
+                      const __grid_constant__ AttnOutScatter sc, PairGrid pg) {
   pdl_trigger();                                        // the next kernel may become resident under my tail
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -391,12 +392,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     float l = 0.f;
 
     if (trs && i == 0) trace[nkv * kTraceStride + 1] = clock64();   // set-up done (TMEM, barriers)
+    bool s_ready = false;                               // the next S sub-block was already complete when probed
     for (int k = 0; k < nsub; ++k) {
       const int h = k & 1, t = k >> 1;
       const int kv_valid = keys - k * SUB;
       const int tro = i == 0 ? 4 + 4 * h : 12;
       const bool trk = trs && (i == 0 || h == 0);
-      mbar_wait(&s_full[i * 2 + h], t & 1);
+      if (!s_ready) mbar_wait_lean(&s_full[i * 2 + h], t & 1);
       if (trk) trace[t * kTraceStride + tro + 0] = clock64();
       tc_fence_after();
       uint32_t s[SUB];
@@ -419,6 +421,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[i * 2 + h]);
+        s_ready = false;
         continue;
       }
       if (kv_valid < SUB) {
@@ -448,7 +451,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       if (__any_sync(0xffffffffu, need)) {
         // O_i must be quiescent: P(k-1)*V is retired once the OTHER S buffer's next completion (S(k+1), or the
         // bare commit when no S(k+1) exists) is signalled; P(k)*V cannot start before this thread publishes P(k)
-        mbar_wait(&s_full[i * 2 + (h ^ 1)], ((k + 1) >> 1) & 1);
+        mbar_wait_lean(&s_full[i * 2 + (h ^ 1)], ((k + 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < DHP; c += 32) {
@@ -496,6 +499,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
       if (trk) trace[t * kTraceStride + tro + 2] = clock64();
+      // probe the next sub-block's barrier now: the round trip (~100 clocks) overlaps the publication below
+      s_ready = k + 1 < nsub && mbar_test_wait(&s_full[i * 2 + (h ^ 1)], ((k + 1) >> 1) & 1);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[i * 2 + h]);
@@ -521,7 +526,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       o = out + (static_cast<int64_t>(b_idx) * Tq + row) * (static_cast<int64_t>(H) * DHP) + h_idx * DHP;
     }
     if (pair) {
-      mbar_wait(&o_done[i], 0);
+      mbar_wait_lean(&o_done[i], 0);
       tc_fence_after();
       const float f = g / l;
 #pragma unroll
@@ -545,8 +550,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     } else {
       // merge the two key halves of this query tile: both accumulators are visible to either warpgroup (same TMEM
       // lanes), so stream i's threads finish output columns [64 i, 64 i + 64) of the merged row
-      mbar_wait(&o_done[0], 0);
-      if (n1 > 0) mbar_wait(&o_done[1], 0);
+      mbar_wait_lean(&o_done[0], 0);
+      if (n1 > 0) mbar_wait_lean(&o_done[1], 0);
       tc_fence_after();
       float2* xs = reinterpret_cast<float2*>(sQ);       // Q is dead: every MMA has retired
       xs[i * 128 + r] = make_float2(m_used, l);

@@ -295,6 +295,8 @@ constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
 // Transposed epilogue of the 2-CTA kernel: the accumulator tile is C^T, i.e. TMEM lane = output column (weight row),
 // TMEM column = token.  Thread `lane` of a warp owns one output column; the 32 lanes of a warp store 32 consecutive
 // output columns of one token per instruction (64 B bf16 / 128 B fp32 runs).
+__device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x & 31); }
+
 __device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t t_row, int col, int tok0, int ntok, int M,
                                                bool first_slice = true) {
   const float b = (ep.bias != nullptr && first_slice) ? __ldg(ep.bias + col) : 0.f;
@@ -308,12 +310,21 @@ __device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t 
     if (t0 >= tend) break;
     const int nv = min(32, tend - t0);                    // warp-uniform
     if (ep.mode == GEMM_EPI_BF16 || ep.mode == GEMM_EPI_BF16_GELU) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
+      // two tokens per store instruction: lanes 2i / 2i+1 swap one value, so an even lane holds columns (c, c+1) of
+      // token j and its odd neighbour columns (c-1, c) of token j+1 -- 4-byte stores, half as many instructions
+      const bool odd = lane_id() & 1;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + (col & ~1);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = __uint_as_float(r[j]) + b;
-        if (ep.mode == GEMM_EPI_BF16_GELU) v = gelu_tanh_f(v);
-        if (j < nv) o[static_cast<int64_t>(j) * ep.ldo] = __float2bfloat16_rn(v);
+      for (int j = 0; j < 32; j += 2) {
+        float v0 = __uint_as_float(r[j]) + b, v1 = __uint_as_float(r[j + 1]) + b;
+        if (ep.mode == GEMM_EPI_BF16_GELU) {
+          v0 = gelu_tanh_f(v0);
+          v1 = gelu_tanh_f(v1);
+        }
+        const float got = __shfl_xor_sync(0xffffffffu, odd ? v0 : v1, 1);
+        const uint32_t pk = odd ? pack_bf16x2(got, v1) : pack_bf16x2(v0, got);
+        const int jj = j + (odd ? 1 : 0);
+        if (jj < nv) *reinterpret_cast<uint32_t*>(o + static_cast<int64_t>(jj) * ep.ldo) = pk;
       }
     } else if (ep.mode == GEMM_EPI_F32) {
       float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
@@ -322,11 +333,22 @@ __device__ __forceinline__ void epilogue_col_t(const GemmEpilogue& ep, uint32_t 
         if (j < nv) o[static_cast<int64_t>(j) * ep.ldo] = __uint_as_float(r[j]) + b;
     } else {  // GEMM_EPI_F32_RESIDUAL: out += alpha * gate[cls(token), col] * (acc + bias), added by the L2
       float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(t0) * ep.ldo + col;
+      // the modulation class belongs to the TOKEN (uniform over the lanes) and the gate to (class, this lane's column):
+      // lane j fetches the class of token j once per 32 tokens; a chunk of one class (the common case: classes are
+      // long runs of tokens) needs one gate load, otherwise one per token -- two dependent global loads per token in
+      // the inner loop made this epilogue cost ~100 clocks per token
+      const int my_cls = (ep.row_cls != nullptr && lane_id() < nv) ? __ldg(ep.row_cls + t0 + lane_id()) : 0;
+      const int cls0 = __shfl_sync(0xffffffffu, my_cls, 0);
+      const bool uniform = __all_sync(0xffffffffu, lane_id() >= nv || my_cls == cls0);
+      const float g0 = ep.gate != nullptr ? __ldg(ep.gate + static_cast<int64_t>(cls0) * ep.gate_stride + col) : 1.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
+        float g = g0;
+        if (!uniform) {
+          const int cls = __shfl_sync(0xffffffffu, my_cls, j);
+          if (ep.gate != nullptr) g = __ldg(ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col);
+        }
         if (j < nv) {
-          const int cls = ep.row_cls != nullptr ? __ldg(ep.row_cls + t0 + j) : 0;
-          const float g = ep.gate != nullptr ? __ldg(ep.gate + static_cast<int64_t>(cls) * ep.gate_stride + col) : 1.f;
           asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + static_cast<int64_t>(j) * ep.ldo),
                        "f"(ep.alpha * g * (__uint_as_float(r[j]) + b))
                        : "memory");
@@ -637,8 +659,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
       for (int kb = 0; kb < num_kb; ++kb) {
+        // plain (CTA-scope) waits: the operands are read by the tensor core through the async proxy, never by this
+        // thread; an acquire at cluster scope compiles to an L1 invalidation (CCTL.IVALL) per K block
         mbar_wait(&full_bar[stage], phase);
-        mbar_wait_cluster(&peer_full[stage], phase);
+        mbar_wait(&peer_full[stage], phase);
         tc_fence_after();
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kHalfBytes));
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * kHalfBytes));
@@ -679,6 +703,197 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// "Wide" 2-CTA variant for the context-parallel shard shapes (432 / 864 token rows per rank).  There the kernels above
+// are bound by the L2 -> SM bandwidth, not by the tensor pipe: with 3 token tiles per weight slab every weight byte
+// leaves the L2 three times and every token byte once per weight tile (QKV at 432 rows: 470 MB per launch = 44 us at
+// the ~10 TB/s the L2 delivers, against 22 us of MMA time).  Here a cluster computes 256 weight rows x UP TO 512
+// TOKENS: two accumulators of tw/2 tokens each fill the 512 tensor-memory columns, so a 432-row shard is ONE token tile,
+// weights leave the L2 once, and per K block an SM receives 16 KB of weights + tw/2 token rows (44 KB for tw = 448)
+// for 2 tw tensor clocks (49 B/clk).  There is no second accumulator stage (the epilogue of an item is not overlapped
+// with the next item's MMAs -- a cluster has one or two items), and the K loop can be split (fp32 residual epilogue:
+// the partial sums are added by the L2), which is what fills the machine when N / 256 is small (N = 4096: 16 slabs).
+//   warp 0 (both CTAs)  TMA producer: this CTA's 128 weight rows, and its quarter of the tokens for either accumulator
+//   warp 1, CTA 1       relay: own `full` complete -> remote arrive on CTA 0's `peer_full`
+//   warp 1, CTA 0       MMA issuer: 2 x 4 tcgen05.mma.cta_group::2 per K block (M 256, N tw/2)
+//   warps 2-5           epilogue of the CTA's 128 output columns x all tokens of the tile
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStagesW = 4;
+constexpr int kStageBytesW = kHalfBytes + 256 * BK * 2;         // 16 KB weights + up to 256 token rows (32 KB)
+constexpr int kSmemBytesW = kStagesW * kStageBytesW + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2w_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, int M, int N,
+                   int K, int tw, int num_t, int splits, GemmEpilogue ep) {
+  // tmap_x: the token operand with a box of tw/4 rows (one CTA's share of one accumulator)
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                       // [stages][128 weight rows x 64]
+  uint8_t* smem_b = smem + kStagesW * kHalfBytes;               // [stages][2 x tw/4 token rows x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * kStageBytesW);
+  uint64_t* full_bar = bars;                         // [stages]  own TMA -> MMA (CTA 0) / relay (CTA 1)
+  uint64_t* peer_full = full_bar + kStagesW;         // [stages]  CTA 1 relay -> CTA 0 MMA (used in CTA 0 only)
+  uint64_t* empty_bar = peer_full + kStagesW;        // [stages]  MMA (multicast) -> own TMA
+  uint64_t* acc_full = empty_bar + kStagesW;         // MMA (multicast) -> own epilogue
+  uint64_t* acc_empty = acc_full + 1;                // all 8 epilogue warps -> MMA (used in CTA 0 only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  const int num_items = (N / 256) * splits * num_t;  // item = (token tile [fastest], K slice, weight slab)
+  const int qrows = tw / 4;                          // token rows per CTA and accumulator
+  const uint32_t b_acc_bytes = static_cast<uint32_t>(qrows) * BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kStagesW; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&peer_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();                                 // both CTAs are running and their barriers exist
+  if (warp == 1) tmem_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ============ TMA producer (both CTAs) ============
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t bytes = kHalfBytes + 2 * b_acc_bytes;
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      const int ti = it % num_t, si = (it / num_t) % splits, wi = it / (num_t * splits);
+      const int w0 = wi * 256 + static_cast<int>(rank) * 128;
+      const int t0 = ti * tw + static_cast<int>(rank) * qrows;   // accumulator j: + j * tw / 2
+      const int kb0 = si * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
+          mbar_expect_tx(&full_bar[stage], bytes);
+          tma_load_2d(smem_a + stage * kHalfBytes, &tmap_w, &full_bar[stage], kb * BK, w0);
+          uint8_t* sb = smem_b + stage * (256 * BK * 2);
+          tma_load_2d(sb, &tmap_x, &full_bar[stage], kb * BK, t0);
+          tma_load_2d(sb + b_acc_bytes, &tmap_x, &full_bar[stage], kb * BK, t0 + tw / 2);
+        }
+        if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ===================== relay (CTA 1) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      const int si = (it / num_t) % splits;
+      const int kb0 = si * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        if (leader) mbar_arrive_cluster_relaxed(mapa_u32(&peer_full[stage], 0));
+        __syncwarp();
+        if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (CTA 0) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t idesc = umma_idesc_bf16(256, static_cast<uint32_t>(tw / 2));
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      const int si = (it / num_t) % splits;
+      const int kb0 = si * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      mbar_wait(acc_empty, acc_phase ^ 1);            // the previous item's epilogue has read the accumulators
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&peer_full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kHalfBytes));
+        const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(smem_b + stage * (256 * BK * 2)));
+        const uint64_t bdesc1 = umma_desc_k_sw128(smem_u32(smem_b + stage * (256 * BK * 2) + b_acc_bytes));
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma2_bf16_ss(tmem_base, adesc + 2 * k, bdesc0 + 2 * k, idesc, (kb > kb0) || k != 0);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma2_bf16_ss(tmem_base + 256, adesc + 2 * k, bdesc1 + 2 * k, idesc, (kb > kb0) || k != 0);
+          umma2_commit_both(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma2_commit_both(acc_full);
+      __syncwarp();
+      acc_phase ^= 1;
+    }
+  } else {
+    // ============ epilogue (warps 2..5, both CTAs: this CTA's 128 output columns x all tokens of the tile) ============
+    const int quarter = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      const int ti = it % num_t, si = (it / num_t) % splits, wi = it / (num_t * splits);
+      const int col = wi * 256 + static_cast<int>(rank) * 128 + quarter * 32 + lane;
+      mbar_wait(acc_full, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int tok0 = ti * tw;
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const int tj = tok0 + j * (tw / 2);
+        if (tj < M) epilogue_col_t(ep, t_row + j * 256, col, tj, min(tw / 2, M - tj), M, si == 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      // the accumulator reads are complete (wait::ld inside the epilogue) and fenced: no memory ordering is needed on
+      // the arrival itself (a release at cluster scope costs ~1000 clocks)
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(acc_empty);
+        else mbar_arrive_cluster_relaxed(mapa_u32(acc_empty, 0));
+      }
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // nobody leaves while the peer may still touch my barriers / smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+int launch_gemm2w(const CUtensorMap* tw_map, const CUtensorMap* tx, int M, int N, int K, int tile_w, int num_t, int splits,
+                  const GemmEpilogue& ep, cudaStream_t stream) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
+    LTX2_CUDA_CHECK(cudaFuncSetAttribute(gemm2w_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesW));
+  }
+  const int items = (N / 256) * num_t * splits;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (items < pairs ? items : pairs);
+  LTX2_CUDA_CHECK(launch_pdl(gemm2w_bf16_kernel, dim3(grid), dim3(kGemmThreads), kSmemBytesW, stream, *tw_map, *tx, M, N, K,
+                             tile_w, num_t, splits, ep));
+  count_launch();
+  return LTX2_OK;
 }
 
 int gemm2_tiles(int M, int N, int tile_w = 256) { return ((M + tile_w - 1) / tile_w) * (N / 256); }
@@ -804,6 +1019,48 @@ GemmPlan plan_gemm(int M, int N, int K, int mode, int max_splits, int n_out_peer
         }
       }
     }
+    // wide pair kernel (256 weight rows x up to 512 tokens, K split for the residual epilogue).  Its K loop runs at the
+    // tensor rate (930 clocks per K block of 2 x 4 N = 224 instructions, tools/gemm_epi_probe.py), but a 432-row shard
+    // gives it only N / 256 items (16-64 for 74 SM pairs) and its epilogue is not overlapped, so measured
+    // (tools/gemm_cp_shapes.py, profiles/r2_gemm_cp_shapes.txt) it loses to the kernels above on every DiT shape
+    // (QKV at 432 rows 55.6 vs 43.6 us, FFN down 68.5 vs 62.9).  It is therefore only taken when forced:
+    // LTX2_GEMM_WIDE=2 (tests, A/B runs).
+    {
+      const char* envw = getenv("LTX2_GEMM_WIDE");
+      const bool off = (envw && envw[0] == '0') || (env2 && (env2[0] == '0' || env2[0] == '2')) || (envt && envt[0] == '2');
+      const bool force_w = envw && envw[0] == '2';
+      const bool modes_ok = mode == GEMM_EPI_BF16 || mode == GEMM_EPI_BF16_GELU || mode == GEMM_EPI_F32 ||
+                            mode == GEMM_EPI_F32_RESIDUAL;
+      if (!off && force_w && modes_ok && N % 256 == 0 && n_out_peers == 0 && M >= 64) {
+        const int pairs = nsm / 2;
+        const int num_t = (M + 511) / 512;
+        const int tw = (((M + num_t - 1) / num_t) + 31) & ~31;
+        const int slabs = N / 256;
+        int best_s = 1;
+        long best_c = -1;
+        for (int sp = 1; sp <= (may_split ? 8 : 1); ++sp) {
+          if (sp > 1 && (sp > max_splits || num_kb / sp < 8)) break;
+          const long items = static_cast<long>(slabs) * num_t * sp;
+          const long waves = (items + pairs - 1) / pairs;
+          // per K block 2 tw tensor clocks; per item the epilogue (not overlapped) and the pipeline fill
+          const long c = waves * (static_cast<long>((num_kb + sp - 1) / sp) * 2 * tw + 6 * tw + 2000);
+          if (best_c < 0 || c < best_c) {
+            best_c = c;
+            best_s = sp;
+          }
+        }
+        // fewer than half of the SM pairs busy: the standard kernel's smaller tiles spread better
+        const long items = static_cast<long>(slabs) * num_t * best_s;
+        if (force_w || items * 2 >= pairs) {
+          p.kernel = GEMM_KERNEL_WIDE;
+          p.tile_w = tw;
+          p.last_w = tw;
+          p.num_t = num_t;
+          p.splits = best_s;
+          return p;
+        }
+      }
+    }
     const bool force_t = envt && envt[0] == '2', force_p = env2 && env2[0] == '2';
     const bool wide_bf16 = (mode == GEMM_EPI_BF16 || mode == GEMM_EPI_BF16_GELU) && N >= 8192 && M <= 2048;
     const bool take_p = best_p > 0 && (force_p || (!force_t && wide_bf16 && best_p * 10 < cost_std * 9 &&
@@ -841,7 +1098,15 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int
   LTX2_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
   LTX2_REQUIRE(ep.out != nullptr || ep.n_out_peers > 0, "gemm: null output");
-  const GemmPlan plan = plan_gemm(M, N, K, ep.mode, ep.max_splits, ep.n_out_peers);
+  // the C^T kernels store bf16 outputs as column pairs: 4-byte aligned rows (n_out_peers = 1 leaves the standard kernel)
+  const bool pair_stores_ok = (ep.ldo % 2 == 0) && (reinterpret_cast<uintptr_t>(ep.out) % 4 == 0);
+  const GemmPlan plan = plan_gemm(M, N, K, ep.mode, ep.max_splits, pair_stores_ok ? ep.n_out_peers : 1);
+  if (plan.kernel == GEMM_KERNEL_WIDE) {
+    CUtensorMap tw, tx;
+    LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));
+    LTX2_PROPAGATE(get_tensor_map_2d(&tx, A, M, K, lda, plan.tile_w / 4));
+    return launch_gemm2w(&tw, &tx, M, N, K, plan.tile_w, plan.num_t, plan.splits, ep, stream);
+  }
   if (plan.kernel == GEMM_KERNEL_PAIR) {
     CUtensorMap tw, txf, txl;
     LTX2_PROPAGATE(get_tensor_map_2d(&tw, W, N, K, ldw, 128));

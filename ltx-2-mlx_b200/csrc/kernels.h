@@ -53,8 +53,9 @@ int gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, int M, i
 
 // Which kernel and tiling gemm_bf16 takes for a problem (pure host logic: needs no GPU, uses 148 SMs when no device
 // is visible).  standard: 128 token rows x bn columns, K split `splits` ways;  transposed: 128 weight rows x tile_w
-// tokens (last tile last_w), num_t token tiles, K split `splits` ways;  pair: SM pairs, 256 weight rows x tile_w tokens.
-enum GemmKernel { GEMM_KERNEL_STANDARD = 0, GEMM_KERNEL_TRANSPOSED = 1, GEMM_KERNEL_PAIR = 2 };
+// tokens (last tile last_w), num_t token tiles, K split `splits` ways;  pair: SM pairs, 256 weight rows x tile_w tokens;
+// wide: SM pairs, 256 weight rows x tile_w <= 512 tokens in two accumulators, K split `splits` ways (shard shapes).
+enum GemmKernel { GEMM_KERNEL_STANDARD = 0, GEMM_KERNEL_TRANSPOSED = 1, GEMM_KERNEL_PAIR = 2, GEMM_KERNEL_WIDE = 3 };
 struct GemmPlan {
   int kernel = GEMM_KERNEL_STANDARD;
   int bn = 256, splits = 1;

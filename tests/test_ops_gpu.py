@@ -407,6 +407,43 @@ def test_gemm_transposed_tiles_for_ragged_token_counts(monkeypatch, M, N, K, mod
     assert rel_err(out_t, out_s) < (2e-3 if mode in ("bf16", "gelu") else 2e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(432, 1536, 512), (432, 4096, 2048), (65, 2048, 256), (864, 2560, 320), (200, 512, 640),
+                                   (1000, 1024, 4096), (512, 768, 1024), (513, 768, 1024), (1500, 512, 576)])
+@pytest.mark.parametrize("mode", ["bf16", "gelu", "f32", "residual", "residual_splitk"])
+def test_gemm_wide_pair_tiles_for_shards(monkeypatch, M, N, K, mode):
+    """Wide pair kernel (cta_group::2, 256 weight rows x up to 512 tokens in two accumulators, K split for the residual
+    epilogue): the context-parallel shard shapes, token counts just above / below one tile (512, 513), a ragged K tail
+    (576 = 9 x 64, 320), every epilogue mode.  Forced on; the standard kernel on the same inputs must agree."""
+    from ltx2_b200 import ops
+    monkeypatch.setenv("LTX2_GEMM_WIDE", "2")
+    a, w = rnd(M, K, seed=95, dtype=torch.bfloat16), rnd(N, K, seed=96, std=K ** -0.5, dtype=torch.bfloat16)
+    bias, x = rnd(N, seed=97), rnd(M, N, seed=98)
+    gate = rnd(3, N, seed=99)
+    cls = (torch.arange(M, device=dev()) % 3).to(torch.int32)
+    acc = a.float() @ w.float().T + bias
+
+    def run():
+        if mode == "bf16":
+            return ops.gemm(a, w, bias).float(), acc, TOL_BF16_OUT
+        if mode == "gelu":
+            return (ops.gemm(a, w, bias, mode=ops.EPI_BF16_GELU).float(),
+                    torch.nn.functional.gelu(acc, approximate="tanh"), TOL_BF16_OUT)
+        if mode == "f32":
+            return ops.gemm(a, w, bias, mode=ops.EPI_F32), acc, TOL_F32_OUT
+        y = x.clone()
+        ops.gemm(a, w, bias, mode=ops.EPI_F32_RESIDUAL, out=y, gate=gate, row_cls=cls, alpha=0.5,
+                 max_splits=8 if mode == "residual_splitk" else 1)
+        return y, x + 0.5 * gate[cls.long()] * acc, TOL_F32_OUT
+
+    out_w, ref, tol = run()
+    assert rel_err(out_w, ref) < tol
+    monkeypatch.setenv("LTX2_GEMM_WIDE", "0")
+    monkeypatch.setenv("LTX2_GEMM_2CTA", "0")
+    monkeypatch.setenv("LTX2_GEMM_T", "0")
+    out_s, _, _ = run()
+    assert rel_err(out_w, out_s) < (2e-3 if mode in ("bf16", "gelu") else 2e-5)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 1024, 4096), (432, 4096, 4096), (432, 4096, 16384), (100, 512, 640)])
 def test_gemm_residual_split_k_small_m(M, N, K):
     """Small-M residual GEMMs (context-parallel ranks) split K across CTAs and accumulate with vector reductions."""

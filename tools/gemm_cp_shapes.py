@@ -41,8 +41,13 @@ for M in (432, 864, 1728, 3456):
         ms_std = timed(fn)
         os.environ.pop("LTX2_GEMM_T")
         os.environ.pop("LTX2_GEMM_2CTA")
+        os.environ["LTX2_GEMM_WIDE"] = "0"
+        ms_nowide = timed(fn)
+        os.environ["LTX2_GEMM_WIDE"] = "2"
+        ms_wide = timed(fn)
+        os.environ.pop("LTX2_GEMM_WIDE")
         ms_auto = timed(fn)
         o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         ms_cublas = timed(lambda: torch.matmul(a, w.t(), out=o2))
-        print(f"M={M:5d} N={N:5d} K={K:5d} {'residual' if resid else 'bf16    '}  standard {ms_std * 1e3:7.1f} us   "
+        print(f"M={M:5d} N={N:5d} K={K:5d} {'residual' if resid else 'bf16    '}  standard {ms_std * 1e3:7.1f} us   T/pair {ms_nowide * 1e3:7.1f} us   wide {ms_wide * 1e3:7.1f} us   "
               f"auto {ms_auto * 1e3:7.1f} us ({fl / ms_auto / 1e9:6.0f} TF/s)   cuBLAS {ms_cublas * 1e3:7.1f} us", flush=True)
