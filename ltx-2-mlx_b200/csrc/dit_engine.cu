@@ -1427,7 +1427,10 @@ extern "C" int ltx2_dit_forward(LtxDit* e, const LtxModalityView* video, const L
     const float cas = isnan(e->cross_attn_scale[l]) ? 1.0f : e->cross_attn_scale[l];
     // split-K reductions are unordered fp32 atomics: only the sharded video stream uses them; the audio stream is
     // REPLICATED across ranks and must stay bit-identical on all of them
-    const int split_v = e->cp.world > 1 ? e->cp.split_k : 1;
+    // LTX2_SHARD_SPLIT_K (diagnostics): the split-K cap of a context-parallel rank on a single GPU, so that a one-GPU
+    // run on a shard-sized token grid launches exactly a rank's GEMM kernels (tools/profile_step.py --grid 1 18 24)
+    static const int shard_split = getenv("LTX2_SHARD_SPLIT_K") ? atoi(getenv("LTX2_SHARD_SPLIT_K")) : 1;
+    const int split_v = e->cp.world > 1 ? e->cp.split_k : (shard_split > 1 ? shard_split : 1);
     g_split_k = split_v;
     LTX2_PROPAGATE(run_self_and_text(e, vb, w.v, l, (sk.video_self_attn & bit) != 0, cas, st));
     if (has_audio) {

@@ -595,7 +595,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tma_prefetch_desc(&tmap_x64);
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&peer_full[s], 1);
+      // CTA 0: own TMA bytes (one expect_tx arrival) AND the relay of CTA 1 -- one barrier, one wait per K block
+      mbar_init(&peer_full[s], 2);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -626,9 +627,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
-          mbar_expect_tx(&full_bar[stage], bytes);
-          tma_load_2d(smem_a + stage * kHalfBytes, &tmap_w, &full_bar[stage], kb * BK, w0);
-          tma_load_2d(smem_b + stage * kHalfBytes, last ? &tmap_x64 : &tmap_x128, &full_bar[stage], kb * BK, t0);
+          // CTA 0's bytes complete on the barrier the MMA issuer waits on (it also counts CTA 1's relay)
+          uint64_t* fb = rank == 0 ? &peer_full[stage] : &full_bar[stage];
+          mbar_expect_tx(fb, bytes);
+          tma_load_2d(smem_a + stage * kHalfBytes, &tmap_w, fb, kb * BK, w0);
+          tma_load_2d(smem_b + stage * kHalfBytes, last ? &tmap_x64 : &tmap_x128, fb, kb * BK, t0);
         }
         if (++stage == kStages2) { stage = 0; phase ^= 1; }
       }
@@ -653,17 +656,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    bool ready = false;                               // the stage about to be consumed was complete when probed
     for (int it = 0; sched_tile(sched, it, wi, ti, nt); ++it) {
       const uint32_t idesc = umma_idesc_bf16(256, static_cast<uint32_t>(nt));
       mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256;
       for (int kb = 0; kb < num_kb; ++kb) {
-        // plain (CTA-scope) waits: the operands are read by the tensor core through the async proxy, never by this
-        // thread; an acquire at cluster scope compiles to an L1 invalidation (CCTL.IVALL) per K block
-        mbar_wait(&full_bar[stage], phase);
-        mbar_wait(&peer_full[stage], phase);
+        // ONE plain (CTA-scope) wait per K block: `peer_full` completes when this CTA's TMA bytes have landed and CTA 1's
+        // relay has arrived.  (The operands are read by the tensor core through the async proxy, never by this thread; an
+        // acquire at cluster scope compiles to an L1 invalidation per wait.)  The barrier round trip costs ~100 clocks
+        // even when the phase is complete, so the NEXT stage is probed before this stage's instructions are issued.
+        if (!ready) mbar_wait(&peer_full[stage], phase);
         tc_fence_after();
+        const int nstage = stage + 1 == kStages2 ? 0 : stage + 1;
+        const uint32_t nphase = stage + 1 == kStages2 ? phase ^ 1 : phase;
+        ready = mbar_test_wait(&peer_full[nstage], nphase);
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kHalfBytes));
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * kHalfBytes));
         if (leader) {
@@ -672,7 +680,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           umma2_commit_both(&empty_bar[stage]);
         }
         __syncwarp();
-        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        stage = nstage;
+        phase = nphase;
       }
       if (leader) umma2_commit_both(&acc_full[acc]);
       __syncwarp();
