@@ -161,6 +161,9 @@ int ltx2_dit_set_cross_attn_scale(LtxDit* dit, int32_t block, float scale /* NaN
  * this library has launched since load. */
 int ltx2_dit_set_profile(LtxDit* dit, int32_t on);
 int ltx2_dit_profile_read(LtxDit* dit, double* ms_out, double* flops_out, int64_t* launches_out, int32_t n_classes);
+/* Profiled launch i (launch order) of the last forward: kernel time, algorithmic FLOPs, class (0 GEMM, 1 attention,
+ * 2 FP8 GEMM); LTX2_ERR_INVALID past the last record. */
+int ltx2_dit_profile_launch(LtxDit* dit, int32_t i, double* ms_out, double* flops_out, int32_t* class_out);
 int64_t ltx2_launch_count(void);
 
 /* Context parallelism over the token axis (no reference counterpart -- the reference is

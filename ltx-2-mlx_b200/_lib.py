@@ -79,6 +79,7 @@ SIGNATURES = {
     "ltx2_dit_set_cross_attn_scale": (_I32, [_P, _I32, _F]),
     "ltx2_dit_set_profile": (_I32, [_P, _I32]),
     "ltx2_dit_profile_read": (_I32, [_P, _P, _P, _P, _I32]),
+    "ltx2_dit_profile_launch": (_I32, [_P, _I32, _P, _P, _P]),
     "ltx2_launch_count": (_I64, []),
     "ltx2_dit_cp_init": (_I32, [_P, _I32, _I32, _I32, _I32, _I32, _P]),
     "ltx2_dit_cp_connect": (_I32, [_P, _P]),

@@ -1544,6 +1544,22 @@ extern "C" int ltx2_dit_profile_read(LtxDit* e, double* ms_out, double* flops_ou
   return LTX2_OK;
 }
 
+// Profiled launch i of the last forward (launch order): kernel time in ms, algorithmic FLOPs, class (0 = GEMM,
+// 1 = attention, 2 = FP8 GEMM).  LTX2_ERR_INVALID when i is past the last record.
+extern "C" int ltx2_dit_profile_launch(LtxDit* e, int32_t i, double* ms_out, double* flops_out, int32_t* class_out) {
+  LTX2_REQUIRE(e && ms_out && flops_out && class_out, "dit_profile_launch: null argument");
+  LTX2_REQUIRE(i >= 0 && i < static_cast<int32_t>(e->prof.recs.size()), "dit_profile_launch: launch %d of %d", i,
+               static_cast<int>(e->prof.recs.size()));
+  LTX2_CUDA_CHECK(cudaDeviceSynchronize());
+  const auto& r = e->prof.recs[i];
+  float ms = 0.f;
+  LTX2_CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof.events[r.e0], e->prof.events[r.e0 + 1]));
+  *ms_out = ms;
+  *flops_out = r.work;
+  *class_out = r.cat;
+  return LTX2_OK;
+}
+
 extern "C" int64_t ltx2_launch_count(void) { return ltx2::launch_count(); }
 
 // =====================================================================================
