@@ -660,7 +660,8 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
         # local token count --, no split-K) every output element is computed by the same instruction sequence on one GPU and on P GPUs, so the
         # sharded forward must be BIT-IDENTICAL -- this checks the sharding, the head exchange and the context broadcast.
         # (2) DEFAULT: shard-shaped GEMM kernels, makespan-optimal attention items and split-K change fp32 summation
-        # orders; the bound is rel_l2 2e-3, a tenth of the engine-vs-oracle tolerance.
+        # orders; the bound is rel_l2 2e-3, a tenth of the engine-vs-oracle tolerance (FP8 linears: 1e-2 -- a last-bit
+        # difference before the per-token E4M3 quantisation moves a whole quantisation step after it).
         canon = {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "0"}
         v, a = b.modalities(5, b.lat_d, alat)
 
@@ -697,8 +698,8 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
                      "what": f"x0 of the full {c['layers']}-block model: context-parallel forward over {world} ranks vs "
                              f"the un-sharded forward of the same model, max over ranks.  pinned kernels (standard GEMM "
                              f"tiles, split-KV attention items only, split-K off): must be bit-exact; default kernel choice "
-                             f"(shard-shaped GEMMs, split-K): rel_l2 <= 2e-3",
-                     "ok": bool(float(t[0]) == 0.0 and float(t[3]) <= 2e-3)}
+                             f"(shard-shaped GEMMs, split-K): rel_l2 <= {1e-2 if fp8 else 2e-3:g}",
+                     "ok": bool(float(t[0]) == 0.0 and float(t[3]) <= (1e-2 if fp8 else 2e-3))}
 
     def run_steps(n, first=0):
         latent, al = b.lat_d.clone(), (b.alat_d.clone() if c["av"] else None)
@@ -887,7 +888,7 @@ def run_ours(args, c):
 
     # ---- the FP8 linear path on the same configuration, reported BESIDE the bf16 line (never instead of it) ----
     fp8_line = None
-    if args.fp8 and world == 1:
+    if args.fp8 and (world == 1 or args.parallel == "cp"):
         fp8_line = run_dit(args, c, dev, rank, local_rank, world, args.config, fp8=True)
 
     # ---- second half of the metric: VAE decode frames/s ----
@@ -948,7 +949,7 @@ def main():
                     help="blocks of the benched model checked against the CPU oracle (48 = the full model, ~1 min)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity legs")
     ap.add_argument("--fp8", action=argparse.BooleanOptionalAction, default=True,
-                    help="N = 1: also time the FP8 linear path of the same configuration (`fp8` key)")
+                    help="also time the FP8 linear path of the same configuration (`fp8` key; at N > 1 under context parallelism)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
     ap.add_argument("--vae-only", action="store_true", help="only the VAE decode leg (prints its object as the line)")
