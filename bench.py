@@ -662,7 +662,9 @@ def run_dit(args, c, dev, rank, local_rank, world, name, fp8=False):
         # (2) DEFAULT: shard-shaped GEMM kernels, makespan-optimal attention items and split-K change fp32 summation
         # orders; the bound is rel_l2 2e-3, a tenth of the engine-vs-oracle tolerance (FP8 linears: 1e-2 -- a last-bit
         # difference before the per-token E4M3 quantisation moves a whole quantisation step after it).
-        canon = {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "0"}
+        # LTX2_ATTN_SPLIT=0: the SM-pair attention kernel (>= 8192 tokens) with whole items per cluster -- its stream-K
+        # cut points depend on the number of (batch, head) slices, i.e. on the rank count
+        canon = {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "0", "LTX2_ATTN_SPLIT": "0"}
         v, a = b.modalities(5, b.lat_d, alat)
 
         def fwd(env=None):
