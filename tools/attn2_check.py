@@ -1,9 +1,22 @@
-import os, sys, math, time
-sys.path.insert(0, "/root/repo")
-import torch
-from ltx2_b200 import ops
+#!/usr/bin/env python
+"""SM-pair attention kernel (attention_2cta_sm100.cu) against the one-SM two-stream kernel: timing with CUDA events and a
+check against a torch fp32 reference on two heads, for the 19B shapes, the context-parallel head shards and the
+N = 12288 configuration; then the pipeline timeline of cluster 0 (ltx2_attention_vrows_trace).  Diagnostics for kernel
+tuning, not a bench value.  Rows: 2cta = the dispatcher's schedule, -ns = whole items per SM pair, -fs = stream-K forced,
+-p2 / -p4 = polynomial share of the exponentials, pair = the one-SM kernel."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from ltx2_b200 import ops  # noqa: E402
+
 dev = torch.device("cuda:0")
 Dh = 128
+
+
 def case(Tq, Tk, heads, B=1, iters=20, check_heads=2, gate=False):
     g = torch.Generator(device=dev).manual_seed(1)
     q = torch.randn(B, heads, Tq, Dh, device=dev, generator=g).to(torch.bfloat16)
@@ -23,7 +36,6 @@ def case(Tq, Tk, heads, B=1, iters=20, check_heads=2, gate=False):
         os.environ.pop("LTX2_ATTN_SPLIT", None)
         os.environ.pop("LTX2_ATTN_DBG", None)
         os.environ.update(env)
-        print(f"   .. {name}", flush=True)
         out = ops.attention_vrows(q, k, v_rows, heads, Dh)
         torch.cuda.synchronize()
         err = float((out[:, :, :check_heads * Dh].float() - ref).norm() / ref.norm())
@@ -40,6 +52,8 @@ def case(Tq, Tk, heads, B=1, iters=20, check_heads=2, gate=False):
         print(f"Tq={Tq} Tk={Tk} H={heads} B={B} {name:8s} {ms*1e3:8.1f} us {flops/ms/1e9:7.1f} TF/s rel.err {err:.2e} finite {bool(torch.isfinite(out).all())}", flush=True)
     d = float((res["2cta"].float() - res["pair"].float()).abs().max())
     print(f"   max |2cta - pair| = {d:.3e}", flush=True)
+
+
 for shape in [(384, 1000, 2), (3456, 3456, 4), (3456, 3456, 16), (3456, 3456, 32), (3456, 1024, 32), (12288, 12288, 8), (6144, 6144, 8)]:
     case(*shape)
 case(640, 333, 4, B=2)
