@@ -196,6 +196,27 @@ def test_attention_sm_pair_kernel_production_shapes(monkeypatch, H, Tq, Tk):
     assert rel_err(outs["0"].float(), outs["1"].float()) < 5e-3
 
 
+def test_attention_long_sequences_dispatch_to_the_sm_pair_kernel(monkeypatch):
+    """From 8192 queries and keys on, head_dim-128 attention takes the SM-pair kernel by itself (the N = 12288
+    configuration of BASELINE.json); checked against torch on one head and against the one-SM kernel on all."""
+    from ltx2_b200 import ops
+    monkeypatch.delenv("LTX2_ATTN_2CTA", raising=False)
+    monkeypatch.delenv("LTX2_ATTN_SPLIT", raising=False)
+    B, H, T, Dh = 1, 3, 8192 + 128, 128
+    q = rnd(B, H, T, Dh, seed=41, dtype=torch.bfloat16)
+    k = rnd(B, H, T, Dh, seed=42, dtype=torch.bfloat16)
+    qkv = rnd(B, T, 3 * H * Dh, seed=43, dtype=torch.bfloat16)
+    v_rows = qkv[:, :, 2 * H * Dh:]
+    v = v_rows.reshape(B, T, H, Dh).permute(0, 2, 1, 3)
+    out = ops.attention_vrows(q, k, v_rows, H, Dh)
+    ref, _ = _attn_ref(q[:, :1], k[:, :1], v[:, :1])
+    assert rel_err(out[:, :, :Dh].float(), ref) < 1.2e-2
+    monkeypatch.setenv("LTX2_ATTN_2CTA", "0")
+    out1 = ops.attention_vrows(q, k, v_rows, H, Dh)
+    assert not torch.equal(out, out1)                     # a different kernel did run
+    assert rel_err(out.float(), out1.float()) < 5e-3
+
+
 def test_attention_single_tile_kernel_still_matches(monkeypatch):
     """LTX2_ATTN_KERNEL=single keeps the one-tile kernel (the head_dim 64 path) reachable at head_dim 128 for A/B runs."""
     from ltx2_b200 import ops
