@@ -429,6 +429,11 @@ int ltx2_attention_plan(int32_t Tq, int32_t BH, int32_t* pairs_per_slice, int32_
  *                           whether the (work item, key block) space is cut into equal ranges per cluster whose partial
  *                           results are merged (split = 1, stream-K) or whole items go round-robin (split = 0). */
 int ltx2_attention_sm_pair_plan(int32_t Tq, int32_t Tk, int32_t BH, int32_t* n_clusters, int32_t* split);
+/*   ltx2_attention_sm_pair_segments: the segments one cluster of that grid walks, 7 ints each {item, first key block,
+ *                           end key block, part, parts, scratch slot, scratch slot of part 0 (-1: whole item)};
+ *                           returns the segment count (>= 0) or a negative status. */
+int ltx2_attention_sm_pair_segments(int32_t Tq, int32_t Tk, int32_t BH, int32_t cluster, int32_t* out7,
+                                    int32_t max_segments);
 
 /* The elementwise tail of one denoising step of the reference's host loops (pipelines/distilled.py:243-251,
  * pipelines/one_stage.py:284-320), fused into one pass over fp32 [M, C] tensors:

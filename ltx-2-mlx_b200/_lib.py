@@ -135,6 +135,7 @@ SIGNATURES = {
     "ltx2_gemm_plan": (_I32, [_I32] * 5 + [_P]),
     "ltx2_attention_plan": (_I32, [_I32, _I32, _P, _P]),
     "ltx2_attention_sm_pair_plan": (_I32, [_I32, _I32, _I32, _P, _P]),
+    "ltx2_attention_sm_pair_segments": (_I32, [_I32, _I32, _I32, _I32, _P, _I32]),
     "ltx2_denoise_update": (_I32, [_P, _P, _P, _F, _P, _P, _F, _F, _P, _P, _I32, _I32, _P]),
     "ltx2_silu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),
     "ltx2_gelu_mul": (_I32, [_P, _P, _P, _I64, _I32, _P]),

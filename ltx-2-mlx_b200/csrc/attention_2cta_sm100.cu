@@ -97,14 +97,14 @@ struct Walker {
   long long G, g, g0, g1;
   int C, c, nblk, n_items, it;
   bool split;
-  __device__ Walker(const Sched2& s, int cluster)
+  __host__ __device__ Walker(const Sched2& s, int cluster)
       : G(static_cast<long long>(s.n_items) * s.nblk), C(s.C), c(cluster), nblk(s.nblk), n_items(s.n_items),
         it(cluster), split(s.split != 0) {
     g0 = G * c / C;
     g1 = G * (c + 1) / C;
     g = g0;
   }
-  __device__ bool next(Seg& sg) {
+  __host__ __device__ bool next(Seg& sg) {
     if (!split) {
       if (it >= n_items) return false;
       sg.item = it;
@@ -743,6 +743,30 @@ void attention_2cta_plan(int Tq, int Tk, int BH, int* n_clusters, int* split) {
   if (sp) C = Cs;
   *n_clusters = C;
   *split = sp ? 1 : 0;
+}
+
+int attention_2cta_segments(int Tq, int Tk, int BH, int cluster, int* out7, int max_segments) {
+  // the walk of one cluster through the work decomposition, exactly as the kernel does it (pure integers)
+  Sched2 sd;
+  const int n_q = (Tq + BQ - 1) / BQ;
+  sd.n_cl = (n_q + 1) / 2;
+  sd.n_items = BH * sd.n_cl;
+  sd.nblk = (Tk + BK2 - 1) / BK2;
+  attention_2cta_plan(Tq, Tk, BH, &sd.C, &sd.split);
+  if (cluster < 0 || cluster >= sd.C) return -1;
+  Walker w(sd, cluster);
+  Seg sg;
+  int n = 0;
+  while (w.next(sg)) {
+    if (n < max_segments) {
+      int* o = out7 + 7 * n;
+      o[0] = sg.item; o[1] = sg.kb0; o[2] = sg.kb1; o[3] = sg.part; o[4] = sg.parts;
+      o[5] = sg.parts > 1 ? sg.slot : -1;
+      o[6] = sg.parts > 1 ? sg.slot0 : -1;
+    }
+    ++n;
+  }
+  return n;
 }
 
 int attention_2cta_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,

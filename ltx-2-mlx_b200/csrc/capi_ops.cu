@@ -209,6 +209,20 @@ int ltx2_attention_sm_pair_plan(int32_t Tq, int32_t Tk, int32_t BH, int32_t* n_c
   return LTX2_OK;
 }
 
+int ltx2_attention_sm_pair_segments(int32_t Tq, int32_t Tk, int32_t BH, int32_t cluster, int32_t* out7,
+                                    int32_t max_segments) {
+  if (Tq <= 0 || Tk <= 0 || BH <= 0 || out7 == nullptr || max_segments < 0) {
+    set_error("attention_sm_pair_segments: bad argument");
+    return LTX2_ERR_INVALID;
+  }
+  const int n = attention_2cta_segments(Tq, Tk, BH, cluster, out7, max_segments);
+  if (n < 0) {
+    set_error("attention_sm_pair_segments: cluster %d out of range", cluster);
+    return LTX2_ERR_INVALID;
+  }
+  return n;
+}
+
 int ltx2_denoise_update(const float* sample, const float* cond_x0, const float* uncond_x0, float cfg_scale,
                         const float* denoise_mask, const float* clean_latent, float sigma, float sigma_next, float* out,
                         float* denoised_out, int32_t M, int32_t C, void* stream) {

@@ -111,6 +111,9 @@ bool attention_2cta_applies(const AttnV& v, int Tq, int Tk, int Dh);
 // the pair kernel's work decomposition (pure host logic): clusters in the grid and whether (item, key block) ranges are
 // split across clusters (stream-K) or whole items go round-robin
 void attention_2cta_plan(int Tq, int Tk, int BH, int* n_clusters, int* split);
+// the segments cluster `cluster` walks, 7 ints each: item, first key block, end key block, part, parts, scratch slot of
+// the segment, scratch slot of part 0 (-1 for whole items); returns the segment count, -1 for a bad cluster index
+int attention_2cta_segments(int Tq, int Tk, int BH, int cluster, int* out7, int max_segments);
 int attention_2cta_bf16(const void* q, const void* k, const AttnV& v, void* out, int B, int H, int Tq, int Tk,
                         float scale, const float* gate_logits, float* lse_out, cudaStream_t stream, long long* trace,
                         const AttnOutScatter& sc);

@@ -120,6 +120,62 @@ def test_sm_pair_attention_schedule():
             assert clusters <= n_items
 
 
+def sm_pair_segments(Tq, Tk, BH, cluster):
+    from ltx2_b200._lib import lib
+    buf = (C.c_int32 * (7 * 64))()
+    n = lib().ltx2_attention_sm_pair_segments(Tq, Tk, BH, cluster, buf, 64)
+    assert 0 <= n <= 64
+    return [tuple(buf[7 * i:7 * i + 7]) for i in range(n)]
+
+
+@pytest.mark.parametrize("force_split", [None, "1"])
+def test_sm_pair_attention_segments_cover_every_key_block_once(monkeypatch, force_split):
+    """The device-side walk of the stream-K decomposition (shared host/device code): over all clusters every
+    (item, key block) is visited exactly once, the parts of a split item are numbered 0..parts-1 in key order, every
+    part knows the scratch slot of part 0, and no two partial segments share a scratch slot."""
+    if force_split is None:
+        monkeypatch.delenv("LTX2_ATTN_SPLIT", raising=False)
+    else:
+        monkeypatch.setenv("LTX2_ATTN_SPLIT", force_split)
+    rng = random.Random(3)
+    shapes = [(3456, 3456, 32), (3456, 3456, 4), (3456, 1024, 32), (12288, 12288, 8), (300, 200, 3), (384, 1000, 2)]
+    shapes += [(rng.randint(129, 6000), rng.randint(1, 6000), rng.randint(1, 40)) for _ in range(25)]
+    for Tq, Tk, BH in shapes:
+        clusters, split = sm_pair_plan(Tq, Tk, BH)
+        n_items = BH * (((Tq + 127) // 128 + 1) // 2)
+        nblk = (Tk + 127) // 128
+        seen = {}
+        slots = set()
+        parts_of = {}
+        for c in range(clusters):
+            for item, kb0, kb1, part, parts, slot, slot0 in sm_pair_segments(Tq, Tk, BH, c):
+                assert 0 <= item < n_items and 0 <= kb0 < kb1 <= nblk
+                for kb in range(kb0, kb1):
+                    assert (item, kb) not in seen, (Tq, Tk, BH, item, kb)
+                    seen[(item, kb)] = c
+                if parts == 1:
+                    assert (kb0, kb1) == (0, nblk) and slot == -1
+                else:
+                    assert split and 0 <= part < parts <= 8
+                    assert slot not in slots
+                    slots.add(slot)
+                    parts_of.setdefault(item, []).append((part, kb0, kb1, slot, slot0, c))
+        assert len(seen) == n_items * nblk, (Tq, Tk, BH)
+        for item, ps in parts_of.items():
+            ps.sort()
+            assert [p[0] for p in ps] == list(range(len(ps))) and len(ps) == max(2, len(ps))
+            assert ps[0][1] == 0 and ps[-1][2] == nblk and all(a[2] == b[1] for a, b in zip(ps, ps[1:]))
+            assert all(p[4] == ps[0][3] for p in ps)                       # everyone knows part 0's slot
+            assert all(p[3] == 2 * p[5] for p in ps[1:])                   # parts >= 1 start their cluster's range
+        assert lib_rejects_cluster(Tq, Tk, BH, clusters)
+
+
+def lib_rejects_cluster(Tq, Tk, BH, cluster):
+    from ltx2_b200._lib import lib
+    buf = (C.c_int32 * 7)()
+    return lib().ltx2_attention_sm_pair_segments(Tq, Tk, BH, cluster, buf, 1) < 0
+
+
 def test_planners_reject_bad_arguments():
     from ltx2_b200._lib import lib
     o = (C.c_int32 * 6)()
