@@ -25,7 +25,8 @@ D = c["heads"] * c["head_dim"]
 cfg = synthetic.DitConfig(num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], num_layers=L,
                           cross_attention_dim=D, caption_channels=c["caption"])
 for fp8 in ((True,) if os.environ.get("PROBE_FP8_ONLY") else (True, False)):
-    for grid in (((432 * world // (18 * 24), 18, 24),) if os.environ.get("PROBE_FP8_ONLY") else ((432 * world // (18 * 24), 18, 24), (1728 * world // (18 * 24), 18, 24))):
+    per_rank = int(os.environ.get("PROBE_ROWS_PER_RANK", "432"))
+    for grid in (((per_rank * world // (18 * 24), 18, 24),) if os.environ.get("PROBE_FP8_ONLY") else ((432 * world // (18 * 24), 18, 24), (1728 * world // (18 * 24), 18, 24))):
         F, H, W = grid
         N, S = F * H * W, c["S"]
         models = []
@@ -42,7 +43,7 @@ for fp8 in ((True,) if os.environ.get("PROBE_FP8_ONLY") else (True, False)):
         pos = synthetic.video_positions(1, F, H, W).to(dev)
         sig = torch.tensor([0.9], device=dev)
         res = []
-        for lim in range(1, L + 1):
+        for lim in range(1, L + 1, int(os.environ.get("PROBE_LAYER_STEP", "1"))):
             outs = []
             for m in (single, sharded):
                 m.set_layer_limit(lim)
