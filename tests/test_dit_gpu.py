@@ -266,3 +266,34 @@ def test_load_transformer_weights_from_safetensors_file(tmp_path):
     lat, ctx, pos = video_inputs(cfg, 1, 2, 3, 4, 24, 160, 64)
     mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.5]), positions=pos)
     assert torch.equal(m2(mod), m3(mod))
+
+
+def test_profile_records_per_launch_and_per_class():
+    """ltx2_dit_set_profile brackets every GEMM / attention launch with events; ltx2_dit_profile_launch returns them one
+    by one (launch order) and their sums are what ltx2_dit_profile_read reports per class."""
+    import ctypes as C
+    from ltx2_b200 import _lib, synthetic
+    from ltx2_b200.transformer import Modality
+
+    cfg = synthetic.DitConfig(num_attention_heads=4, attention_head_dim=128, in_channels=32, out_channels=32, num_layers=2,
+                              cross_attention_dim=512, caption_channels=64)
+    m, _ = build(cfg, seed=5)
+    lat, ctx, pos = video_inputs(cfg, 1, 2, 4, 6, 24, seed=50, ctx_dim=64)
+    mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.7]), positions=pos)
+    L = _lib.lib()
+    _lib.check(L.ltx2_dit_set_profile(m._h, 1))
+    m(mod)
+    ms, fl, ln = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
+    _lib.check(L.ltx2_dit_profile_read(m._h, ms, fl, ln, 3))
+    one_ms, one_fl, one_cls = C.c_double(), C.c_double(), C.c_int32()
+    sums, counts, i = [0.0, 0.0, 0.0], [0, 0, 0], 0
+    while L.ltx2_dit_profile_launch(m._h, i, C.byref(one_ms), C.byref(one_fl), C.byref(one_cls)) == 0:
+        assert one_ms.value > 0 and one_fl.value > 0 and 0 <= one_cls.value < 3
+        sums[one_cls.value] += one_ms.value
+        counts[one_cls.value] += 1
+        i += 1
+    _lib.check(L.ltx2_dit_set_profile(m._h, 0))
+    assert i == sum(ln) and counts == list(ln)
+    assert counts[1] == 2 * cfg.num_layers                 # self + text attention per block
+    for c in range(3):
+        assert abs(sums[c] - ms[c]) <= 1e-6 * max(1.0, ms[c])
