@@ -11,7 +11,7 @@ D = c["heads"] * c["head_dim"]
 cfg = synthetic.DitConfig(num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], num_layers=L, cross_attention_dim=D, caption_channels=c["caption"])
 m = LTXModel(model_type=LTXModelType.VideoOnly, num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], num_layers=L, cross_attention_dim=D, caption_channels=c["caption"], device=dev, fp8_linear=True)
 m.load_weights(iter_engine_weights(synthetic.iter_dit_weights(cfg, seed=0, device=dev, dtype=torch.bfloat16), False))
-F, H, W = 9, 16, 24
+F, H, W = (9, 16, 24) if os.environ.get("DET_TOKENS", "3456") == "3456" else (1, 18, 24)
 N, S = F*H*W, c["S"]
 lat = synthetic.latents((1, N, 128), seed=42).to(dev)
 ctx = synthetic.latents((1, S, c["caption"]), seed=7, std=0.1).to(torch.bfloat16).to(dev)
@@ -20,7 +20,7 @@ x0 = X0Model(m)
 for env in ({}, {"LTX2_GEMM_T": "0", "LTX2_GEMM_2CTA": "0", "LTX2_ATTN_PAIRS": "0"}):
     os.environ.update(env)
     outs = []
-    for i in range(6):
+    for i in range(int(os.environ.get("DET_RUNS", "6"))):
         m.reset_context_cache()
         mod = Modality(latent=lat, context=ctx, context_mask=None, timesteps=torch.tensor([0.9], device=dev), positions=pos)
         outs.append(x0(mod).clone())
