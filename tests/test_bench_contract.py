@@ -51,3 +51,27 @@ def test_committed_bench_line_has_the_contract_keys(path):
 
 def test_there_are_committed_bench_lines():
     assert LINES, "profiles/bench_r1c_*.json missing"
+
+
+def test_round2_scaling_beats_round1_at_every_gpu_count():
+    """The committed round-2 lines against round 1's SCALE numbers (11.25 / 19.04 / 30.54 / 46.17 steps/s,
+    efficiency 0.85 / 0.68 / 0.51 at 2 / 4 / 8 GPUs; VAE 1590 / 2510 / 2458 / 2512 frames/s): every point is higher,
+    the multi-GPU lines were timed over >= 100 steps, and 8 GPUs decode 65 frames more than 3.5x as fast as one."""
+    lines = {}
+    for n in (1, 2, 4, 8):
+        p = os.path.join(ROOT, "profiles", f"bench_r2_n{n}.json")
+        if not os.path.exists(p):
+            pytest.skip(f"{p} missing")
+        lines[n] = json.loads(open(p).read().strip().splitlines()[-1])
+    r1 = {1: 11.25, 2: 19.04, 4: 30.54, 8: 46.17}
+    r1_eff = {2: 0.85, 4: 0.68, 8: 0.51}
+    r1_vae = {1: 1590.0, 2: 2510.0, 4: 2458.0, 8: 2512.0}
+    for n, d in lines.items():
+        assert d["n_gpus"] == n and d["value"] > r1[n]
+        assert d["vae_frames_per_s"] > r1_vae[n]
+        if n > 1:
+            assert d["value"] / (n * lines[1]["value"]) > r1_eff[n]
+            assert d["long_run"]["steps"] >= 100 and abs(d["long_run"]["value"] / d["value"] - 1) < 0.05
+    assert lines[8]["vae_frames_per_s"] > 3.5 * lines[1]["vae_frames_per_s"]
+    names = {c["config"]["name"] for c in lines[8].get("configs", [])}
+    assert {"22b-av", "dev-cfg"} <= names
