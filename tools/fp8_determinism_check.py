@@ -1,10 +1,17 @@
-import os, sys
-sys.path.insert(0, "/root/repo")
-import torch
-import bench
-from ltx2_b200 import synthetic
-from ltx2_b200.loader import iter_engine_weights
-from ltx2_b200.transformer import LTXModel, LTXModelType, Modality, X0Model
+#!/usr/bin/env python
+"""Run-to-run determinism of the 48-block FP8 forward on one GPU (DET_TOKENS=3456 | 432, DET_RUNS=n), with the default
+and with the pinned kernel choice: every run must be bit-identical to the first.  Diagnostics."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from ltx2_b200 import synthetic  # noqa: E402
+from ltx2_b200.loader import iter_engine_weights  # noqa: E402
+from ltx2_b200.transformer import LTXModel, LTXModelType, Modality, X0Model  # noqa: E402
+
 dev = torch.device("cuda:0")
 c = dict(bench.CONFIGS["19b"]); L = 48
 D = c["heads"] * c["head_dim"]

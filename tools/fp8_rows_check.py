@@ -1,6 +1,14 @@
-import sys, torch
-sys.path.insert(0, "/root/repo")
-from ltx2_b200 import ops
+#!/usr/bin/env python
+"""FP8 GEMM (ltx2_gemm_e4m3): the first M rows of a 3456-row launch against a launch on those M rows alone, for the
+context-parallel shard sizes (different tile widths are chosen) -- must be bit-identical.  Diagnostics."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from ltx2_b200 import ops  # noqa: E402
+
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 for K in (4096, 16384):
